@@ -1,0 +1,76 @@
+// Shared device helpers and parameter blocks for the DiffLinker hot-path kernels (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace dl {
+
+constexpr int H = 128;         // hidden_nf (configs/*.yml `nf: 128`), compile-time specialisation
+constexpr int MAX_DIN = 32;    // F + C + 1 upper bound
+constexpr int MAX_XHD = 16;    // 3 + F upper bound (threads per node in k_finish)
+
+// silu(x) = x * sigmoid(x) (nn.SiLU, reference src/lightning.py:23-27). ex2.approx + fast divide:
+// ~2 ulp each, far inside the 1e-4 end-to-end tolerance (DESIGN.md "numerics").
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// Packed fp32 weights of one GCL (src/egnn.py:19-30). *_t = k-major ("transposed") [K][128].
+struct GclW {
+  const float* W1a_t;  // [128][128]  edge_mlp.0.weight[:, 0:H]^T     (h_row part)
+  const float* W1b_t;  // [128][128]  edge_mlp.0.weight[:, H:2H]^T    (h_col part)
+  const float* b1;     // [128]
+  const float* wd;     // [128]       edge_mlp.0.weight[:, 2H]        (block distance column)
+  const float* w0;     // [128]       edge_mlp.0.weight[:, 2H+1]      (input distance column)
+  const float* W2_t;   // [128][128]  edge_mlp.2.weight^T
+  const float* b2;     // [128]
+  const float* W3_t;   // [256][128]  node_mlp.0.weight^T  (rows 0..127: h part, 128..255: agg part)
+  const float* b3;     // [128]
+  const float* W4_t;   // [128][128]  node_mlp.2.weight^T
+  const float* b4;     // [128]
+  const void* W2_tc;   // fp16 hi/lo UMMA-canonical tiles of edge_mlp.2.weight (tcgen05 path)
+};
+
+// Packed weights of one EquivariantUpdate (src/egnn.py:90-97).
+struct EqW {
+  const float* W1a_t;
+  const float* W1b_t;
+  const float* b1;
+  const float* wd;
+  const float* w0;
+  const float* W2_t;
+  const float* b2;
+  const float* w5;     // [128] coord_mlp.4.weight (no bias)
+  const void* W2_tc;
+};
+
+// First-layer projection of an edge MLP applied per node: A = h W1a^T + b1, B = h W1b^T.
+struct ProjW {
+  const float* W1a_t;
+  const float* W1b_t;
+  const float* b1;
+};
+
+// Per-(B,N) work plan, built once per mask set by k_plan_* (masks are constant over the T steps).
+struct Plan {
+  const int* rowidx;   // [B][N] live rows (any non-zero edge weight), ascending
+  const int* colidx;   // [B][N] live columns
+  const int* xrowidx;  // [B][N] live rows that also have linker_mask != 0 (coordinate update rows)
+  const int* nr;       // [B]
+  const int* nc;       // [B]
+  const int* nxr;      // [B]
+  const int4* items;   // GCL work items (b, first row slot, row count, 0)
+  const int* n_items;  // [1]
+  const int* xmols;    // molecules with nxr > 0 (coordinate-update work items)
+  const int* n_xmols;  // [1]
+};
+
+struct Geom {
+  int B, N;
+  int F;       // in_node_nf
+  int C;       // context_node_nf
+  int D;       // F + C + condition_time
+  int graph_type;
+  float norm_constant;
+  float normalization_factor;
+};
+
+}  // namespace dl

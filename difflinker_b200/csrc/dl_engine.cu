@@ -1,0 +1,731 @@
+// difflinker_b200 engine: C-ABI (include/difflinker_b200.h), weight packing, workspace, launch sequences,
+// CUDA-graph replay of the reverse-diffusion loop. Kernels live in kernels_simt.cuh / kernels_tc.cuh.
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/difflinker_b200.h"
+#include "kernels_simt.cuh"
+#include "kernels_tc.cuh"
+
+using namespace dl;
+
+static thread_local char g_err[1024] = "";
+static void set_err(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+#define CK(call)                                                                          \
+  do {                                                                                    \
+    cudaError_t _e = (call);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      set_err("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(_e));       \
+      return DL_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+namespace {
+
+struct Workspace {
+  int B = 0, N = 0;
+  float *nm = nullptr, *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *ABg = nullptr, *ABc = nullptr,
+        *agg = nullptr, *z = nullptr;
+  int* cls = nullptr;
+  int *rowidx = nullptr, *colidx = nullptr, *xrowidx = nullptr, *nr = nullptr, *nc = nullptr, *nxr = nullptr,
+      *n_items = nullptr, *xmols = nullptr, *n_xmols = nullptr;
+  int4* items = nullptr;
+  int* tile_ctr = nullptr;
+  void* tc_scratch = nullptr;
+  std::vector<void*> allocs;
+};
+
+struct HostStage {  // device staging for the *_host entry points
+  size_t cap = 0;
+  char* buf = nullptr;
+};
+
+}  // namespace
+
+struct dl_engine {
+  dl_config cfg{};
+  int D = 0;
+  int num_sms = 0;
+  bool finalized = false;
+  std::map<std::string, std::vector<float>> raw;
+  float* wblob = nullptr;      // packed fp32 weights
+  void* wblob_tc = nullptr;    // packed fp16 hi/lo tiles
+  std::vector<GclW> gcl;       // [L*S]
+  std::vector<EqW> eq;         // [L]
+  const float *We_t = nullptr, *be = nullptr, *Wo = nullptr, *bo = nullptr;
+  Workspace ws;
+  cudaStream_t loop_stream = nullptr;
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+  float* coef_dev = nullptr;
+  int coef_cap = 0;
+  int* step_ctr = nullptr;     // [2]: step_prep, step_fin
+  int64_t launches = 0;
+  HostStage stage;
+  bool use_tc = false;
+  // pointers of the most recent forward (for dl_time_edge_kernel)
+  const int8_t* last_edge_mask = nullptr;
+  const float* last_linker_mask = nullptr;
+  int last_B = 0, last_N = 0;
+};
+
+namespace {
+
+struct ExpectedParam {
+  std::string name;
+  int64_t numel;
+};
+
+std::vector<ExpectedParam> expected_params(const dl_config& c) {
+  const int D = c.in_node_nf + c.context_node_nf + (c.condition_time ? 1 : 0);
+  const int Hh = c.hidden_nf;
+  std::vector<ExpectedParam> v;
+  v.push_back({"dynamics.embedding.weight", (int64_t)Hh * D});
+  v.push_back({"dynamics.embedding.bias", Hh});
+  v.push_back({"dynamics.embedding_out.weight", (int64_t)D * Hh});
+  v.push_back({"dynamics.embedding_out.bias", D});
+  char buf[160];
+  for (int l = 0; l < c.n_layers; ++l) {
+    for (int s = 0; s < c.inv_sublayers; ++s) {
+      snprintf(buf, sizeof(buf), "dynamics.e_block_%d.gcl_%d.", l, s);
+      std::string p(buf);
+      v.push_back({p + "edge_mlp.0.weight", (int64_t)Hh * (2 * Hh + 2)});
+      v.push_back({p + "edge_mlp.0.bias", Hh});
+      v.push_back({p + "edge_mlp.2.weight", (int64_t)Hh * Hh});
+      v.push_back({p + "edge_mlp.2.bias", Hh});
+      v.push_back({p + "node_mlp.0.weight", (int64_t)Hh * 2 * Hh});
+      v.push_back({p + "node_mlp.0.bias", Hh});
+      v.push_back({p + "node_mlp.2.weight", (int64_t)Hh * Hh});
+      v.push_back({p + "node_mlp.2.bias", Hh});
+    }
+    snprintf(buf, sizeof(buf), "dynamics.e_block_%d.gcl_equiv.", l);
+    std::string p(buf);
+    v.push_back({p + "coord_mlp.0.weight", (int64_t)Hh * (2 * Hh + 2)});
+    v.push_back({p + "coord_mlp.0.bias", Hh});
+    v.push_back({p + "coord_mlp.2.weight", (int64_t)Hh * Hh});
+    v.push_back({p + "coord_mlp.2.bias", Hh});
+    v.push_back({p + "coord_mlp.4.weight", Hh});
+  }
+  return v;
+}
+
+// Host-side packer: appends 16-byte aligned segments to one blob and remembers offsets.
+struct Packer {
+  std::vector<float> blob;
+  size_t add(const std::vector<float>& seg) {
+    while (blob.size() % 4) blob.push_back(0.f);
+    size_t off = blob.size();
+    blob.insert(blob.end(), seg.begin(), seg.end());
+    return off;
+  }
+};
+
+// (out,in) row-major sub-block [0:out) x [c0:c0+k) -> k-major [k][out]
+std::vector<float> transpose_block(const std::vector<float>& W, int out, int in_stride, int c0, int k) {
+  std::vector<float> t((size_t)k * out);
+  for (int o = 0; o < out; ++o)
+    for (int i = 0; i < k; ++i) t[(size_t)i * out + o] = W[(size_t)o * in_stride + c0 + i];
+  return t;
+}
+std::vector<float> column(const std::vector<float>& W, int out, int in_stride, int c) {
+  std::vector<float> t(out);
+  for (int o = 0; o < out; ++o) t[o] = W[(size_t)o * in_stride + c];
+  return t;
+}
+
+template <typename T>
+dl_status dev_alloc(Workspace& ws, T** p, size_t count) {
+  void* q = nullptr;
+  CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+  ws.allocs.push_back(q);
+  *p = reinterpret_cast<T*>(q);
+  return DL_OK;
+}
+
+void free_workspace(Workspace& ws) {
+  for (void* p : ws.allocs) cudaFree(p);
+  ws = Workspace();
+}
+
+dl_status ensure_workspace(dl_engine* e, int B, int N) {
+  Workspace& ws = e->ws;
+  if (ws.B == B && ws.N == N) return DL_OK;
+  free_workspace(ws);
+  const size_t n = (size_t)B * N;
+  const int xd = 3 + e->cfg.in_node_nf;
+  dl_status s;
+#define WSA(field, cnt) if ((s = dev_alloc(ws, &ws.field, (cnt))) != DL_OK) return s
+  WSA(nm, n); WSA(x0, n * 3); WSA(xa, n * 3); WSA(xb, n * 3); WSA(h, n * H); WSA(ABg, n * 2 * H); WSA(ABc, n * 2 * H);
+  WSA(agg, n * H); WSA(z, n * xd); WSA(cls, n);
+  WSA(rowidx, n); WSA(colidx, n); WSA(xrowidx, n); WSA(nr, B); WSA(nc, B); WSA(nxr, B); WSA(n_items, 1);
+  WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(tile_ctr, 64);
+#undef WSA
+  ws.B = B; ws.N = N;
+  return DL_OK;
+}
+
+Plan make_plan(const Workspace& ws) {
+  Plan p;
+  p.rowidx = ws.rowidx; p.colidx = ws.colidx; p.xrowidx = ws.xrowidx; p.nr = ws.nr; p.nc = ws.nc; p.nxr = ws.nxr;
+  p.items = ws.items; p.n_items = ws.n_items; p.xmols = ws.xmols; p.n_xmols = ws.n_xmols;
+  return p;
+}
+
+Geom make_geom(const dl_engine* e, int B, int N) {
+  Geom g;
+  g.B = B; g.N = N; g.F = e->cfg.in_node_nf; g.C = e->cfg.context_node_nf; g.D = e->D;
+  g.graph_type = e->cfg.graph_type; g.norm_constant = e->cfg.norm_constant;
+  g.normalization_factor = e->cfg.normalization_factor;
+  return g;
+}
+
+#define LAUNCH_CHECK()                                                                    \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      set_err("%s:%d kernel launch -> %s", __FILE__, __LINE__, cudaGetErrorString(_e));   \
+      return DL_ERR_CUDA;                                                                 \
+    }                                                                                     \
+  } while (0)
+
+// Masks are constant over a whole sample_chain: build the work plan once.
+dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const float* linker_mask,
+                     const int8_t* edge_mask, cudaStream_t st) {
+  Workspace& ws = e->ws;
+  CK(cudaMemsetAsync(ws.agg, 0, (size_t)B * N * H * sizeof(float), st));  // dead rows aggregate to exactly 0
+  k_plan_mol<<<B, 256, 2 * N * sizeof(int), st>>>(N, e->cfg.graph_type, edge_mask, node_mask, linker_mask, ws.rowidx,
+                                                  ws.colidx, ws.xrowidx, ws.nr, ws.nc, ws.nxr);
+  LAUNCH_CHECK();
+  const int tile_edges = e->use_tc ? tc::TN : ET;
+  const int max_rows = e->use_tc ? tc::MAXR : MAXR;
+  k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols,
+                                ws.n_xmols);
+  LAUNCH_CHECK();
+  e->launches += 2;
+  return DL_OK;
+}
+
+struct FwdIO {
+  // Dynamics.forward mode
+  const float* xh = nullptr; const float* t = nullptr; int t_numel = 0; float* out = nullptr;
+  // common
+  const int8_t* node_mask = nullptr; const float* linker_mask = nullptr; const int8_t* edge_mask = nullptr;
+  const float* context = nullptr; int* nan_flags = nullptr;
+  // sampler mode
+  bool sampler = false; const float* fragment_mask = nullptr; const float* noise = nullptr; float* chain = nullptr;
+  int T = 0; float norm0 = 1.f, norm1 = 1.f, bias1 = 0.f;
+};
+
+ProjW proj_of(const GclW& w) { return ProjW{w.W1a_t, w.W1b_t, w.b1}; }
+ProjW proj_of(const EqW& w) { return ProjW{w.W1a_t, w.W1b_t, w.b1}; }
+
+dl_status launch_edge(dl_engine* e, const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc,
+                      cudaStream_t st) {
+  if (e->use_tc) {
+    dl_status s = tc::launch_edge_tc(gm, ea, coord, w2_tc, e->num_sms, st);
+    if (s != DL_OK) return s;
+  } else {
+    if (coord) k_edge_simt<true><<<e->num_sms, 256, EDGE_SIMT_SMEM, st>>>(gm, ea);
+    else k_edge_simt<false><<<e->num_sms, 256, EDGE_SIMT_SMEM, st>>>(gm, ea);
+  }
+  LAUNCH_CHECK();
+  e->launches += 1;
+  return DL_OK;
+}
+
+// One Dynamics.forward worth of launches (1 + L*(2S+2) + 1 kernels).
+dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStream_t st) {
+  Workspace& ws = e->ws;
+  const Geom gm = make_geom(e, B, N);
+  const int n = B * N;
+  const int L = e->cfg.n_layers, S = e->cfg.inv_sublayers;
+  const int node_blocks = (n + NODE_TM - 1) / NODE_TM;
+  const size_t node_smem = 3 * NODE_TM * LDX * sizeof(float);
+
+  PrepArgs pa{};
+  pa.xh = io.sampler ? ws.z : io.xh;
+  pa.node_mask = io.node_mask; pa.linker_mask = io.linker_mask;
+  pa.t = io.t; pa.t_numel = io.t_numel; pa.context = io.context;
+  pa.We_t = e->We_t; pa.be = e->be; pa.proj = proj_of(e->gcl[0]);
+  pa.nm = ws.nm; pa.x0 = ws.x0; pa.x = ws.xa; pa.cls = ws.cls; pa.h = ws.h; pa.AB = ws.ABg;
+  pa.coef = io.sampler ? e->coef_dev : nullptr;
+  pa.step_prep = io.sampler ? e->step_ctr : nullptr;
+  pa.step_fin = io.sampler ? e->step_ctr + 1 : nullptr;
+  k_prep<<<node_blocks, 256, 0, st>>>(gm, pa);
+  LAUNCH_CHECK();
+  e->launches += 1;
+
+  float* xin = ws.xa;
+  float* xout = ws.xb;
+  const Plan plan = make_plan(ws);
+  e->last_edge_mask = io.edge_mask; e->last_linker_mask = io.linker_mask; e->last_B = B; e->last_N = N;
+  for (int l = 0; l < L; ++l) {
+    for (int s = 0; s < S; ++s) {
+      const GclW& w = e->gcl[l * S + s];
+      EdgeArgs ea{};
+      ea.AB = ws.ABg; ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+      ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
+      ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr;
+      dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st);
+      if (st2 != DL_OK) return st2;
+
+      NodeArgs na{};
+      na.h = ws.h; na.agg = ws.agg; na.nm = ws.nm; na.W3_t = w.W3_t; na.b3 = w.b3; na.W4_t = w.W4_t; na.b4 = w.b4;
+      if (s + 1 < S) {
+        na.proj1 = proj_of(e->gcl[l * S + s + 1]); na.AB1 = ws.ABg; na.AB2 = nullptr;
+      } else {
+        na.proj1 = proj_of(e->eq[l]); na.AB1 = ws.ABc;
+        if (l + 1 < L) { na.proj2 = proj_of(e->gcl[(l + 1) * S]); na.AB2 = ws.ABg; }
+        else na.AB2 = nullptr;
+      }
+      k_node<<<node_blocks, 256, node_smem, st>>>(n, na);
+      LAUNCH_CHECK();
+      e->launches += 1;
+    }
+    k_copy_x<<<(n * 3 + 255) / 256, 256, 0, st>>>(n * 3, xin, xout);
+    LAUNCH_CHECK();
+    e->launches += 1;
+    const EqW& w = e->eq[l];
+    EdgeArgs ea{};
+    ea.AB = ws.ABc; ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+    ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = w.w5;
+    ea.plan = plan; ea.agg = nullptr; ea.x_out = xout;
+    dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st);
+    if (st2 != DL_OK) return st2;
+    std::swap(xin, xout);
+  }
+
+  FinishArgs fa{};
+  fa.h = ws.h; fa.x = xin; fa.x0 = ws.x0; fa.nm = ws.nm; fa.Wo = e->Wo; fa.bo = e->bo;
+  fa.out = io.sampler ? nullptr : io.out; fa.nan_flags = io.nan_flags;
+  if (io.sampler) {
+    fa.z = ws.z; fa.fragment_mask = io.fragment_mask; fa.linker_mask = io.linker_mask; fa.noise = io.noise;
+    fa.coef = e->coef_dev; fa.step_fin = e->step_ctr + 1; fa.step_prep = e->step_ctr; fa.T = io.T;
+    fa.norm0 = io.norm0; fa.norm1 = io.norm1; fa.bias1 = io.bias1; fa.chain = io.chain;
+  }
+  k_finish<<<(n + 15) / 16, 256, 0, st>>>(gm, fa);
+  LAUNCH_CHECK();
+  e->launches += 1;
+  return DL_OK;
+}
+
+int launches_per_forward(const dl_engine* e) { return 2 + e->cfg.n_layers * (2 * e->cfg.inv_sublayers + 2); }
+
+dl_status check_shapes(const dl_engine* e, int B, int N) {
+  if (!e || !e->finalized) { set_err("engine not finalized (dl_finalize_weights)"); return DL_ERR_INVALID; }
+  if (B <= 0 || N <= 0) { set_err("B and N must be positive (got %d, %d)", B, N); return DL_ERR_INVALID; }
+  if ((int64_t)B * N * N > (int64_t)1 << 40) { set_err("B*N*N too large"); return DL_ERR_INVALID; }
+  return DL_OK;
+}
+
+dl_status stage_reserve(dl_engine* e, size_t bytes) {
+  if (e->stage.cap >= bytes) return DL_OK;
+  if (e->stage.buf) cudaFree(e->stage.buf);
+  e->stage.buf = nullptr; e->stage.cap = 0;
+  CK(cudaMalloc((void**)&e->stage.buf, bytes));
+  e->stage.cap = bytes;
+  return DL_OK;
+}
+
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+}  // namespace
+
+extern "C" {
+
+const char* dl_version(void) { return "difflinker_b200 0.1 (sm_100a)"; }
+const char* dl_last_error(void) { return g_err; }
+
+dl_status dl_create(const dl_config* cfg, dl_engine** out) {
+  if (!cfg || !out) { set_err("null argument"); return DL_ERR_INVALID; }
+  if (cfg->hidden_nf != H) { set_err("hidden_nf must be %d (got %d)", H, cfg->hidden_nf); return DL_ERR_UNSUPPORTED; }
+  if (cfg->n_dims != 3) { set_err("n_dims must be 3"); return DL_ERR_UNSUPPORTED; }
+  const int D = cfg->in_node_nf + cfg->context_node_nf + (cfg->condition_time ? 1 : 0);
+  if (D > MAX_DIN || cfg->in_node_nf < 1 || 3 + cfg->in_node_nf > MAX_XHD) {
+    set_err("unsupported feature widths F=%d C=%d", cfg->in_node_nf, cfg->context_node_nf);
+    return DL_ERR_UNSUPPORTED;
+  }
+  if (cfg->n_layers < 1 || cfg->inv_sublayers < 1) { set_err("n_layers/inv_sublayers must be >= 1"); return DL_ERR_INVALID; }
+  if (cfg->graph_type < 0 || cfg->graph_type > 3) { set_err("bad graph_type"); return DL_ERR_INVALID; }
+  if (cfg->graph_type != DL_GRAPH_FC && cfg->context_node_nf < 2) {
+    set_err("pocket graphs need fragment_only/pocket_only context columns"); return DL_ERR_INVALID;
+  }
+  int ndev = 0;
+  CK(cudaGetDeviceCount(&ndev));
+  if (cfg->device < 0 || cfg->device >= ndev) { set_err("device %d not available (%d devices)", cfg->device, ndev); return DL_ERR_INVALID; }
+  CK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, cfg->device));
+  if (prop.major != 10) {
+    set_err("difflinker_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+    return DL_ERR_UNSUPPORTED;
+  }
+  dl_engine* e = new dl_engine();
+  e->cfg = *cfg;
+  e->D = D;
+  e->num_sms = prop.multiProcessorCount;
+  e->use_tc = tc::AVAILABLE && cfg->edge_impl != DL_EDGE_SIMT;
+  CK(cudaStreamCreateWithFlags(&e->loop_stream, cudaStreamNonBlocking));
+  CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
+  CK(cudaEventCreateWithFlags(&e->ev_out, cudaEventDisableTiming));
+  CK(cudaEventCreate(&e->ev_t0));
+  CK(cudaEventCreate(&e->ev_t1));
+  CK(cudaMalloc((void**)&e->step_ctr, 2 * sizeof(int)));
+  CK(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * NODE_TM * LDX * sizeof(float)));
+  CK(cudaFuncSetAttribute(k_edge_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
+  CK(cudaFuncSetAttribute(k_edge_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
+  dl_status s = tc::configure();
+  if (s != DL_OK) { delete e; return s; }
+  *out = e;
+  return DL_OK;
+}
+
+dl_status dl_destroy(dl_engine* e) {
+  if (!e) return DL_OK;
+  cudaSetDevice(e->cfg.device);
+  cudaDeviceSynchronize();
+  free_workspace(e->ws);
+  if (e->wblob) cudaFree(e->wblob);
+  if (e->wblob_tc) cudaFree(e->wblob_tc);
+  if (e->coef_dev) cudaFree(e->coef_dev);
+  if (e->step_ctr) cudaFree(e->step_ctr);
+  if (e->stage.buf) cudaFree(e->stage.buf);
+  if (e->loop_stream) cudaStreamDestroy(e->loop_stream);
+  if (e->ev_in) cudaEventDestroy(e->ev_in);
+  if (e->ev_out) cudaEventDestroy(e->ev_out);
+  if (e->ev_t0) cudaEventDestroy(e->ev_t0);
+  if (e->ev_t1) cudaEventDestroy(e->ev_t1);
+  delete e;
+  return DL_OK;
+}
+
+int64_t dl_expected_param_count(const dl_engine* e) {
+  if (!e) return 0;
+  int64_t n = 0;
+  for (auto& p : expected_params(e->cfg)) n += p.numel;
+  return n;
+}
+
+dl_status dl_set_weight(dl_engine* e, const char* name, const float* data, int64_t numel) {
+  if (!e || !name || !data) { set_err("null argument"); return DL_ERR_INVALID; }
+  for (auto& p : expected_params(e->cfg)) {
+    if (p.name == name) {
+      if (p.numel != numel) {
+        set_err("weight %s: expected %lld elements, got %lld", name, (long long)p.numel, (long long)numel);
+        return DL_ERR_WEIGHTS;
+      }
+      e->raw[p.name].assign(data, data + numel);
+      e->finalized = false;
+      return DL_OK;
+    }
+  }
+  set_err("unexpected weight name %s", name);
+  return DL_ERR_WEIGHTS;
+}
+
+dl_status dl_finalize_weights(dl_engine* e) {
+  if (!e) { set_err("null engine"); return DL_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device));
+  for (auto& p : expected_params(e->cfg))
+    if (!e->raw.count(p.name)) { set_err("missing weight %s", p.name.c_str()); return DL_ERR_WEIGHTS; }
+  const int L = e->cfg.n_layers, S = e->cfg.inv_sublayers, D = e->D;
+  const int IN1 = 2 * H + 2;
+  Packer pk;
+  std::vector<__half> tcblob;
+  struct GOff { size_t W1a, W1b, b1, wd, w0, W2, b2, W3, b3, W4, b4, w5, tc; };
+  std::vector<GOff> goff(L * S), eoff(L);
+  auto R = [&](const std::string& k) -> const std::vector<float>& { return e->raw[k]; };
+  size_t oWe = pk.add(transpose_block(R("dynamics.embedding.weight"), H, D, 0, D));
+  size_t obe = pk.add(R("dynamics.embedding.bias"));
+  size_t oWo = pk.add(R("dynamics.embedding_out.weight"));
+  size_t obo = pk.add(R("dynamics.embedding_out.bias"));
+  char buf[160];
+  for (int l = 0; l < L; ++l) {
+    for (int s = 0; s < S; ++s) {
+      snprintf(buf, sizeof(buf), "dynamics.e_block_%d.gcl_%d.", l, s);
+      std::string p(buf);
+      GOff& o = goff[l * S + s];
+      const auto& W1 = R(p + "edge_mlp.0.weight");
+      o.W1a = pk.add(transpose_block(W1, H, IN1, 0, H));
+      o.W1b = pk.add(transpose_block(W1, H, IN1, H, H));
+      o.b1 = pk.add(R(p + "edge_mlp.0.bias"));
+      o.wd = pk.add(column(W1, H, IN1, 2 * H));
+      o.w0 = pk.add(column(W1, H, IN1, 2 * H + 1));
+      o.W2 = pk.add(transpose_block(R(p + "edge_mlp.2.weight"), H, H, 0, H));
+      o.b2 = pk.add(R(p + "edge_mlp.2.bias"));
+      o.W3 = pk.add(transpose_block(R(p + "node_mlp.0.weight"), H, 2 * H, 0, 2 * H));
+      o.b3 = pk.add(R(p + "node_mlp.0.bias"));
+      o.W4 = pk.add(transpose_block(R(p + "node_mlp.2.weight"), H, H, 0, H));
+      o.b4 = pk.add(R(p + "node_mlp.2.bias"));
+      o.tc = tc::pack_w2(R(p + "edge_mlp.2.weight"), tcblob);
+    }
+    snprintf(buf, sizeof(buf), "dynamics.e_block_%d.gcl_equiv.", l);
+    std::string p(buf);
+    GOff& o = eoff[l];
+    const auto& W1 = R(p + "coord_mlp.0.weight");
+    o.W1a = pk.add(transpose_block(W1, H, IN1, 0, H));
+    o.W1b = pk.add(transpose_block(W1, H, IN1, H, H));
+    o.b1 = pk.add(R(p + "coord_mlp.0.bias"));
+    o.wd = pk.add(column(W1, H, IN1, 2 * H));
+    o.w0 = pk.add(column(W1, H, IN1, 2 * H + 1));
+    o.W2 = pk.add(transpose_block(R(p + "coord_mlp.2.weight"), H, H, 0, H));
+    o.b2 = pk.add(R(p + "coord_mlp.2.bias"));
+    o.w5 = pk.add(R(p + "coord_mlp.4.weight"));
+    o.tc = tc::pack_w2(R(p + "coord_mlp.2.weight"), tcblob);
+  }
+  if (e->wblob) { cudaFree(e->wblob); e->wblob = nullptr; }
+  if (e->wblob_tc) { cudaFree(e->wblob_tc); e->wblob_tc = nullptr; }
+  CK(cudaMalloc((void**)&e->wblob, pk.blob.size() * sizeof(float)));
+  CK(cudaMemcpy(e->wblob, pk.blob.data(), pk.blob.size() * sizeof(float), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&e->wblob_tc, std::max<size_t>(tcblob.size(), 1) * sizeof(__half)));
+  CK(cudaMemcpy(e->wblob_tc, tcblob.data(), tcblob.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  const float* base = e->wblob;
+  const __half* tbase = reinterpret_cast<const __half*>(e->wblob_tc);
+  e->We_t = base + oWe; e->be = base + obe; e->Wo = base + oWo; e->bo = base + obo;
+  e->gcl.assign(L * S, GclW{});
+  e->eq.assign(L, EqW{});
+  for (int i = 0; i < L * S; ++i) {
+    const GOff& o = goff[i];
+    e->gcl[i] = GclW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0, base + o.W2, base + o.b2,
+                     base + o.W3,  base + o.b3,  base + o.W4, base + o.b4, tbase + o.tc};
+  }
+  for (int l = 0; l < L; ++l) {
+    const GOff& o = eoff[l];
+    e->eq[l] = EqW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0,
+                   base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc};
+  }
+  e->finalized = true;
+  return DL_OK;
+}
+
+dl_status dl_dynamics_forward(dl_engine* e, int32_t B, int32_t N, const float* t, int32_t t_numel, const float* xh,
+                              const int8_t* node_mask, const float* linker_mask, const int8_t* edge_mask,
+                              const float* context, float* out, int32_t* nan_flags, void* stream) {
+  dl_status s = check_shapes(e, B, N);
+  if (s != DL_OK) return s;
+  if (!xh || !node_mask || !out) { set_err("xh/node_mask/out must not be null"); return DL_ERR_INVALID; }
+  if (e->cfg.condition_time && (!t || (t_numel != 1 && t_numel != B))) { set_err("t must hold 1 or B values"); return DL_ERR_INVALID; }
+  if (e->cfg.context_node_nf > 0 && !context) { set_err("context required (context_node_nf=%d)", e->cfg.context_node_nf); return DL_ERR_INVALID; }
+  if (e->cfg.centering) { set_err("centering (inpainting models) is not implemented yet"); return DL_ERR_UNSUPPORTED; }
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if ((s = ensure_workspace(e, B, N)) != DL_OK) return s;
+  CK(cudaEventRecord(e->ev_t0, st));
+  if (nan_flags) CK(cudaMemsetAsync(nan_flags, 0, B * sizeof(int32_t), st));
+  if ((s = build_plan(e, B, N, node_mask, linker_mask, edge_mask, st)) != DL_OK) return s;
+  FwdIO io;
+  io.xh = xh; io.t = t; io.t_numel = t_numel; io.out = out; io.node_mask = node_mask; io.linker_mask = linker_mask;
+  io.edge_mask = edge_mask; io.context = context; io.nan_flags = nan_flags;
+  if ((s = enqueue_forward(e, B, N, io, st)) != DL_OK) return s;
+  CK(cudaEventRecord(e->ev_t1, st));
+  return DL_OK;
+}
+
+dl_status dl_dynamics_forward_host(dl_engine* e, int32_t B, int32_t N, const float* t, int32_t t_numel,
+                                   const float* xh, const int8_t* node_mask, const float* linker_mask,
+                                   const int8_t* edge_mask, const float* context, float* out, int32_t* nan_flags) {
+  dl_status s = check_shapes(e, B, N);
+  if (s != DL_OK) return s;
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t n = (size_t)B * N;
+  const int xd = 3 + e->cfg.in_node_nf, C = e->cfg.context_node_nf;
+  const size_t o_t = 0, o_xh = o_t + align256(sizeof(float) * std::max(t_numel, 1)), o_nm = o_xh + align256(n * xd * 4),
+               o_lm = o_nm + align256(n), o_em = o_lm + align256(n * 4), o_ctx = o_em + align256(n * N),
+               o_out = o_ctx + align256(n * std::max(C, 1) * 4), o_fl = o_out + align256(n * xd * 4),
+               total = o_fl + align256(B * 4);
+  if ((s = stage_reserve(e, total)) != DL_OK) return s;
+  char* d = e->stage.buf;
+  cudaStream_t st = e->loop_stream;
+  if (t) CK(cudaMemcpyAsync(d + o_t, t, sizeof(float) * t_numel, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_xh, xh, n * xd * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_nm, node_mask, n, cudaMemcpyHostToDevice, st));
+  if (linker_mask) CK(cudaMemcpyAsync(d + o_lm, linker_mask, n * 4, cudaMemcpyHostToDevice, st));
+  if (edge_mask && e->cfg.graph_type == DL_GRAPH_FC) CK(cudaMemcpyAsync(d + o_em, edge_mask, n * N, cudaMemcpyHostToDevice, st));
+  if (context) CK(cudaMemcpyAsync(d + o_ctx, context, n * C * 4, cudaMemcpyHostToDevice, st));
+  s = dl_dynamics_forward(e, B, N, t ? (const float*)(d + o_t) : nullptr, t_numel, (const float*)(d + o_xh),
+                          (const int8_t*)(d + o_nm), linker_mask ? (const float*)(d + o_lm) : nullptr,
+                          (edge_mask && e->cfg.graph_type == DL_GRAPH_FC) ? (const int8_t*)(d + o_em) : nullptr,
+                          context ? (const float*)(d + o_ctx) : nullptr, (float*)(d + o_out), (int32_t*)(d + o_fl), st);
+  if (s != DL_OK) return s;
+  std::vector<int32_t> flags(B);
+  CK(cudaMemcpyAsync(out, d + o_out, n * xd * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(flags.data(), d + o_fl, B * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  bool any = false;
+  for (int i = 0; i < B; ++i) { any |= flags[i] != 0; if (nan_flags) nan_flags[i] = flags[i]; }
+  return any ? DL_NAN_DETECTED : DL_OK;
+}
+
+dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                          const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                          const float* linker_mask, const int8_t* edge_mask, const float* context,
+                          const float* noise, const dl_step_coef* coef, const float* norm, float* chain,
+                          int32_t* nan_flags, void* stream) {
+  dl_status s = check_shapes(e, B, N);
+  if (s != DL_OK) return s;
+  if (sampler != DL_SAMPLER_LINKER) { set_err("inpainting sampler is not implemented yet"); return DL_ERR_UNSUPPORTED; }
+  if (e->cfg.centering) { set_err("centering (inpainting models) is not implemented yet"); return DL_ERR_UNSUPPORTED; }
+  if (!xh || !node_mask || !fragment_mask || !linker_mask || !noise || !coef || !norm || !chain) {
+    set_err("null argument"); return DL_ERR_INVALID;
+  }
+  if (T < 1 || keep_frames < 1 || keep_frames > T) { set_err("need 1 <= keep_frames <= T"); return DL_ERR_INVALID; }
+  if (e->cfg.context_node_nf > 0 && !context) { set_err("context required"); return DL_ERR_INVALID; }
+  static_assert(sizeof(dl_step_coef) == 32, "dl_step_coef layout");
+  CK(cudaSetDevice(e->cfg.device));
+  cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
+  cudaStream_t st = e->loop_stream;
+  if ((s = ensure_workspace(e, B, N)) != DL_OK) return s;
+  if (e->coef_cap < T + 1) {
+    if (e->coef_dev) cudaFree(e->coef_dev);
+    e->coef_dev = nullptr;
+    CK(cudaMalloc((void**)&e->coef_dev, (size_t)(T + 1) * sizeof(dl_step_coef)));
+    e->coef_cap = T + 1;
+  }
+  // order the private loop stream after the caller's stream (the legacy default stream cannot be captured)
+  if (user != st) {
+    CK(cudaEventRecord(e->ev_in, user));
+    CK(cudaStreamWaitEvent(st, e->ev_in, 0));
+  }
+  CK(cudaMemcpyAsync(e->coef_dev, coef, (size_t)(T + 1) * sizeof(dl_step_coef), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(e->step_ctr, 0, 2 * sizeof(int), st));
+  if (nan_flags) CK(cudaMemsetAsync(nan_flags, 0, B * sizeof(int32_t), st));
+  const int n = B * N, xd = 3 + e->cfg.in_node_nf;
+  // frames that no reverse step is the last writer of stay zero, as torch.zeros in edm.py:143
+  CK(cudaMemsetAsync(chain, 0, (size_t)keep_frames * n * xd * sizeof(float), st));
+  k_init_z<<<(n * xd + 255) / 256, 256, 0, st>>>(n, xd, xh, fragment_mask, linker_mask, noise, e->ws.z);
+  LAUNCH_CHECK();
+  e->launches += 1;
+  if ((s = build_plan(e, B, N, node_mask, linker_mask, edge_mask, st)) != DL_OK) return s;
+
+  FwdIO io;
+  io.sampler = true; io.node_mask = node_mask; io.linker_mask = linker_mask; io.edge_mask = edge_mask;
+  io.context = context; io.nan_flags = nan_flags; io.fragment_mask = fragment_mask; io.noise = noise;
+  io.chain = chain; io.T = T; io.norm0 = norm[0]; io.norm1 = norm[1]; io.bias1 = norm[2];
+
+  // capture ONE reverse step; the step index lives on the device, so the same graph serves all T+1 steps
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  const int64_t before = e->launches;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  s = enqueue_forward(e, B, N, io, st);
+  cudaError_t ce = cudaStreamEndCapture(st, &graph);
+  if (s != DL_OK) { if (graph) cudaGraphDestroy(graph); return s; }
+  if (ce != cudaSuccess) { set_err("cudaStreamEndCapture -> %s", cudaGetErrorString(ce)); return DL_ERR_CUDA; }
+  const int64_t per_step = e->launches - before;
+  CK(cudaGraphInstantiate(&exec, graph, 0));
+  CK(cudaEventRecord(e->ev_t0, st));
+  for (int r = 0; r <= T; ++r) {
+    cudaError_t le = cudaGraphLaunch(exec, st);
+    if (le != cudaSuccess) {
+      set_err("cudaGraphLaunch step %d -> %s", r, cudaGetErrorString(le));
+      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
+      return DL_ERR_CUDA;
+    }
+  }
+  CK(cudaEventRecord(e->ev_t1, st));
+  e->launches = before + per_step * (T + 1);
+  if (user != st) {
+    CK(cudaEventRecord(e->ev_out, st));
+    CK(cudaStreamWaitEvent(user, e->ev_out, 0));
+  }
+  // exec/graph destruction is deferred by the runtime until the launched work has finished
+  CK(cudaGraphExecDestroy(exec));
+  CK(cudaGraphDestroy(graph));
+  return DL_OK;
+}
+
+dl_status dl_sample_chain_host(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                               const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                               const float* linker_mask, const int8_t* edge_mask, const float* context,
+                               const float* noise, const dl_step_coef* coef, const float* norm, float* chain,
+                               int32_t* nan_flags) {
+  dl_status s = check_shapes(e, B, N);
+  if (s != DL_OK) return s;
+  if (!xh || !node_mask || !fragment_mask || !linker_mask || !noise || !coef || !norm || !chain) {
+    set_err("null argument"); return DL_ERR_INVALID;
+  }
+  if (T < 1 || keep_frames < 1 || keep_frames > T) { set_err("need 1 <= keep_frames <= T"); return DL_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device));
+  const size_t n = (size_t)B * N;
+  const int xd = 3 + e->cfg.in_node_nf, C = e->cfg.context_node_nf;
+  const bool has_em = edge_mask && e->cfg.graph_type == DL_GRAPH_FC;
+  const size_t o_xh = 0, o_nm = o_xh + align256(n * xd * 4), o_fm = o_nm + align256(n), o_lm = o_fm + align256(n * 4),
+               o_em = o_lm + align256(n * 4), o_ctx = o_em + align256(has_em ? n * N : 1),
+               o_nz = o_ctx + align256(n * std::max(C, 1) * 4), o_ch = o_nz + align256((size_t)(T + 2) * n * xd * 4),
+               o_fl = o_ch + align256((size_t)keep_frames * n * xd * 4), total = o_fl + align256(B * 4);
+  if ((s = stage_reserve(e, total)) != DL_OK) return s;
+  char* d = e->stage.buf;
+  cudaStream_t st = e->loop_stream;
+  CK(cudaMemcpyAsync(d + o_xh, xh, n * xd * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_nm, node_mask, n, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_fm, fragment_mask, n * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_lm, linker_mask, n * 4, cudaMemcpyHostToDevice, st));
+  if (has_em) CK(cudaMemcpyAsync(d + o_em, edge_mask, n * N, cudaMemcpyHostToDevice, st));
+  if (context) CK(cudaMemcpyAsync(d + o_ctx, context, n * C * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_nz, noise, (size_t)(T + 2) * n * xd * 4, cudaMemcpyHostToDevice, st));
+  s = dl_sample_chain(e, sampler, B, N, T, keep_frames, (const float*)(d + o_xh), (const int8_t*)(d + o_nm),
+                      (const float*)(d + o_fm), (const float*)(d + o_lm), has_em ? (const int8_t*)(d + o_em) : nullptr,
+                      context ? (const float*)(d + o_ctx) : nullptr, (const float*)(d + o_nz), coef, norm,
+                      (float*)(d + o_ch), (int32_t*)(d + o_fl), st);
+  if (s != DL_OK) return s;
+  std::vector<int32_t> flags(B);
+  CK(cudaMemcpyAsync(chain, d + o_ch, (size_t)keep_frames * n * xd * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaMemcpyAsync(flags.data(), d + o_fl, B * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  bool any = false;
+  for (int i = 0; i < B; ++i) { any |= flags[i] != 0; if (nan_flags) nan_flags[i] = flags[i]; }
+  return any ? DL_NAN_DETECTED : DL_OK;
+}
+
+int64_t dl_launch_count(const dl_engine* e) { return e ? e->launches : 0; }
+
+float dl_last_elapsed_ms(dl_engine* e) {
+  if (!e) return -1.f;
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) != cudaSuccess) { cudaGetLastError(); return -1.f; }
+  return ms;
+}
+
+float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
+  if (!e || !e->finalized || e->last_B == 0 || reps < 1) { set_err("dl_time_edge_kernel: no previous forward"); return -1.f; }
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess) return -1.f;
+  Workspace& ws = e->ws;
+  const Geom gm = make_geom(e, e->last_B, e->last_N);
+  const GclW& w = e->gcl[0];
+  EdgeArgs ea{};
+  ea.AB = ws.ABg; ea.x = ws.xa; ea.x0 = ws.x0; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+  ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
+  ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr;
+  cudaStream_t st = e->loop_stream;
+  for (int i = 0; i < 2; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;
+  if (cudaEventRecord(e->ev_t0, st) != cudaSuccess) return -1.f;
+  for (int i = 0; i < reps; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;
+  if (cudaEventRecord(e->ev_t1, st) != cudaSuccess) return -1.f;
+  if (cudaStreamSynchronize(st) != cudaSuccess) { set_err("dl_time_edge_kernel: %s", cudaGetErrorString(cudaGetLastError())); return -1.f; }
+  float ms = -1.f;
+  if (cudaEventElapsedTime(&ms, e->ev_t0, e->ev_t1) != cudaSuccess) return -1.f;
+  return ms / reps;
+}
+
+dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err) {
+  if (!e) { set_err("null engine"); return DL_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device));
+  return tc::selftest(e->num_sms, max_abs_err, max_rel_err);
+}
+
+}  // extern "C"

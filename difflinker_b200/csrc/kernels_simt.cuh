@@ -1,0 +1,665 @@
+// fp32 SIMT kernels of the DiffLinker hot path: work plan, node-level layers, reference edge kernel,
+// output/z-update.  The tcgen05 edge kernel (kernels_tc.cuh) replaces k_edge_simt on the product path;
+// k_edge_simt stays as the on-device cross-check (dl_selftest_tc, DL_EDGE_SIMT).
+#pragma once
+#include "common.cuh"
+
+namespace dl {
+
+// ------------------------------------------------------------------------------------------------
+// Work plan
+// ------------------------------------------------------------------------------------------------
+// One CTA per molecule. Finds rows/columns of the (N x N) edge-weight matrix that carry any non-zero
+// weight; everything else is skipped exactly (0 * finite == 0, DESIGN.md "masked work").
+// FC graphs: weights are the caller's int8 edge_mask (datasets.py:365-369) or all ones when NULL.
+// Pocket graphs: the weight is a per-step distance predicate, so every valid node is live.
+__global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edge_mask,
+                           const int8_t* __restrict__ node_mask, const float* __restrict__ linker_mask,
+                           int* __restrict__ rowidx, int* __restrict__ colidx, int* __restrict__ xrowidx,
+                           int* __restrict__ nr, int* __restrict__ nc, int* __restrict__ nxr) {
+  extern __shared__ int sm_plan[];
+  int* rowlive = sm_plan;        // [N]
+  int* collive = sm_plan + N;    // [N]
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  for (int i = tid; i < N; i += blockDim.x) { rowlive[i] = 0; collive[i] = 0; }
+  __syncthreads();
+  if (graph_type == 0 && edge_mask != nullptr) {
+    const int8_t* em = edge_mask + (size_t)b * N * N;
+    for (int i = warp; i < N; i += nwarp) {
+      int any = 0;
+      for (int j = lane; j < N; j += 32) {
+        int v = em[(size_t)i * N + j];
+        if (v != 0) { any = 1; collive[j] = 1; }
+      }
+      any = __any_sync(0xffffffffu, any);
+      if (lane == 0 && any) rowlive[i] = 1;
+    }
+  } else if (graph_type == 0) {
+    for (int i = tid; i < N; i += blockDim.x) { rowlive[i] = 1; collive[i] = 1; }
+  } else {
+    for (int i = tid; i < N; i += blockDim.x) {
+      int v = node_mask[(size_t)b * N + i] != 0;
+      rowlive[i] = v; collive[i] = v;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int a = 0, c = 0, x = 0;
+    for (int i = 0; i < N; ++i) {
+      if (rowlive[i]) {
+        rowidx[(size_t)b * N + a++] = i;
+        if (linker_mask == nullptr || linker_mask[(size_t)b * N + i] != 0.0f) xrowidx[(size_t)b * N + x++] = i;
+      }
+      if (collive[i]) colidx[(size_t)b * N + c++] = i;
+    }
+    nr[b] = a; nc[b] = c; nxr[b] = x;
+  }
+}
+
+// Single thread: flatten per-molecule row groups into the GCL work list. A work item is `rows_per_tile`
+// complete rows (so the segment sum over j never crosses CTAs and stays order-deterministic).
+__global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __restrict__ nr,
+                             const int* __restrict__ nc, const int* __restrict__ nxr, int4* __restrict__ items,
+                             int* __restrict__ n_items, int* __restrict__ xmols, int* __restrict__ n_xmols) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  int cnt = 0, xc = 0;
+  for (int b = 0; b < B; ++b) {
+    int r = nr[b], c = nc[b];
+    if (r > 0 && c > 0) {
+      int per = c >= tile_edges ? 1 : tile_edges / c;
+      if (per > max_rows) per = max_rows;
+      for (int r0 = 0; r0 < r; r0 += per) items[cnt++] = make_int4(b, r0, min(per, r - r0), 0);
+    }
+    if (nxr[b] > 0 && c > 0) xmols[xc++] = b;
+  }
+  *n_items = cnt;
+  *n_xmols = xc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Node-level SIMT tile GEMM: 32 nodes x 128 channels per CTA (256 threads).
+// warp w owns nodes 4w..4w+3, lane owns channels 4*lane..4*lane+3.
+// ------------------------------------------------------------------------------------------------
+constexpr int NODE_TM = 32;
+constexpr int LDX = 132;  // smem row stride (floats), keeps float4 alignment
+
+template <int K>
+__device__ __forceinline__ void warp_gemm_4x4(const float* __restrict__ xs, const float* __restrict__ Wt, int lane,
+                                              float (&acc)[4][4]) {
+#pragma unroll 2
+  for (int k = 0; k < K; k += 4) {
+    float4 w[4], x[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) w[q] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k + q) * H + lane * 4));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) x[r] = *reinterpret_cast<const float4*>(xs + r * LDX + k);
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const float xv[4] = {x[r].x, x[r].y, x[r].z, x[r].w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[r][0] = fmaf(xv[q], w[q].x, acc[r][0]);
+        acc[r][1] = fmaf(xv[q], w[q].y, acc[r][1]);
+        acc[r][2] = fmaf(xv[q], w[q].z, acc[r][2]);
+        acc[r][3] = fmaf(xv[q], w[q].w, acc[r][3]);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+}
+
+// A = hs W1a^T + b1 -> AB[:, 0:128];  B = hs W1b^T -> AB[:, 128:256]   (first Linear of an edge MLP,
+// split per SURVEY.md section 8(a) "verified restatement": egnn.py:45-50 / 103 with the concat distributed).
+__device__ __forceinline__ void project_ab(const float* hs_warp, const ProjW& pw, float* __restrict__ AB, int g0,
+                                           int n_total, int warp, int lane) {
+  float acc[4][4];
+  zero_acc(acc);
+  warp_gemm_4x4<H>(hs_warp, pw.W1a_t, lane, acc);
+  const float4 bb = __ldg(reinterpret_cast<const float4*>(pw.b1 + lane * 4));
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int g = g0 + warp * 4 + r;
+    if (g < n_total)
+      *reinterpret_cast<float4*>(AB + (size_t)g * 2 * H + lane * 4) =
+          make_float4(acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w);
+  }
+  zero_acc(acc);
+  warp_gemm_4x4<H>(hs_warp, pw.W1b_t, lane, acc);
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int g = g0 + warp * 4 + r;
+    if (g < n_total)
+      *reinterpret_cast<float4*>(AB + (size_t)g * 2 * H + H + lane * 4) =
+          make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+  }
+}
+
+// Dynamics.forward prologue (egnn.py:387-407) + EGNN.embedding (egnn.py:224) + first projection.
+//   nm = node_mask; x0 = xh[:, :3]*nm; h_in = [xh[:, 3:]*nm, t, context]; h = We h_in + be
+// In sampler mode (step_ctr != nullptr) `xh` is the engine's z buffer and t comes from coef[step].
+struct PrepArgs {
+  const float* xh;          // (B*N, 3+F)
+  const int8_t* node_mask;  // (B*N)
+  const float* linker_mask; // (B*N) or null
+  const float* t;           // (t_numel) or null in sampler mode
+  int t_numel;
+  const float* context;     // (B*N, C) or null
+  const float* We_t;        // [D][128]
+  const float* be;          // [128]
+  ProjW proj;
+  float* nm;                // out (B*N)
+  float* x0;                // out (B*N,3)
+  float* x;                 // out (B*N,3)
+  int* cls;                 // out (B*N) node class for pocket graphs: 0 invalid, 1 ligand, 2 pocket
+  float* h;                 // out (B*N,128)
+  float* AB;                // out (B*N,256)
+  const float* coef;        // device dl_step_coef table (8 floats per row) or null
+  const int* step_prep;     // device counter read here
+  int* step_fin;            // device counter written here
+};
+
+__global__ void __launch_bounds__(256) k_prep(Geom gm, PrepArgs a) {
+  __shared__ __align__(16) float hs[NODE_TM * LDX];
+  __shared__ float hin[NODE_TM][MAX_DIN];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n_total = gm.B * gm.N;
+  const int g0 = blockIdx.x * NODE_TM;
+  const int xd = 3 + gm.F;
+  int step = 0;
+  if (a.step_prep != nullptr) {
+    step = *a.step_prep;
+    if (blockIdx.x == 0 && tid == 0) *a.step_fin = step;
+  }
+  for (int idx = tid; idx < NODE_TM * MAX_DIN; idx += 256) {
+    int r = idx / MAX_DIN, d = idx % MAX_DIN;
+    int g = g0 + r;
+    float v = 0.f;
+    if (g < n_total && d < gm.D) {
+      float m = (float)a.node_mask[g];
+      if (d < gm.F) {
+        v = a.xh[(size_t)g * xd + 3 + d] * m;
+      } else if (d == gm.F && gm.D > gm.F + gm.C) {  // time column (condition_time)
+        if (a.coef != nullptr) v = a.coef[(size_t)step * 8 + 0];
+        else v = a.t[a.t_numel == 1 ? 0 : g / gm.N];
+      } else {
+        int cidx = d - (gm.D - gm.C);
+        v = a.context[(size_t)g * gm.C + cidx];
+      }
+    }
+    hin[r][d] = v;
+  }
+  if (tid < NODE_TM) {
+    int g = g0 + tid;
+    if (g < n_total) {
+      float m = (float)a.node_mask[g];
+      a.nm[g] = m;
+      for (int d = 0; d < 3; ++d) {
+        float v = a.xh[(size_t)g * xd + d] * m;
+        a.x0[(size_t)g * 3 + d] = v;
+        a.x[(size_t)g * 3 + d] = v;
+      }
+      if (gm.graph_type != 0) {
+        // egnn.py:566-570: ligand = (linker | fragment_only) & valid ; pocket = pocket_only & valid
+        int valid = m != 0.f;
+        int pk = a.context[(size_t)g * gm.C + gm.C - 1] != 0.f;
+        int fr = a.context[(size_t)g * gm.C + gm.C - 2] != 0.f;
+        int lk = a.linker_mask != nullptr ? (a.linker_mask[g] != 0.f) : 0;
+        int c = 0;
+        if (valid) {
+          if (gm.graph_type == 1) c = 1;  // '4A': a single class, one cut-off
+          else c = (lk || fr) ? 1 : (pk ? 2 : 3);
+        }
+        a.cls[g] = c;
+      }
+    }
+  }
+  __syncthreads();
+  // embedding: K = D (tiny) -> straight dot products
+  {
+    float acc[4][4];
+    zero_acc(acc);
+    for (int d = 0; d < gm.D; ++d) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(a.We_t + (size_t)d * H + lane * 4));
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float xv = hin[warp * 4 + r][d];
+        acc[r][0] = fmaf(xv, w.x, acc[r][0]);
+        acc[r][1] = fmaf(xv, w.y, acc[r][1]);
+        acc[r][2] = fmaf(xv, w.z, acc[r][2]);
+        acc[r][3] = fmaf(xv, w.w, acc[r][3]);
+      }
+    }
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.be + lane * 4));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      float4 o = make_float4(acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w);
+      *reinterpret_cast<float4*>(hs + (warp * 4 + r) * LDX + lane * 4) = o;
+      int g = g0 + warp * 4 + r;
+      if (g < n_total) *reinterpret_cast<float4*>(a.h + (size_t)g * H + lane * 4) = o;
+    }
+  }
+  __syncwarp();
+  project_ab(hs + warp * 4 * LDX, a.proj, a.AB, g0, n_total, warp, lane);
+}
+
+// GCL.node_model + node_mask (egnn.py:62-80), then the first-layer projections of whatever edge MLP
+// consumes the new h next (the following GCL, and/or the block's coord_mlp + the next block's gcl_0).
+struct NodeArgs {
+  float* h;             // (B*N,128) in/out (rows are CTA-private)
+  const float* agg;     // (B*N,128)  sum_j m_ij*EM_ij / normalization_factor
+  const float* nm;      // (B*N)
+  const float* W3_t; const float* b3; const float* W4_t; const float* b4;
+  ProjW proj1; float* AB1;
+  ProjW proj2; float* AB2;  // AB2 == nullptr -> skip
+};
+
+__global__ void __launch_bounds__(256) k_node(int n_total, NodeArgs a) {
+  extern __shared__ __align__(16) float sm_node[];
+  float* hs = sm_node;                    // [32][LDX]
+  float* as = sm_node + NODE_TM * LDX;    // [32][LDX]
+  float* hid = as + NODE_TM * LDX;        // [32][LDX]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g0 = blockIdx.x * NODE_TM;
+  // each warp loads its own 4 rows (all later reads of those rows are by the same warp)
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int row = warp * 4 + r, g = g0 + row;
+    float4 hv = make_float4(0, 0, 0, 0), av = hv;
+    if (g < n_total) {
+      hv = *reinterpret_cast<const float4*>(a.h + (size_t)g * H + lane * 4);
+      av = *reinterpret_cast<const float4*>(a.agg + (size_t)g * H + lane * 4);
+    }
+    *reinterpret_cast<float4*>(hs + row * LDX + lane * 4) = hv;
+    *reinterpret_cast<float4*>(as + row * LDX + lane * 4) = av;
+  }
+  __syncwarp();
+  float acc[4][4];
+  zero_acc(acc);
+  warp_gemm_4x4<H>(hs + warp * 4 * LDX, a.W3_t, lane, acc);
+  warp_gemm_4x4<H>(as + warp * 4 * LDX, a.W3_t + (size_t)H * H, lane, acc);
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.b3 + lane * 4));
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      *reinterpret_cast<float4*>(hid + (warp * 4 + r) * LDX + lane * 4) =
+          make_float4(silu_f(acc[r][0] + bb.x), silu_f(acc[r][1] + bb.y), silu_f(acc[r][2] + bb.z),
+                      silu_f(acc[r][3] + bb.w));
+  }
+  __syncwarp();
+  zero_acc(acc);
+  warp_gemm_4x4<H>(hid + warp * 4 * LDX, a.W4_t, lane, acc);
+  {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(a.b4 + lane * 4));
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      int row = warp * 4 + r, g = g0 + row;
+      float m = g < n_total ? a.nm[g] : 0.f;
+      float4 hv = *reinterpret_cast<const float4*>(hs + row * LDX + lane * 4);
+      float4 o = make_float4((hv.x + (acc[r][0] + bb.x)) * m, (hv.y + (acc[r][1] + bb.y)) * m,
+                             (hv.z + (acc[r][2] + bb.z)) * m, (hv.w + (acc[r][3] + bb.w)) * m);
+      __syncwarp();
+      *reinterpret_cast<float4*>(hs + row * LDX + lane * 4) = o;
+      if (g < n_total) *reinterpret_cast<float4*>(a.h + (size_t)g * H + lane * 4) = o;
+    }
+  }
+  __syncwarp();
+  project_ab(hs + warp * 4 * LDX, a.proj1, a.AB1, g0, n_total, warp, lane);
+  if (a.AB2 != nullptr) project_ab(hs + warp * 4 * LDX, a.proj2, a.AB2, g0, n_total, warp, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Edge weights
+// ------------------------------------------------------------------------------------------------
+// FC graphs: the caller's int8 edge_mask value (0/-1/-2, datasets.py:365-369) or 1 when absent.
+// Pocket graphs (egnn.py:554-596): a 0/1 predicate on the *input* coordinates of this forward call.
+__device__ __forceinline__ float edge_weight(int graph_type, const int8_t* __restrict__ em_mol, int N, int i, int j,
+                                             int ci, int cj, float d0) {
+  if (graph_type == 0) return em_mol != nullptr ? (float)em_mol[(size_t)i * N + j] : 1.0f;
+  if (i == j || ci == 0 || cj == 0) return 0.f;
+  float dist = sqrtf(d0);
+  if (graph_type == 1) return dist <= 4.0f ? 1.f : 0.f;
+  if (ci == 3 || cj == 3) return 0.f;               // valid atom that is neither ligand nor pocket
+  if (ci == 1 && cj == 1) return 1.f;               // ligand-ligand: fully connected
+  if (ci == 2 && cj == 2) return dist <= 4.0f ? 1.f : 0.f;
+  float cut = graph_type == 2 ? 4.0f : 10.0f;       // FC-4A : FC-10A-4A
+  return dist <= cut ? 1.f : 0.f;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Reference fp32 SIMT edge kernel: second Linear of the edge / coord MLP as a 128x128x128 tile GEMM.
+//   GCL   (egnn.py:45-66):   agg_i = sum_j silu(W2 silu(A_i+B_j+d_ij wd+d0_ij w0)+b2) * EM_ij / nf
+//   COORD (egnn.py:101-117): x_i  += (sum_j cd_ij * (w5 . silu(W2 silu(...)+b2)) * EM_ij / nf) * linker_mask_i
+// Tile = up to 128 edges = whole rows x all live columns (or one row x 128-column chunks when nc > 128).
+// ------------------------------------------------------------------------------------------------
+constexpr int ET = 128;          // edges per tile
+constexpr int MAXR = 8;          // max rows per tile
+constexpr int LDB = H + 1;       // Bs row stride (bank-conflict-free column walks)
+
+struct EdgeArgs {
+  const float* AB;          // (B*N,256)
+  const float* x;           // (B*N,3) current coordinates
+  const float* x0;          // (B*N,3) input coordinates (d0)
+  const int8_t* edge_mask;  // (B*N*N) or null
+  const int* cls;           // (B*N) pocket classes (graph_type != 0)
+  const float* nm;          // (B*N)
+  const float* linker_mask; // (B*N) or null
+  const float* W2_t; const float* b2; const float* wd; const float* w0; const float* w5;
+  Plan plan;
+  float* agg;               // GCL out (B*N,128)
+  float* x_out;             // COORD out (B*N,3)
+};
+
+constexpr size_t EDGE_SIMT_SMEM =
+    sizeof(float) * ((size_t)H * H /*W2s*/ + (size_t)H * ET /*S1*/ + (size_t)ET * LDB /*Bs*/ + (size_t)MAXR * H /*As*/ +
+                     4 * H /*b2,wd,w0,w5*/ + ET /*ems*/ + ET * 3 /*cds*/ + ET /*phis*/);
+
+template <bool COORD>
+__global__ void __launch_bounds__(256, 1) k_edge_simt(Geom gm, EdgeArgs a) {
+  extern __shared__ __align__(16) float sm_edge[];
+  float* W2s = sm_edge;
+  float* S1 = W2s + H * H;
+  float* Bs = S1 + H * ET;
+  float* As = Bs + ET * LDB;
+  float* b2s = As + MAXR * H;
+  float* wds = b2s + H;
+  float* w0s = wds + H;
+  float* w5s = w0s + H;
+  float* ems = w5s + H;
+  float* cds = ems + ET;
+  float* phis = cds + ET * 3;
+  __shared__ float xacc[COORD ? 1 : 1];  // placeholder to keep static smem trivial
+  (void)xacc;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = gm.N;
+  for (int idx = tid; idx < H * H / 4; idx += 256)
+    reinterpret_cast<float4*>(W2s)[idx] = __ldg(reinterpret_cast<const float4*>(a.W2_t) + idx);
+  if (tid < H) {
+    b2s[tid] = a.b2[tid]; wds[tid] = a.wd[tid]; w0s[tid] = a.w0[tid];
+    w5s[tid] = COORD ? a.w5[tid] : 0.f;
+  }
+  __syncthreads();
+
+  const int n_work = COORD ? *a.plan.n_xmols : *a.plan.n_items;
+  for (int wi = blockIdx.x; wi < n_work; wi += gridDim.x) {
+    int b, r_begin, r_count;
+    if (COORD) { b = a.plan.xmols[wi]; r_begin = 0; r_count = a.plan.nxr[b]; }
+    else { int4 it = a.plan.items[wi]; b = it.x; r_begin = it.y; r_count = it.z; }
+    const int nc = a.plan.nc[b];
+    const int* rows = (COORD ? a.plan.xrowidx : a.plan.rowidx) + (size_t)b * N;
+    const int* cols = a.plan.colidx + (size_t)b * N;
+    const size_t gb = (size_t)b * N;
+    const int8_t* em_mol = a.edge_mask ? a.edge_mask + gb * N : nullptr;
+    int per = nc >= ET ? 1 : ET / nc;
+    if (per > MAXR) per = MAXR;
+
+    for (int rt = 0; rt < r_count; rt += per) {          // row groups (GCL items hold exactly one)
+      const int nrt = min(per, r_count - rt);
+      for (int r = warp; r < nrt; r += 8) {               // A rows
+        int i = rows[r_begin + rt + r];
+        *reinterpret_cast<float4*>(As + r * H + lane * 4) =
+            *reinterpret_cast<const float4*>(a.AB + (gb + i) * 2 * H + lane * 4);
+      }
+      float run = 0.f;                                    // GCL: running row sum across column chunks
+      float xrun = 0.f;                                   // COORD: thread (r,dim) running sum
+      for (int c0 = 0; c0 < nc; c0 += ET) {
+        const int ncc = min(ET, nc - c0);
+        const int Et = nrt * ncc;
+        __syncthreads();                                  // previous tile fully consumed
+        for (int idx = tid; idx < ncc * H; idx += 256) {  // B rows of the live columns
+          int jj = idx >> 7, k = idx & (H - 1);
+          Bs[jj * LDB + k] = a.AB[(gb + cols[c0 + jj]) * 2 * H + H + k];
+        }
+        __syncthreads();
+        {                                                 // first layer + SiLU -> S1[k][e]
+          const int e = tid & (ET - 1), kh = tid >> 7;
+          const bool valid = e < Et;
+          int rr = 0, jj = 0;
+          float d = 0.f, d0 = 0.f;
+          if (valid) {
+            rr = e / ncc; jj = e - rr * ncc;
+            const int i = rows[r_begin + rt + rr], j = cols[c0 + jj];
+            const float* xi = a.x + (gb + i) * 3; const float* xj = a.x + (gb + j) * 3;
+            const float* yi = a.x0 + (gb + i) * 3; const float* yj = a.x0 + (gb + j) * 3;
+            float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+            d = dx * dx + dy * dy + dz * dz;
+            float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
+            d0 = ex * ex + ey * ey + ez * ez;
+            if (kh == 0) {
+              int ci = 0, cj = 0;
+              if (gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
+              ems[e] = edge_weight(gm.graph_type, em_mol, N, i, j, ci, cj, d0);
+              if (COORD) {
+                float inv = 1.0f / (sqrtf(d + 1e-8f) + gm.norm_constant);   // egnn.py:299-300
+                cds[e * 3 + 0] = dx * inv; cds[e * 3 + 1] = dy * inv; cds[e * 3 + 2] = dz * inv;
+              }
+            }
+          } else if (kh == 0) {
+            ems[e] = 0.f;
+            if (COORD) { cds[e * 3 + 0] = 0.f; cds[e * 3 + 1] = 0.f; cds[e * 3 + 2] = 0.f; }
+          }
+          const float* Ar = As + rr * H;
+          const float* Br = Bs + jj * LDB;
+#pragma unroll 8
+          for (int kk = 0; kk < H / 2; ++kk) {
+            int k = kh * (H / 2) + kk;
+            float pre = Ar[k] + Br[k] + d * wds[k] + d0 * w0s[k];
+            S1[k * ET + e] = valid ? silu_f(pre) : 0.f;
+          }
+        }
+        __syncthreads();
+        // 128x128x128 GEMM, 8x8 register tile
+        const int ty = tid >> 4, tx = tid & 15;
+        float acc[8][8];
+#pragma unroll
+        for (int p = 0; p < 8; ++p)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) acc[p][q] = 0.f;
+#pragma unroll 4
+        for (int k = 0; k < H; ++k) {
+          float4 a0 = *reinterpret_cast<const float4*>(S1 + k * ET + ty * 4);
+          float4 a1 = *reinterpret_cast<const float4*>(S1 + k * ET + 64 + ty * 4);
+          float4 b0 = *reinterpret_cast<const float4*>(W2s + k * H + tx * 4);
+          float4 b1 = *reinterpret_cast<const float4*>(W2s + k * H + 64 + tx * 4);
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+          for (int p = 0; p < 8; ++p)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[p][q] = fmaf(av[p], bv[q], acc[p][q]);
+        }
+        __syncthreads();                                  // S1 no longer read -> reuse as Outs[e][c]
+        float* Outs = S1;
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+          int e = (p < 4 ? ty * 4 + p : 64 + ty * 4 + (p - 4));
+          float w = COORD ? 1.f : ems[e];
+#pragma unroll
+          for (int qh = 0; qh < 2; ++qh) {
+            int c = qh * 64 + tx * 4;
+            float4 o;
+            o.x = silu_f(acc[p][qh * 4 + 0] + b2s[c + 0]) * w;
+            o.y = silu_f(acc[p][qh * 4 + 1] + b2s[c + 1]) * w;
+            o.z = silu_f(acc[p][qh * 4 + 2] + b2s[c + 2]) * w;
+            o.w = silu_f(acc[p][qh * 4 + 3] + b2s[c + 3]) * w;
+            *reinterpret_cast<float4*>(Outs + e * H + c) = o;
+          }
+        }
+        __syncthreads();
+        if (!COORD) {
+          // deterministic segment sum over j, thread = (row parity, channel)
+          const int c = tid & (H - 1);
+          if (nc <= ET) {
+            for (int rr = tid >> 7; rr < nrt; rr += 2) {
+              float s = 0.f;
+              for (int jj = 0; jj < ncc; ++jj) s += Outs[(rr * ncc + jj) * H + c];
+              a.agg[(gb + rows[r_begin + rt + rr]) * H + c] = s / gm.normalization_factor;
+            }
+          } else if (tid < H) {
+            for (int jj = 0; jj < ncc; ++jj) run += Outs[jj * H + c];
+            if (c0 + ET >= nc) a.agg[(gb + rows[r_begin + rt]) * H + c] = run / gm.normalization_factor;
+          }
+        } else {
+          for (int e = warp; e < Et; e += 8) {            // phi_e = w5 . m_e  (coord_mlp.4, egnn.py:90-97)
+            float s = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s = fmaf(Outs[e * H + lane + 32 * q], w5s[lane + 32 * q], s);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (lane == 0) phis[e] = s * ems[e];
+          }
+          __syncthreads();
+          if (tid < nrt * 3) {
+            int rr = tid / 3, dim = tid - rr * 3;
+            float s = 0.f;
+            for (int jj = 0; jj < ncc; ++jj) s += cds[(rr * ncc + jj) * 3 + dim] * phis[rr * ncc + jj];
+            xrun += s;
+            if (c0 + ET >= nc) {
+              int i = rows[r_begin + rt + rr];
+              float lm = a.linker_mask ? a.linker_mask[gb + i] : 1.f;
+              float xv = a.x[(gb + i) * 3 + dim];
+              a.x_out[(gb + i) * 3 + dim] = (xv + (xrun / gm.normalization_factor) * lm) * a.nm[gb + i];
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// Rows the coordinate update does not touch keep x (x is already masked: (x + 0)*nm == x).
+// Runs before k_edge<COORD> writes the updated rows into the same buffer.
+__global__ void k_copy_x(int n3, const float* __restrict__ src, float* __restrict__ dst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n3) dst[i] = src[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Output stage: EGNN.embedding_out (egnn.py:235-237), vel (egnn.py:420), slicing (430-435), NaN flags (441),
+// and -- in sampler mode -- the reverse-diffusion update of z fused in (edm.py:196-206 / 225-233).
+// 16 threads per node (one per output column), 16 nodes per CTA.
+// ------------------------------------------------------------------------------------------------
+struct FinishArgs {
+  const float* h;        // (B*N,128) final hidden state
+  const float* x;        // (B*N,3) final coordinates
+  const float* x0;       // (B*N,3)
+  const float* nm;
+  const float* Wo;       // [D][128] embedding_out.weight (first F rows used)
+  const float* bo;       // [D]
+  float* out;            // Dynamics.forward output (B*N,3+F) or null
+  int* nan_flags;        // (B) or null
+  // sampler mode
+  float* z;              // (B*N,3+F) in/out, null when not sampling
+  const float* fragment_mask; const float* linker_mask;
+  const float* noise;    // (T+2,B*N,3+F)
+  const float* coef;     // device table, 8 floats per row
+  const int* step_fin; int* step_prep;
+  int T;
+  float norm0, norm1, bias1;
+  float* chain;          // (keep,B*N,3+F)
+};
+
+__global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
+  const int tid = threadIdx.x;
+  const int d = tid & 15, r = tid >> 4;
+  const int n_total = gm.B * gm.N;
+  const int g = blockIdx.x * 16 + r;
+  const int xd = 3 + gm.F;
+  int step = 0;
+  if (a.z != nullptr) {
+    step = *a.step_fin;
+    if (blockIdx.x == 0 && tid == 0) *a.step_prep = step + 1;
+  }
+  const bool act = g < n_total && d < xd;
+  float e = 0.f;
+  if (act) {
+    float m = a.nm[g];
+    if (d < 3) {
+      e = (a.x[(size_t)g * 3 + d] - a.x0[(size_t)g * 3 + d]) * m;
+    } else {
+      const float* hr = a.h + (size_t)g * H;
+      const float* wr = a.Wo + (size_t)(d - 3) * H;
+      float s = 0.f;
+#pragma unroll 8
+      for (int k = 0; k < H; k += 4) {
+        float4 hv = *reinterpret_cast<const float4*>(hr + k);
+        float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
+        s = fmaf(hv.x, wv.x, s); s = fmaf(hv.y, wv.y, s); s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
+      }
+      e = (s + a.bo[d - 3]) * m;
+    }
+    if (e != e && a.nan_flags != nullptr) {
+      // bit0: NaN in vel, bit1: NaN in h (utils.py:274-282); bits 8.. = 1 + index of the first failing
+      // reverse step. Later steps do not add bits: the reference raises at the first failing step.
+      const int bits = d < 3 ? 1 : 2;
+      const int tag = (a.z != nullptr ? step + 1 : 0) << 8;
+      int* p = a.nan_flags + g / gm.N;
+      const int old = atomicCAS(p, 0, bits | tag);
+      if (old != 0 && (old & ~0xff) == tag) atomicOr(p, bits);
+    }
+    if (a.out != nullptr) a.out[(size_t)g * xd + d] = e;
+  }
+  if (a.z == nullptr) return;
+
+  const float* cf = a.coef + (size_t)step * 8;
+  const float ca = cf[1], cb = cf[2], cc = cf[3];
+  const int frame = __float_as_int(cf[4]);
+  float znew = 0.f;
+  float lm = 0.f, fm = 0.f;
+  if (act) {
+    lm = a.linker_mask[g]; fm = a.fragment_mask[g];
+    const float zt = a.z[(size_t)g * xd + d];
+    const float eps = e * lm;                                                 // edm.py:196 / 225
+    const float nz = a.noise[((size_t)(step + 1) * n_total + g) * xd + d] * lm;  // utils.py:189-192
+    if (step < a.T) {
+      float mu = zt / ca - cb * eps;                                          // edm.py:199
+      float zs = mu + cc * nz;                                                // edm.py:205, 342-345
+      znew = zt * fm + zs * lm;                                               // edm.py:206
+      a.z[(size_t)g * xd + d] = znew;
+      if (frame >= 0) {
+        float o = d < 3 ? znew * a.norm0 : znew * a.norm1 + a.bias1;          // edm.py:352-361
+        a.chain[((size_t)frame * n_total + g) * xd + d] = o;
+      }
+    } else {
+      float mux = ca * (zt - cb * eps);                                       // edm.py:241 (ca = 1/alpha_0)
+      float xo = mux + cc * nz;                                               // edm.py:228
+      znew = zt * fm + xo * lm;                                               // edm.py:229
+    }
+  }
+  if (step >= a.T) {
+    // edm.py:231-233: unnormalise, h = one_hot(argmax(h)) * node_mask. argmax over the 16-lane group.
+    float hv = (act && d >= 3) ? znew * a.norm1 + a.bias1 : -INFINITY;
+    int best = d;
+    float bv = hv;
+    const unsigned gmask = 0xffffffffu;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      float ov = __shfl_xor_sync(gmask, bv, o, 16);
+      int oi = __shfl_xor_sync(gmask, best, o, 16);
+      if (ov > bv || (ov == bv && oi < best)) { bv = ov; best = oi; }
+    }
+    if (act) {
+      float o = d < 3 ? znew * a.norm0 : ((d == best ? 1.f : 0.f) * a.nm[g]);
+      a.chain[(size_t)g * xd + d] = o;                                        // chain[0], edm.py:174
+    }
+  }
+}
+
+// z0 = xh*fragment_mask + (noise[0]*linker_mask)*linker_mask   (edm.py:136-137)
+__global__ void k_init_z(int n_total, int xd, const float* __restrict__ xh, const float* __restrict__ fm,
+                         const float* __restrict__ lm, const float* __restrict__ noise, float* __restrict__ z) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_total * xd) return;
+  int g = idx / xd;
+  float l = lm[g];
+  z[idx] = xh[idx] * fm[g] + (noise[idx] * l) * l;
+}
+
+}  // namespace dl

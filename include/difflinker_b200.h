@@ -1,0 +1,164 @@
+/*
+ * difflinker_b200 -- C-ABI of the B200-native DiffLinker denoising hot path.
+ *
+ * The reference (igashov/DiffLinker) is pure Python/PyTorch and has no FFI; the boundary this library
+ * replaces is the set of Python call sites listed below.  Every entry point is
+ * extern "C", takes plain pointers/sizes (no torch types), is stream-ordered and non-blocking unless
+ * stated, and returns a dl_status.  One engine per GPU, used from one host thread at a time.
+ *
+ *   reference interface (file:line)                      entry point here
+ *   ---------------------------------------------------  ------------------------------------------
+ *   Dynamics.__init__            src/egnn.py:324-372     dl_create / dl_destroy
+ *   Dynamics.load_state_dict     (ckpt keys)  dl_set_weight / dl_finalize_weights
+ *   Dynamics.forward             src/egnn.py:374-447     dl_dynamics_forward (+ _host)
+ *   DynamicsWithPockets.forward  src/egnn.py:471-552     dl_dynamics_forward with graph_type != DL_GRAPH_FC
+ *   EDM.sample_chain             src/edm.py:126-176      dl_sample_chain (+ _host)
+ *     sample_p_zs_given_zt_only_linker  edm.py:178-208
+ *     sample_p_xh_given_z0_only_linker  edm.py:210-235
+ *   InpaintingEDM.sample_chain   src/edm.py:549-612      dl_sample_chain with DL_SAMPLER_INPAINT
+ *   utils.FoundNaNException      src/utils.py:274-289    DL_NAN_DETECTED + per-molecule nan_flags
+ *
+ * Memory: all `const` device pointers are caller-owned and only read; outputs are caller-owned.
+ * Floats are fp32, masks int8 exactly as datasets.collate produces them (src/const.py:6-7,
+ * src/datasets.py:353-369: edge_mask values are {0,-1,-2}, self-loops live).
+ */
+#ifndef DIFFLINKER_B200_H_
+#define DIFFLINKER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dl_engine dl_engine; /* opaque */
+
+typedef enum dl_status {
+  DL_OK = 0,
+  DL_NAN_DETECTED = 1,        /* dynamics produced NaN: see nan_flags (bit0 = coordinates, bit1 = features) */
+  DL_ERR_INVALID = -1,        /* bad argument / unsupported configuration */
+  DL_ERR_CUDA = -2,           /* CUDA runtime error; dl_last_error() has the text */
+  DL_ERR_WEIGHTS = -3,        /* unknown / missing / wrongly sized weight */
+  DL_ERR_UNSUPPORTED = -4
+} dl_status;
+
+enum { DL_GRAPH_FC = 0, DL_GRAPH_4A = 1, DL_GRAPH_FC_4A = 2, DL_GRAPH_FC_10A_4A = 3 };
+enum { DL_EDGE_AUTO = 0, DL_EDGE_SIMT = 1, DL_EDGE_TCGEN05 = 2 };
+enum { DL_SAMPLER_LINKER = 0, DL_SAMPLER_INPAINT = 1 };
+
+/* Mirrors the kwargs of Dynamics.__init__ (src/egnn.py:324-329) that reach the hot path. */
+typedef struct dl_config {
+  int32_t n_dims;               /* 3 */
+  int32_t in_node_nf;           /* F: width of the atom-feature block of xh (one-hot [+ charge]) */
+  int32_t context_node_nf;      /* C */
+  int32_t hidden_nf;            /* H: must be 128 (every published config, configs/[all].yml `nf: 128`) */
+  int32_t n_layers;             /* L equivariant blocks */
+  int32_t inv_sublayers;        /* S GCLs per block */
+  int32_t condition_time;       /* 0/1 */
+  int32_t centering;            /* 0/1 (True only for inpainting models, lightning.py:99) */
+  int32_t graph_type;           /* DL_GRAPH_* */
+  int32_t device;               /* CUDA ordinal */
+  int32_t edge_impl;            /* DL_EDGE_*: AUTO = tcgen05 tensor-core path */
+  float norm_constant;          /* EquivariantBlock norm_constant (configs: 1e-6) */
+  float normalization_factor;   /* 100 */
+} dl_config;
+
+/* Per-reverse-step scalars, computed by the caller with the reference's own formulae
+ * (edm.py:369-403) so the device loop reproduces them bit-for-bit. Row r = 0..T-1 is reverse step
+ * s = T-1-r; row T is the final p(x,h|z0) step. */
+typedef struct dl_step_coef {
+  float t;          /* value of the time feature fed to the dynamics ((s+1)/T, or 0 for the last row) */
+  float a;          /* rows < T: alpha_{t|s}        ; row T: 1/alpha_0                         */
+  float b;          /* rows < T: sigma2_{t|s}/alpha_{t|s}/sigma_t ; row T: sigma_0             */
+  float c;          /* rows < T: sigma_{t|s}*sigma_s/sigma_t      ; row T: sigma_x = exp(gamma_0/2) */
+  int32_t frame;    /* chain frame this step is the LAST writer of ((s*keep)//T, edm.py:162), or -1 */
+  /* inpainting only (edm.py:650-670): q(z_s|z_t,x) on fragment atoms */
+  float qa;         /* alpha_{t|s}*sigma_s^2/sigma_t^2 */
+  float qb;         /* alpha_s*sigma2_{t|s}/sigma_t^2   */
+  float pad;
+} dl_step_coef;
+
+const char* dl_version(void);
+const char* dl_last_error(void);
+
+dl_status dl_create(const dl_config* cfg, dl_engine** out);
+dl_status dl_destroy(dl_engine* e);
+
+/* `name` is the reference state_dict key relative to the Dynamics module, e.g.
+ * "dynamics.e_block_0.gcl_1.edge_mlp.2.weight"; `data` is a HOST pointer to fp32 in the reference's
+ * own (out,in) row-major layout.  Blocking (copies immediately). */
+dl_status dl_set_weight(dl_engine* e, const char* name, const float* data, int64_t numel);
+/* Verifies that every parameter of the configured architecture was provided, repacks them for the
+ * kernels (k-major fp32 + fp16 hi/lo UMMA tiles) and uploads. Blocking. */
+dl_status dl_finalize_weights(dl_engine* e);
+/* Number of parameters (floats) the configured architecture expects; for load_state_dict checks. */
+int64_t dl_expected_param_count(const dl_engine* e);
+
+/*
+ * One Dynamics.forward (egnn.py:374-447 / 471-552). DEVICE pointers.
+ *   t          (t_numel) floats, t_numel == B or 1
+ *   xh         (B,N,3+F)
+ *   node_mask  (B,N) int8
+ *   linker_mask (B,N) fp32 or NULL (inpainting, edm.py:505,632)
+ *   edge_mask  FC graphs: (B*N*N) int8 or NULL (= all ones); pocket graphs: ignored (edges never cross
+ *              molecules here; the reference's batch-id vector egnn.py:557,573 is implied by the layout)
+ *   context    (B,N,C) fp32 or NULL when C == 0
+ *   out        (B,N,3+F)
+ *   nan_flags  (B) int32, written (not accumulated): bit0 NaN in vel, bit1 NaN in h; may be NULL
+ * Enqueued on `stream` (a cudaStream_t); returns immediately.
+ */
+dl_status dl_dynamics_forward(dl_engine* e, int32_t B, int32_t N, const float* t, int32_t t_numel, const float* xh,
+                              const int8_t* node_mask, const float* linker_mask, const int8_t* edge_mask,
+                              const float* context, float* out, int32_t* nan_flags, void* stream);
+
+/* Same with HOST buffers; copies in, runs, copies out, synchronises; returns DL_NAN_DETECTED if any
+ * nan_flags entry is non-zero (nan_flags, if given, is a host array of B int32). */
+dl_status dl_dynamics_forward_host(dl_engine* e, int32_t B, int32_t N, const float* t, int32_t t_numel,
+                                   const float* xh, const int8_t* node_mask, const float* linker_mask,
+                                   const int8_t* edge_mask, const float* context, float* out, int32_t* nan_flags);
+
+/*
+ * The whole reverse-diffusion loop (edm.py:126-235), on device, one CUDA-graph replay per step.
+ *   xh         (B,N,3+F) normalised input (x/norm0, (h-bias)/norm1), DEVICE
+ *   fragment_mask, linker_mask (B,N) fp32 DEVICE; node_mask (B,N) int8; edge_mask, context as above
+ *   noise      (T+2,B,N,3+F) UNMASKED standard normal draws, DEVICE: slab 0 initialises the linker,
+ *              slab 1+r feeds reverse step r, slab T+1 the final p(x|z0) draw -- i.e. the reference's
+ *              torch.randn call order (edm.py:328-345).  For DL_SAMPLER_INPAINT: (2T+3,...) slabs in the
+ *              order edm.py:565,577-592,605-610 consumes them.
+ *   coef       (T+1) dl_step_coef, HOST
+ *   norm       {norm_values[0], norm_values[1], norm_biases[1]} HOST (edm.py:347-355)
+ *   chain      (keep_frames,B,N,3+F) DEVICE out; chain[0] holds final x and one-hot h (edm.py:174)
+ *   nan_flags  (B) int32 DEVICE out: sticky bits as above, OR'ed with (first_nan_row+1)<<8
+ * Enqueued on `stream`; the caller synchronises and inspects nan_flags (FoundNaNException mapping).
+ */
+dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                          const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                          const float* linker_mask, const int8_t* edge_mask, const float* context,
+                          const float* noise, const dl_step_coef* coef, const float* norm, float* chain,
+                          int32_t* nan_flags, void* stream);
+
+/* HOST-buffer variant (pinned or pageable): H2D of all inputs incl. noise, loop, D2H of chain and flags,
+ * synchronises. Returns DL_NAN_DETECTED if any flag is set. */
+dl_status dl_sample_chain_host(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                               const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                               const float* linker_mask, const int8_t* edge_mask, const float* context,
+                               const float* noise, const dl_step_coef* coef, const float* norm, float* chain,
+                               int32_t* nan_flags);
+
+/* Instrumentation for bench.py: kernels launched by this engine since creation, and the device time (ms)
+ * of the most recent dl_sample_chain loop / dl_dynamics_forward measured with CUDA events on `stream`
+ * (valid after the stream has been synchronised). */
+int64_t dl_launch_count(const dl_engine* e);
+float dl_last_elapsed_ms(dl_engine* e);
+/* Average device time (ms, CUDA events on the engine's loop stream) of the dominant kernel -- the layer-0 GCL
+ * edge kernel -- relaunched `reps` times on the engine's current workspace (state of the last call; the
+ * caller's mask tensors of that call must still be alive). Blocking. Negative on error. For bench.py's roofline. */
+float dl_time_edge_kernel(dl_engine* e, int32_t reps);
+/* Self-test of the tcgen05 edge-MLP tile against the SIMT path on random data. Blocking.
+ * Returns DL_OK and writes the max abs/rel error. */
+dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFLINKER_B200_H_ */

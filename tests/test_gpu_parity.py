@@ -1,0 +1,241 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, via the reference-facing modules) against the golden vectors
+of the live reference and against the CPU oracle on the same seeded inputs.
+Tolerance (BASELINE.json north_star): 1e-4 relative fp32 on coordinates/features, atom types identical."""
+import math
+
+import pytest
+import torch
+
+from difflinker_b200 import FoundNaNException, synthetic
+from difflinker_b200.batching import collate, create_templates_for_linker_generation
+import dl_helpers as helpers
+from oracle import difflinker_oracle as orc
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-4
+
+DYN_CASES = ["dyn_small_fc", "dyn_small_fc_tscalar", "dyn_cfg1", "dyn_small_geom_anchors",
+             "dyn_small_pocket_FC-10A-4A", "dyn_small_pocket_FC-4A", "dyn_small_pocket_4A"]
+IMPLS = ["simt", "auto"]
+
+
+def dev():
+    assert torch.cuda.is_available()
+    return torch.device("cuda", 0)
+
+
+def rel_err(got, want):
+    return (got.double() - want.double()).abs().max().item() / max(want.double().abs().max().item(), 1e-30)
+
+
+def run_dyn(dyn, t, z, nm, lm, em, ctx, device):
+    mv = lambda v: None if v is None else v.to(device)
+    return dyn(mv(t), mv(z), mv(nm), mv(lm), mv(em), mv(ctx)).cpu()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", DYN_CASES)
+def test_dynamics_forward_matches_reference_golden(name, impl):
+    meta, a = helpers.load_golden(name)
+    spec = helpers.spec_by_name(meta["spec"])
+    dyn, hp = helpers.build_dynamics(spec, meta["seed"], edge_impl=impl)
+    assert helpers.state_sha(dyn.state_dict()) == meta["sha"]
+    out = run_dyn(dyn, a["t"], a["xh"], a["node_mask"], a["linker_mask"], a["edge_mask"], a["context"], dev())
+    assert out.shape == a["out"].shape
+    assert rel_err(out[..., :3], a["out"][..., :3]) <= REL_TOL
+    assert rel_err(out[..., 3:], a["out"][..., 3:]) <= REL_TOL
+    assert torch.equal(out * (1 - a["node_mask"].float()), torch.zeros_like(out))   # masked rows exactly zero
+
+
+@pytest.mark.parametrize("name", ["dyn_small_fc", "dyn_cfg1"])
+def test_host_buffer_entry_point_equals_device_entry_point(name):
+    meta, a = helpers.load_golden(name)
+    dyn, hp = helpers.build_dynamics(helpers.spec_by_name(meta["spec"]), meta["seed"])
+    on_dev = run_dyn(dyn, a["t"], a["xh"], a["node_mask"], a["linker_mask"], a["edge_mask"], a["context"], dev())
+    on_host = dyn(a["t"], a["xh"], a["node_mask"], a["linker_mask"], a["edge_mask"], a["context"])   # CPU tensors
+    assert not on_host.is_cuda and torch.equal(on_host, on_dev)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("name", ["chain_cfg1", "chain_cfg1_nsteps20"])
+def test_sample_chain_matches_reference_golden(name, impl):
+    meta, a = helpers.load_golden(name)
+    spec = helpers.spec_by_name(meta["spec"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"], edge_impl=impl)
+    ddpm.edm.T = meta["T"]
+    d = dev()
+    data = collate(synthetic.make_items(spec, batch=meta["batch"]))
+    tpl = create_templates_for_linker_generation(data, data['linker_mask'].sum(1).view(-1).int())
+    B, N = tpl['positions'].shape[:2]
+    noise = helpers.noise_tensor(meta["noise_seed"], meta["T"], B, N, spec.F)
+    from difflinker_b200 import utils
+    x = utils.remove_partial_mean_with_mask(tpl['positions'], tpl['atom_mask'], tpl['fragment_mask'])
+    mv = lambda v: v.to(d)
+    chain = ddpm.edm.sample_chain(x=mv(x), h=mv(tpl['one_hot']), node_mask=mv(tpl['atom_mask']),
+                                  fragment_mask=mv(tpl['fragment_mask']), linker_mask=mv(tpl['linker_mask']),
+                                  edge_mask=mv(tpl['edge_mask']), context=mv(tpl['fragment_mask']),
+                                  keep_frames=meta["keep_frames"], noise=mv(noise)).cpu()
+    want = a["chain"]
+    assert chain.shape == want.shape
+    assert torch.equal(chain[0][..., 3:], want[0][..., 3:]), "atom types differ"
+    lm = tpl['linker_mask']
+    assert rel_err(chain[0][..., :3] * lm, want[0][..., :3] * lm) <= REL_TOL
+    for f in range(1, meta["keep_frames"]):
+        assert rel_err(chain[f], want[f]) <= REL_TOL, f
+    # fragments pass through the sampler bit-identically (edm.py:137,206,229)
+    fm = tpl['fragment_mask']
+    assert torch.equal(chain[0][..., :3] * fm, x * fm)
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("spec_name,nb", [("cfg2_zinc_ragged", 8), ("cfg3_geom_ragged", 4)])
+def test_forward_at_config_shapes_vs_oracle(spec_name, nb, impl):
+    spec = synthetic.SPECS[spec_name]
+    dyn, hp = helpers.build_dynamics(spec, 0, edge_impl=impl)
+    batch = collate(synthetic.make_items(spec, batch=nb))
+    z, t = helpers.random_latent(batch, 5)
+    ctx = helpers.context_of(batch, spec)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'],
+                                    batch['linker_mask'], batch['edge_mask'], ctx)
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], ctx, dev())
+    assert rel_err(got[..., :3], want[..., :3]) <= REL_TOL
+    assert rel_err(got[..., 3:], want[..., 3:]) <= REL_TOL
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+@pytest.mark.parametrize("N,B,L", [(1, 2, 1), (2, 1, 1), (13, 3, 2), (150, 2, 1), (257, 1, 1)])
+def test_odd_shapes_vs_oracle(N, B, L, impl):
+    """N=1 (self loop only), N not a tile multiple, N > one 128-column chunk, N > 256."""
+    spec = synthetic.WorkloadSpec(f"odd{N}", B=B, N=N, n_min=max(1, N // 2), l_min=0, l_max=max(0, min(5, N - 1)),
+                                  F=8, L=L, T=4, seed=31)
+    g = torch.Generator().manual_seed(N)
+    items = []
+    for b in range(B):
+        n = N if b == 0 else max(1, N - 3 * b)
+        lk = min(n - 1, 1 + b) if n > 1 else 0
+        fm = torch.zeros(n); fm[:n - lk] = 1
+        items.append(dict(uuid=b, name=str(b), positions=2 * torch.randn((n, 3), generator=g),
+                          one_hot=torch.eye(8)[torch.randint(0, 8, (n,), generator=g)], anchors=torch.zeros(n),
+                          fragment_mask=fm, linker_mask=1 - fm, num_atoms=n))
+    batch = collate(items)
+    dyn, hp = helpers.build_dynamics(spec, 1, edge_impl=impl)
+    z, t = helpers.random_latent(batch, 9)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'],
+                                    batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'])
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    assert (got - want).abs().max().item() <= REL_TOL * max(want.abs().max().item(), 1e-3)
+
+
+def test_edge_mask_none_and_linker_mask_none():
+    """edge_mask=None -> every pair weighs 1 (egnn.py:58-59 skipped); linker_mask=None -> every row moves
+    (inpainting call sites, edm.py:505,632)."""
+    spec = helpers.EXTRA_SPECS["small_fc"]
+    dyn, hp = helpers.build_dynamics(spec, 4)
+    batch = collate(synthetic.make_items(spec))
+    z, t = helpers.random_latent(batch, 2, pad_garbage=False)
+    for em, lm in [(None, batch['linker_mask']), (batch['edge_mask'], None), (None, None)]:
+        with torch.no_grad():
+            want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'], lm, em,
+                                        batch['fragment_mask'])
+        got = run_dyn(dyn, t, z, batch['atom_mask'], lm, em, batch['fragment_mask'], dev())
+        assert rel_err(got, want) <= REL_TOL
+
+
+def test_fully_masked_molecule_and_empty_linker():
+    spec = helpers.EXTRA_SPECS["small_fc"]
+    dyn, hp = helpers.build_dynamics(spec, 4)
+    batch = collate(synthetic.make_items(spec))
+    batch['atom_mask'][1] = 0                                    # molecule 1 has no valid atoms at all
+    batch['edge_mask'] = batch['edge_mask'].view(spec.B, -1).clone()
+    batch['edge_mask'][1] = 0
+    batch['edge_mask'] = batch['edge_mask'].view(-1, 1)
+    batch['linker_mask'][2] = 0                                  # molecule 2 has no linker atoms
+    z, t = helpers.random_latent(batch, 3)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'],
+                                    batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'])
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    assert rel_err(got, want) <= REL_TOL
+    assert torch.equal(got[1], torch.zeros_like(got[1]))
+    assert torch.equal(got[2][..., :3], torch.zeros_like(got[2][..., :3]))   # nothing moves without linker rows
+
+
+def test_e3_equivariance():
+    """Rotating + translating the input rotates vel and leaves h invariant (coord2diff uses differences only)."""
+    spec = helpers.EXTRA_SPECS["small_fc"]
+    dyn, hp = helpers.build_dynamics(spec, 6)
+    batch = collate(synthetic.make_items(spec))
+    z, t = helpers.random_latent(batch, 8, pad_garbage=False)
+    g = torch.Generator().manual_seed(1)
+    q, _ = torch.linalg.qr(torch.randn(3, 3, generator=g))
+    if torch.det(q) < 0:
+        q[:, 0] = -q[:, 0]
+    z2 = z.clone()
+    z2[..., :3] = (z[..., :3] @ q.T + torch.tensor([1.5, -2.0, 0.7])) * batch['atom_mask'].float()
+    a = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    b = run_dyn(dyn, t, z2, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    assert (b[..., :3] - a[..., :3] @ q.T).abs().max().item() <= 2e-4 * max(a[..., :3].abs().max().item(), 1e-3)
+    assert rel_err(b[..., 3:], a[..., 3:]) <= 2e-4
+
+
+def test_nan_raises_found_nan_exception_with_indices():
+    spec = helpers.EXTRA_SPECS["small_fc"]
+    dyn, hp = helpers.build_dynamics(spec, 4)
+    batch = collate(synthetic.make_items(spec))
+    z, t = helpers.random_latent(batch, 3, pad_garbage=False)
+    z[1, 0, 0] = float('nan')                                    # poisons coordinates and, through d_ij, features
+    with pytest.raises(FoundNaNException) as ei:
+        run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    e = ei.value
+    assert (e.x_h_nan_idx | e.only_x_nan_idx | e.only_h_nan_idx) == {1}
+    # and the engine stays usable afterwards
+    z[1, 0, 0] = 0.0
+    out = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    assert torch.isfinite(out).all()
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_full_size_sampling_properties(impl):
+    """BASELINE configs[1] size (B=256, N=40, L=6) with a shortened chain: size-independent invariants."""
+    spec = synthetic.SPECS["cfg2_zinc_ragged"]
+    ddpm, hp = helpers.build_ddpm(spec, 0, edge_impl=impl, diffusion_steps=12)
+    d = dev()
+    ddpm = ddpm.to(d)
+    data = collate(synthetic.make_items(spec))
+    data = {k: (v.to(d) if torch.is_tensor(v) else v) for k, v in data.items()}
+    torch.manual_seed(123)
+    chain, node_mask = ddpm.sample_chain(data, keep_frames=4)
+    torch.manual_seed(123)
+    chain2, _ = ddpm.sample_chain(data, keep_frames=4)
+    assert chain.shape == (4, spec.B, spec.N, 3 + spec.F)                       # sample_trajectories.py:49-51
+    assert torch.equal(chain, chain2), "same torch seed must give the same sample (deterministic kernels)"
+    final = chain[0]
+    nm = node_mask.float()
+    assert torch.isfinite(chain).all()
+    assert torch.equal(final * (1 - nm), torch.zeros_like(final))               # utils.py:99-101
+    onehot = final[..., 3:]
+    assert torch.equal(onehot.sum(-1), nm.squeeze(-1)) and set(onehot.unique().tolist()) <= {0.0, 1.0}
+    fm = data['fragment_mask']
+    from difflinker_b200 import utils
+    x0 = utils.remove_partial_mean_with_mask(data['positions'], data['atom_mask'], fm)
+    assert torch.equal(final[..., :3] * fm, x0 * fm)                            # fragments untouched
+    assert torch.equal(final[..., 3:] * fm, data['one_hot'] * fm)
+    lm = data['linker_mask']
+    assert ((final[..., :3] * lm).abs().sum(dim=(1, 2)) > 0).all()              # every linker moved somewhere
+
+
+def test_full_size_forward_vs_oracle_sampled_molecules():
+    """Full B=256 launch on the GPU; the oracle checks a slice of molecules (they are independent)."""
+    spec = synthetic.SPECS["cfg2_zinc_ragged"]
+    dyn, hp = helpers.build_dynamics(spec, 0)
+    batch = collate(synthetic.make_items(spec))
+    z, t = helpers.random_latent(batch, 5)
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    idx = torch.tensor([0, 1, 77, 128, 255])
+    em = batch['edge_mask'].view(spec.B, -1)[idx].reshape(-1, 1)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t[idx], z[idx], batch['atom_mask'][idx],
+                                    batch['linker_mask'][idx], em, batch['fragment_mask'][idx])
+    assert rel_err(got[idx], want) <= REL_TOL

@@ -1,0 +1,141 @@
+"""CPU: the C-ABI library loads and exports what include/difflinker_b200.h declares; the Python mirrors keep the
+reference's interface (constructor kwargs, state_dict keys, exception attributes); sharding logic under gloo."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+import difflinker_b200
+from difflinker_b200 import _native, synthetic
+from difflinker_b200.distributed import batch_ids_for_rank, shard_range
+from difflinker_b200.utils import FoundNaNException
+import dl_helpers as helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "difflinker_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dl_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _native.load_library()
+    names = header_functions()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _native.SYMBOLS, f"{n} has no ctypes prototype"
+    assert b"sm_100a" in lib.dl_version()
+
+
+def test_state_dict_keys_and_param_count_match_reference_layout():
+    m, hp = helpers.build_ddpm(synthetic.SPECS["cfg2_zinc"], 0)
+    keys = list(m.state_dict().keys())
+    assert keys[0] == "edm.gamma.gamma"
+    assert "edm.dynamics.dynamics.embedding.weight" in keys
+    assert "edm.dynamics.dynamics.e_block_5.gcl_1.edge_mlp.2.weight" in keys
+    assert "edm.dynamics.dynamics.e_block_0.gcl_equiv.coord_mlp.4.weight" in keys
+    assert "edm.dynamics.dynamics.e_block_0.gcl_equiv.coord_mlp.4.bias" not in keys
+    sd = m.state_dict()
+    assert tuple(sd["edm.dynamics.dynamics.e_block_0.gcl_0.edge_mlp.0.weight"].shape) == (128, 258)
+    assert tuple(sd["edm.dynamics.dynamics.embedding.weight"].shape) == (128, 10)
+    n_dyn = sum(v.numel() for k, v in sd.items() if k.startswith("edm.dynamics."))
+    assert n_dyn + 501 == 1490815                                       # L=6, D=10, incl. gamma
+    assert sd["edm.gamma.gamma"].numel() == 501
+
+
+def test_unsupported_options_refuse_loudly():
+    with pytest.raises(NotImplementedError):
+        difflinker_b200.Dynamics(n_dims=3, in_node_nf=8, context_node_nf=1, hidden_nf=128, attention=True)
+    with pytest.raises(NotImplementedError):
+        difflinker_b200.Dynamics(n_dims=3, in_node_nf=8, context_node_nf=1, hidden_nf=128, model='gnn_dynamics')
+    with pytest.raises(NotImplementedError):
+        difflinker_b200.EDM(dynamics=None, in_node_nf=8, n_dims=3, noise_schedule='learned')
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_no_cpu_fallback_without_gpu():
+    dyn, hp = helpers.build_dynamics(helpers.EXTRA_SPECS["small_fc"], 0)
+    z = torch.zeros(1, 4, 11)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dyn(torch.zeros(1, 1), z, torch.ones(1, 4, 1), torch.ones(1, 4, 1), torch.ones(16, 1), torch.ones(1, 4, 1))
+
+
+def test_nan_exception_mapping():
+    e = FoundNaNException(flags=[0, 1, 2, 3 | (7 << 8), 1 | (9 << 8)])
+    assert e.x_h_nan_idx == {3} and e.only_x_nan_idx == {1, 4} and e.only_h_nan_idx == {2}
+    assert e.first_step == 6
+    x = torch.zeros(3, 2, 3); h = torch.zeros(3, 2, 8)
+    x[1, 0, 0] = float('nan'); h[1, 1, 1] = float('nan'); h[2, 0, 0] = float('nan')
+    e2 = FoundNaNException(x, h)
+    assert e2.x_h_nan_idx == {1} and e2.only_h_nan_idx == {2} and e2.only_x_nan_idx == set()
+
+
+def test_shard_helpers():
+    for n, w in [(10, 3), (8, 8), (3, 4), (0, 2)]:
+        spans = [shard_range(n, r, w) for r in range(w)]
+        assert spans[0][0] == 0 and spans[-1][1] == n
+        assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+        assert max(hi - lo for lo, hi in spans) - min(hi - lo for lo, hi in spans) <= 1
+    assert batch_ids_for_rank(7, 1, 3) == [1, 4]
+    assert sorted(sum((batch_ids_for_rank(7, r, 3) for r in range(3)), [])) == list(range(7))
+
+
+def test_weight_broadcast_world_size_2_gloo(tmp_path):
+    """N>1 path on CPU: rank 1 starts from different weights and must end up with rank 0's after the single
+    broadcast; per-rank batches are disjoint."""
+    script = tmp_path / "w.py"
+    script.write_text(f"""
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {ROOT!r} + '/tests')
+from difflinker_b200 import synthetic
+from difflinker_b200.distributed import broadcast_module_weights, batch_ids_for_rank
+import dl_helpers as helpers
+dist.init_process_group("gloo")
+rank = dist.get_rank()
+m, hp = helpers.build_ddpm(helpers.EXTRA_SPECS["small_fc"], seed=rank)
+n = broadcast_module_weights(m, src=0)
+sha = helpers.state_sha(m.state_dict())
+ref, _ = helpers.build_ddpm(helpers.EXTRA_SPECS["small_fc"], seed=0)
+assert sha == helpers.state_sha(ref.state_dict()), rank
+assert n == sum(p.numel() for p in m.parameters())
+ids = batch_ids_for_rank(5, rank, 2)
+gathered = [None, None]
+dist.all_gather_object(gathered, ids)
+assert sorted(gathered[0] + gathered[1]) == [0, 1, 2, 3, 4]
+dist.destroy_process_group()
+print("rank", rank, "ok")
+""")
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert res.stdout.count("ok") == 2
+
+
+def test_accelerate_swaps_reference_edm():
+    """Whole-loop drop-in: a *reference* DDPM (live reference, build container only) gets the native EDM with
+    the same weights; strict state_dict load proves the key layout."""
+    from oracle.ref_loader import load_reference, reference_available
+    if not reference_available():
+        pytest.skip("reference checkout not present on this machine")
+    ns = load_reference()
+    spec = helpers.EXTRA_SPECS["small_fc"]
+    hp = synthetic.model_hparams(spec)
+    torch.manual_seed(3)
+    ref = ns.lightning.DDPM(**hp, data_path=None, batch_size=2, lr=1e-4, torch_device='cpu', test_epochs=1,
+                            n_stability_samples=1)
+    ref.hparams = hp                                         # the Lightning stub has no save_hyperparameters
+    before = {k: v.clone() for k, v in ref.edm.state_dict().items()}
+    ref.edm.T = 7
+    out = difflinker_b200.accelerate(ref)
+    assert out is ref and isinstance(ref.edm, difflinker_b200.EDM) and ref.edm.T == 7
+    after = ref.edm.state_dict()
+    assert list(after.keys()) == list(before.keys())
+    assert all(torch.equal(after[k], before[k]) for k in before)

@@ -1,0 +1,110 @@
+"""CPU: the oracle restatement against the golden vectors produced by the live reference
+(oracle/make_golden.py), and the product's host-side mirrors against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from difflinker_b200 import batching, synthetic
+from difflinker_b200.noise import PredefinedNoiseSchedule
+from oracle import difflinker_oracle as orc
+import dl_helpers as helpers
+
+DYN_CASES = ["dyn_small_fc", "dyn_small_fc_tscalar", "dyn_cfg1", "dyn_small_geom_anchors",
+             "dyn_small_pocket_FC-10A-4A", "dyn_small_pocket_FC-4A", "dyn_small_pocket_4A"]
+
+
+@pytest.mark.parametrize("name", DYN_CASES)
+def test_oracle_dynamics_matches_reference_golden(name):
+    meta, a = helpers.load_golden(name)
+    spec = helpers.spec_by_name(meta["spec"])
+    dyn, hp = helpers.build_dynamics(spec, meta["seed"])
+    assert helpers.state_sha(dyn.state_dict()) == meta["sha"], "seeded weights differ from the fixture's"
+    with torch.no_grad():
+        out = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), a["t"], a["xh"], a["node_mask"],
+                                   a["linker_mask"], a["edge_mask"], a["context"])
+    # same torch ops in the same order as the reference: bit-exact on the same torch build, tight otherwise
+    assert (out - a["out"]).abs().max().item() <= 2e-6
+    assert torch.equal(out * (1 - a["node_mask"].float()), torch.zeros_like(out))  # utils.py:99-101
+
+
+@pytest.mark.parametrize("name", ["chain_cfg1", "chain_cfg1_nsteps20"])
+def test_oracle_chain_matches_reference_golden(name):
+    meta, a = helpers.load_golden(name)
+    spec = helpers.spec_by_name(meta["spec"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"])
+    assert helpers.state_sha(ddpm.edm.dynamics.state_dict()) == meta["sha"]
+    data = orc.collate_molecules(synthetic.make_items(spec, batch=meta["batch"]))
+    tpl = orc.linker_templates(data, data['linker_mask'].sum(1).view(-1).int())
+    x = orc.remove_partial_mean(tpl['positions'], tpl['atom_mask'], tpl['fragment_mask'])
+    gam = orc.gamma_table(hp['diffusion_noise_schedule'], hp['diffusion_steps'], hp['diffusion_noise_precision'])
+    with torch.no_grad():
+        chain = orc.edm_sample_chain(ddpm.edm.dynamics.state_dict(), helpers.oracle_cfg(hp), gam, meta["T"], x,
+                                     tpl['one_hot'], tpl['atom_mask'], tpl['fragment_mask'], tpl['linker_mask'],
+                                     tpl['edge_mask'], tpl['fragment_mask'], keep_frames=meta["keep_frames"],
+                                     norm_values=tuple(hp['normalize_factors']),
+                                     noise_fn=helpers.seeded_noise(meta["noise_seed"]))
+    assert chain.shape == a["chain"].shape                              # (keep_frames,B,N,3+F)
+    assert (chain - a["chain"]).abs().max().item() <= 5e-5
+    assert torch.equal(chain[0][:, :, 3:], a["chain"][0][:, :, 3:])     # atom types identical
+
+
+def test_gamma_tables_match_reference_golden():
+    _, a = helpers.load_golden("gamma_tables")
+    for key, ref in a.items():
+        sched, T, prec = key.split("__")
+        assert torch.equal(orc.gamma_table(sched, int(T), float(prec)), ref), key
+        assert torch.equal(PredefinedNoiseSchedule(sched, int(T), float(prec)).gamma.detach(), ref), key
+
+
+@pytest.mark.parametrize("name", ["chain_cfg1", "chain_cfg1_nsteps20"])
+def test_step_coefficients_match_reference_golden(name):
+    meta, a = helpers.load_golden(name)
+    spec = helpers.spec_by_name(meta["spec"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"])
+    ddpm.edm.T = meta["T"]                                              # --n_steps override, generate.py:103-104
+    rows = ddpm.edm.step_coefficients(meta["keep_frames"], meta["batch"])
+    got = np.array([[r.t, r.a, r.b, r.c] for r in rows], dtype=np.float32)
+    assert np.array_equal(got, a["coef"].numpy())
+    T, keep = meta["T"], meta["keep_frames"]
+    # frame bookkeeping (edm.py:162): every frame > 0 has exactly one last writer, frame 0 belongs to the final step
+    frames = [rows[r].frame for r in range(T)]
+    for f in range(1, keep):
+        writers = [T - 1 - r for r in range(T) if frames[r] == f]
+        assert writers == [min(s for s in range(T) if (s * keep) // T == f)]
+    assert all(f != 0 for f in frames) and rows[T].frame == -1
+
+
+@pytest.mark.parametrize("spec_name,nb", [("cfg1_plumbing", 4), ("cfg2_zinc_ragged", 6), ("cfg4_pockets", 2)])
+def test_batching_matches_oracle_contract(spec_name, nb):
+    spec = synthetic.SPECS[spec_name]
+    items = synthetic.make_items(spec, batch=nb)
+    mine, ora = batching.collate(items), orc.collate_molecules(items)
+    for k, v in ora.items():
+        if torch.is_tensor(v):
+            assert v.dtype == mine[k].dtype and torch.equal(v, mine[k]), k
+    assert mine['atom_mask'].dtype == torch.int8 and mine['edge_mask'].dtype == torch.int8
+    if not spec.pocket:
+        assert sorted(mine['edge_mask'].unique().tolist()) == [-2, -1, 0][-len(mine['edge_mask'].unique()):]
+        em = mine['edge_mask'].view(nb, spec.N, spec.N)
+        n0 = int(mine['atom_mask'][0].sum())
+        assert int(em[0].diagonal()[:n0].min()) == -2 and int(em[0].diagonal()[:n0].max()) == -2  # live self loops
+    sizes = mine['linker_mask'].sum(1).view(-1).int() + 2
+    mt = batching.create_templates_for_linker_generation(mine, sizes)
+    ot = orc.linker_templates(ora, sizes)
+    for k, v in ot.items():
+        if torch.is_tensor(v):
+            assert torch.equal(v, mt[k]), k
+    assert torch.equal(mt['linker_mask'].sum(1).view(-1).int(), sizes)
+
+
+def test_empty_linker_and_single_atom_edge_cases():
+    # a molecule whose requested linker size is 0 and a one-atom fragment still collate
+    items = [dict(uuid=0, name='a', positions=torch.randn(1, 3), one_hot=torch.eye(8)[:1], anchors=torch.ones(1),
+                  fragment_mask=torch.ones(1), linker_mask=torch.zeros(1), num_atoms=1),
+             dict(uuid=1, name='b', positions=torch.randn(4, 3), one_hot=torch.eye(8)[:4], anchors=torch.zeros(4),
+                  fragment_mask=torch.tensor([1., 1, 0, 0]), linker_mask=torch.tensor([0., 0, 1, 1]), num_atoms=4)]
+    b = batching.collate(items)
+    assert b['positions'].shape == (2, 4, 3) and b['edge_mask'].shape == (2 * 16, 1)
+    t = batching.create_templates_for_linker_generation(b, [0, 3])
+    assert t['positions'].shape == (2, 5, 3)
+    assert t['atom_mask'][0].sum() == 1 and t['atom_mask'][1].sum() == 5
