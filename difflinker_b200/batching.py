@@ -35,10 +35,10 @@ def collate(batch):
     bs, n = atom_mask.shape
     if "pocket_mask" in batch[0]:
         # pocket models: `edge_mask` carries the molecule index of every node (int8!) instead of a mask
-        out["edge_mask"] = torch.arange(bs, dtype=torch.int64).repeat_interleave(n).to(TORCH_INT)
+        out["edge_mask"] = torch.arange(bs, dtype=torch.int64, device=atom_mask.device).repeat_interleave(n).to(TORCH_INT)
     else:
         pair = atom_mask[:, None, :] * atom_mask[:, :, None]
-        pair = pair * (~torch.eye(n, dtype=TORCH_INT)).unsqueeze(0)
+        pair = pair * (~torch.eye(n, dtype=TORCH_INT, device=atom_mask.device)).unsqueeze(0)
         out["edge_mask"] = pair.view(bs * n * n, 1)
     for key in DATA_ATTRS_TO_ADD_LAST_DIM:
         if key in out:
