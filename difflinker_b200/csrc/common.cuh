@@ -27,6 +27,8 @@ struct GclW {
   const float* W4_t;   // [128][128]  node_mlp.2.weight^T
   const float* b4;     // [128]
   const void* W2_tc;   // fp16 hi/lo UMMA-canonical tiles of edge_mlp.2.weight (tcgen05 path)
+  float w2_descale;    // 1 / (power-of-two scale applied to W2_tc)
+  float wdmax, w0max;  // max|wd|, max|w0|: per-edge bound on the first-layer activations
 };
 
 // Packed weights of one EquivariantUpdate (src/egnn.py:90-97).
@@ -40,6 +42,8 @@ struct EqW {
   const float* b2;
   const float* w5;     // [128] coord_mlp.4.weight (no bias)
   const void* W2_tc;
+  float w2_descale;
+  float wdmax, w0max;
 };
 
 // First-layer projection of an edge MLP applied per node: A = h W1a^T + b1, B = h W1b^T.

@@ -41,7 +41,7 @@ namespace {
 struct Workspace {
   int B = 0, N = 0;
   float *nm = nullptr, *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *ABg = nullptr, *ABc = nullptr,
-        *agg = nullptr, *z = nullptr;
+        *agg = nullptr, *z = nullptr, *ABgmax = nullptr, *ABcmax = nullptr;
   int* cls = nullptr;
   int *rowidx = nullptr, *colidx = nullptr, *xrowidx = nullptr, *nr = nullptr, *nc = nullptr, *nxr = nullptr,
       *n_items = nullptr, *xmols = nullptr, *n_xmols = nullptr;
@@ -171,7 +171,7 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   dl_status s;
 #define WSA(field, cnt) if ((s = dev_alloc(ws, &ws.field, (cnt))) != DL_OK) return s
   WSA(nm, n); WSA(x0, n * 3); WSA(xa, n * 3); WSA(xb, n * 3); WSA(h, n * H); WSA(ABg, n * 2 * H); WSA(ABc, n * 2 * H);
-  WSA(agg, n * H); WSA(z, n * xd); WSA(cls, n);
+  WSA(agg, n * H); WSA(z, n * xd); WSA(cls, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
   WSA(rowidx, n); WSA(colidx, n); WSA(xrowidx, n); WSA(nr, B); WSA(nc, B); WSA(nxr, B); WSA(n_items, 1);
   WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(tile_ctr, 64);
 #undef WSA
@@ -262,7 +262,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   pa.node_mask = io.node_mask; pa.linker_mask = io.linker_mask;
   pa.t = io.t; pa.t_numel = io.t_numel; pa.context = io.context;
   pa.We_t = e->We_t; pa.be = e->be; pa.proj = proj_of(e->gcl[0]);
-  pa.nm = ws.nm; pa.x0 = ws.x0; pa.x = ws.xa; pa.cls = ws.cls; pa.h = ws.h; pa.AB = ws.ABg;
+  pa.nm = ws.nm; pa.x0 = ws.x0; pa.x = ws.xa; pa.cls = ws.cls; pa.h = ws.h; pa.AB = ws.ABg; pa.ABmax = ws.ABgmax;
   pa.coef = io.sampler ? e->coef_dev : nullptr;
   pa.step_prep = io.sampler ? e->step_ctr : nullptr;
   pa.step_fin = io.sampler ? e->step_ctr + 1 : nullptr;
@@ -278,7 +278,8 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     for (int s = 0; s < S; ++s) {
       const GclW& w = e->gcl[l * S + s];
       EdgeArgs ea{};
-      ea.AB = ws.ABg; ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+      ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
+      ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
       ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
       ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr;
       dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st);
@@ -287,10 +288,10 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       NodeArgs na{};
       na.h = ws.h; na.agg = ws.agg; na.nm = ws.nm; na.W3_t = w.W3_t; na.b3 = w.b3; na.W4_t = w.W4_t; na.b4 = w.b4;
       if (s + 1 < S) {
-        na.proj1 = proj_of(e->gcl[l * S + s + 1]); na.AB1 = ws.ABg; na.AB2 = nullptr;
+        na.proj1 = proj_of(e->gcl[l * S + s + 1]); na.AB1 = ws.ABg; na.ABmax1 = ws.ABgmax; na.AB2 = nullptr;
       } else {
-        na.proj1 = proj_of(e->eq[l]); na.AB1 = ws.ABc;
-        if (l + 1 < L) { na.proj2 = proj_of(e->gcl[(l + 1) * S]); na.AB2 = ws.ABg; }
+        na.proj1 = proj_of(e->eq[l]); na.AB1 = ws.ABc; na.ABmax1 = ws.ABcmax;
+        if (l + 1 < L) { na.proj2 = proj_of(e->gcl[(l + 1) * S]); na.AB2 = ws.ABg; na.ABmax2 = ws.ABgmax; }
         else na.AB2 = nullptr;
       }
       k_node<<<node_blocks, 256, node_smem, st>>>(n, na);
@@ -302,7 +303,8 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     e->launches += 1;
     const EqW& w = e->eq[l];
     EdgeArgs ea{};
-    ea.AB = ws.ABc; ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+    ea.AB = ws.ABc; ea.ABmax = ws.ABcmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
+    ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
     ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = w.w5;
     ea.plan = plan; ea.agg = nullptr; ea.x_out = xout;
     dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st);
@@ -447,7 +449,8 @@ dl_status dl_finalize_weights(dl_engine* e) {
   const int IN1 = 2 * H + 2;
   Packer pk;
   std::vector<__half> tcblob;
-  struct GOff { size_t W1a, W1b, b1, wd, w0, W2, b2, W3, b3, W4, b4, w5, tc; };
+  struct GOff { size_t W1a, W1b, b1, wd, w0, W2, b2, W3, b3, W4, b4, w5, tc; float descale, wdmax, w0max; };
+  auto absmax = [](const std::vector<float>& v) { float m = 0.f; for (float x : v) m = std::max(m, std::fabs(x)); return m; };
   std::vector<GOff> goff(L * S), eoff(L);
   auto R = [&](const std::string& k) -> const std::vector<float>& { return e->raw[k]; };
   size_t oWe = pk.add(transpose_block(R("dynamics.embedding.weight"), H, D, 0, D));
@@ -472,7 +475,8 @@ dl_status dl_finalize_weights(dl_engine* e) {
       o.b3 = pk.add(R(p + "node_mlp.0.bias"));
       o.W4 = pk.add(transpose_block(R(p + "node_mlp.2.weight"), H, H, 0, H));
       o.b4 = pk.add(R(p + "node_mlp.2.bias"));
-      o.tc = tc::pack_w2(R(p + "edge_mlp.2.weight"), tcblob);
+      o.tc = tc::pack_w2(R(p + "edge_mlp.2.weight"), tcblob, &o.descale);
+      o.wdmax = absmax(column(W1, H, IN1, 2 * H)); o.w0max = absmax(column(W1, H, IN1, 2 * H + 1));
     }
     snprintf(buf, sizeof(buf), "dynamics.e_block_%d.gcl_equiv.", l);
     std::string p(buf);
@@ -486,7 +490,8 @@ dl_status dl_finalize_weights(dl_engine* e) {
     o.W2 = pk.add(transpose_block(R(p + "coord_mlp.2.weight"), H, H, 0, H));
     o.b2 = pk.add(R(p + "coord_mlp.2.bias"));
     o.w5 = pk.add(R(p + "coord_mlp.4.weight"));
-    o.tc = tc::pack_w2(R(p + "coord_mlp.2.weight"), tcblob);
+    o.tc = tc::pack_w2(R(p + "coord_mlp.2.weight"), tcblob, &o.descale);
+    o.wdmax = absmax(column(W1, H, IN1, 2 * H)); o.w0max = absmax(column(W1, H, IN1, 2 * H + 1));
   }
   if (e->wblob) { cudaFree(e->wblob); e->wblob = nullptr; }
   if (e->wblob_tc) { cudaFree(e->wblob_tc); e->wblob_tc = nullptr; }
@@ -502,12 +507,12 @@ dl_status dl_finalize_weights(dl_engine* e) {
   for (int i = 0; i < L * S; ++i) {
     const GOff& o = goff[i];
     e->gcl[i] = GclW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0, base + o.W2, base + o.b2,
-                     base + o.W3,  base + o.b3,  base + o.W4, base + o.b4, tbase + o.tc};
+                     base + o.W3,  base + o.b3,  base + o.W4, base + o.b4, tbase + o.tc, o.descale, o.wdmax, o.w0max};
   }
   for (int l = 0; l < L; ++l) {
     const GOff& o = eoff[l];
     e->eq[l] = EqW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0,
-                   base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc};
+                   base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc, o.descale, o.wdmax, o.w0max};
   }
   e->finalized = true;
   return DL_OK;
@@ -708,7 +713,8 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   const Geom gm = make_geom(e, e->last_B, e->last_N);
   const GclW& w = e->gcl[0];
   EdgeArgs ea{};
-  ea.AB = ws.ABg; ea.x = ws.xa; ea.x0 = ws.x0; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+  ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
+  ea.x = ws.xa; ea.x0 = ws.x0; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
   ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr;
   cudaStream_t st = e->loop_stream;

@@ -117,8 +117,17 @@ __device__ __forceinline__ void zero_acc(float (&acc)[4][4]) {
 
 // A = hs W1a^T + b1 -> AB[:, 0:128];  B = hs W1b^T -> AB[:, 128:256]   (first Linear of an edge MLP,
 // split per SURVEY.md section 8(a) "verified restatement": egnn.py:45-50 / 103 with the concat distributed).
-__device__ __forceinline__ void project_ab(const float* hs_warp, const ProjW& pw, float* __restrict__ AB, int g0,
-                                           int n_total, int warp, int lane) {
+__device__ __forceinline__ float warp_absmax4(const float (&v)[4]) {
+  float m = fmaxf(fmaxf(fabsf(v[0]), fabsf(v[1])), fmaxf(fabsf(v[2]), fabsf(v[3])));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return m;
+}
+
+// ABmax[g] = (max_k |A[g][k]|, max_k |B[g][k]|): bounds the first-layer pre-activation of every edge, which the
+// tcgen05 path uses to pick an exact power-of-two scale that keeps its fp16 operands in range.
+__device__ __forceinline__ void project_ab(const float* hs_warp, const ProjW& pw, float* __restrict__ AB,
+                                           float* __restrict__ ABmax, int g0, int n_total, int warp, int lane) {
   float acc[4][4];
   zero_acc(acc);
   warp_gemm_4x4<H>(hs_warp, pw.W1a_t, lane, acc);
@@ -126,18 +135,24 @@ __device__ __forceinline__ void project_ab(const float* hs_warp, const ProjW& pw
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     int g = g0 + warp * 4 + r;
-    if (g < n_total)
-      *reinterpret_cast<float4*>(AB + (size_t)g * 2 * H + lane * 4) =
-          make_float4(acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w);
+    const float o[4] = {acc[r][0] + bb.x, acc[r][1] + bb.y, acc[r][2] + bb.z, acc[r][3] + bb.w};
+    const float mx = warp_absmax4(o);
+    if (g < n_total) {
+      *reinterpret_cast<float4*>(AB + (size_t)g * 2 * H + lane * 4) = make_float4(o[0], o[1], o[2], o[3]);
+      if (lane == 0) ABmax[(size_t)g * 2] = mx;
+    }
   }
   zero_acc(acc);
   warp_gemm_4x4<H>(hs_warp, pw.W1b_t, lane, acc);
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
     int g = g0 + warp * 4 + r;
-    if (g < n_total)
+    const float mx = warp_absmax4(acc[r]);
+    if (g < n_total) {
       *reinterpret_cast<float4*>(AB + (size_t)g * 2 * H + H + lane * 4) =
           make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+      if (lane == 0) ABmax[(size_t)g * 2 + 1] = mx;
+    }
   }
 }
 
@@ -160,6 +175,7 @@ struct PrepArgs {
   int* cls;                 // out (B*N) node class for pocket graphs: 0 invalid, 1 ligand, 2 pocket
   float* h;                 // out (B*N,128)
   float* AB;                // out (B*N,256)
+  float* ABmax;             // out (B*N,2)
   const float* coef;        // device dl_step_coef table (8 floats per row) or null
   const int* step_prep;     // device counter read here
   int* step_fin;            // device counter written here
@@ -246,7 +262,7 @@ __global__ void __launch_bounds__(256) k_prep(Geom gm, PrepArgs a) {
     }
   }
   __syncwarp();
-  project_ab(hs + warp * 4 * LDX, a.proj, a.AB, g0, n_total, warp, lane);
+  project_ab(hs + warp * 4 * LDX, a.proj, a.AB, a.ABmax, g0, n_total, warp, lane);
 }
 
 // GCL.node_model + node_mask (egnn.py:62-80), then the first-layer projections of whatever edge MLP
@@ -256,8 +272,8 @@ struct NodeArgs {
   const float* agg;     // (B*N,128)  sum_j m_ij*EM_ij / normalization_factor
   const float* nm;      // (B*N)
   const float* W3_t; const float* b3; const float* W4_t; const float* b4;
-  ProjW proj1; float* AB1;
-  ProjW proj2; float* AB2;  // AB2 == nullptr -> skip
+  ProjW proj1; float* AB1; float* ABmax1;
+  ProjW proj2; float* AB2; float* ABmax2;  // AB2 == nullptr -> skip
 };
 
 __global__ void __launch_bounds__(256) k_node(int n_total, NodeArgs a) {
@@ -310,8 +326,8 @@ __global__ void __launch_bounds__(256) k_node(int n_total, NodeArgs a) {
     }
   }
   __syncwarp();
-  project_ab(hs + warp * 4 * LDX, a.proj1, a.AB1, g0, n_total, warp, lane);
-  if (a.AB2 != nullptr) project_ab(hs + warp * 4 * LDX, a.proj2, a.AB2, g0, n_total, warp, lane);
+  project_ab(hs + warp * 4 * LDX, a.proj1, a.AB1, a.ABmax1, g0, n_total, warp, lane);
+  if (a.AB2 != nullptr) project_ab(hs + warp * 4 * LDX, a.proj2, a.AB2, a.ABmax2, g0, n_total, warp, lane);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -344,6 +360,8 @@ constexpr int LDB = H + 1;       // Bs row stride (bank-conflict-free column wal
 
 struct EdgeArgs {
   const float* AB;          // (B*N,256)
+  const float* ABmax;       // (B*N,2) row maxima of |A|, |B|
+  float w2_descale, wdmax, w0max;
   const float* x;           // (B*N,3) current coordinates
   const float* x0;          // (B*N,3) input coordinates (d0)
   const int8_t* edge_mask;  // (B*N*N) or null

@@ -1,16 +1,612 @@
-// tcgen05 edge kernel -- placeholder until the tensor-core path lands (next commit).
+// tcgen05 / TMEM edge kernel: the second Linear of every edge / coord MLP (85-91 % of the path's FLOPs,
+// SURVEY.md section 8(d)) on the 5th-generation tensor cores, fused with its producer (first Linear + SiLU) and its
+// consumer (bias + SiLU + edge weight + segment sum), so no per-edge tensor ever reaches HBM or L2.
+//
+// Numerics: fp32 operands are split into fp16 hi + lo (x = hi + lo, |lo| <= 2^-11 |x|) and the product is
+// accumulated as  W_hi s_hi + W_hi s_lo + W_lo s_hi  in fp32 TMEM accumulators ("3xFP16", ~2^-22 relative
+// per product) -- fp32-grade, which is what the 1e-4 end-to-end tolerance needs; plain bf16/tf32 operands
+// do not meet it.  Range: W is pre-scaled per matrix, and every edge's activation row per tile, by exact powers
+// of two chosen from a-priori bounds so that |operand| < 2^14 (fp16 tops out at 65504 and diverging samples do
+// exceed it); the combined descale is folded into the epilogue's first FMA, so scaling costs no accuracy.
+//
+// Layouts (no swizzle, K-major, canonical "interleave" form, cute/atom/mma_traits_sm100.hpp):
+//   operand tile in smem = [kc 0..15][row][8 halves]   (kc = 16-byte chunk along K=128)
+//   core matrix = 8 rows x 16 B contiguous (SBO = 128 B between 8-row groups, LBO = slab pitch between kc)
+// GCL  (swapped operands): D[c, e] = sum_k W2[c,k] s[e,k]  -> TMEM lane = output channel, column = edge;
+//        each epilogue thread owns one channel and walks the edges of a row sequentially, so the segment sum
+//        over j is an in-register, order-deterministic reduction (no shuffles, no atomics).
+// COORD (natural operands): D[e, c]: TMEM lane = edge, columns = channels; the thread reduces over channels
+//        with w5 in registers (coord_mlp.4), then a 3-wide segment sum through shared memory.
 #pragma once
 #include <cuda_fp16.h>
+
+#include <cmath>
+#include <cstdio>
 #include <vector>
+
 #include "../../include/difflinker_b200.h"
 #include "kernels_simt.cuh"
 
-namespace dl { namespace tc {
-constexpr int TN = 128;
-constexpr int MAXR = 8;
-constexpr bool AVAILABLE = false;
-inline dl_status configure() { return DL_OK; }
-inline size_t pack_w2(const std::vector<float>&, std::vector<__half>& blob) { return blob.size(); }
-inline dl_status launch_edge_tc(const Geom&, const EdgeArgs&, bool, const void*, int, cudaStream_t) { return DL_ERR_UNSUPPORTED; }
-inline dl_status selftest(int, float*, float*) { return DL_ERR_UNSUPPORTED; }
-}}
+namespace dl {
+namespace tc {
+
+constexpr bool AVAILABLE = true;
+constexpr int TN = 256;                    // edges per tile
+constexpr int MAXR = 32;                   // rows per tile
+constexpr int KC = 16;                     // 16-byte chunks per K=128 row of fp16
+constexpr int W_LBO = H * 16;              // 2048 B: W slab pitch
+constexpr int B_LBO = TN * 16 + 16;        // 4112 B: activation slab pitch (+16 B: conflict-free producer stores)
+constexpr int SBO = 128;
+constexpr int W_BYTES = KC * W_LBO;        // 32 KB per fp16 copy
+constexpr int B_BYTES = KC * B_LBO;        // 65,792 B per fp16 copy
+constexpr float F16_TARGET = 16384.0f;     // operands are scaled by exact powers of two to stay below 2^14
+
+// shared memory map (bytes from a 1024-aligned base)
+constexpr int OFF_WHI = 0;
+constexpr int OFF_WLO = OFF_WHI + W_BYTES;
+constexpr int OFF_BHI = OFF_WLO + W_BYTES;
+constexpr int OFF_BLO = OFF_BHI + B_BYTES;
+constexpr int OFF_TBL = OFF_BLO + B_BYTES;              // 2 x per-tile tables
+constexpr int TBL_ROWOFF = 0;                           // int  [TN]  AB offset (floats) of the edge's row node
+constexpr int TBL_COLOFF = TBL_ROWOFF + TN * 4;         // int  [TN]  AB offset of the column node's B half
+constexpr int TBL_D = TBL_COLOFF + TN * 4;              // f32  [TN]  |x_i-x_j|^2 of this block
+constexpr int TBL_D0 = TBL_D + TN * 4;                  // f32  [TN]  |x0_i-x0_j|^2 of the call's input
+constexpr int TBL_SC = TBL_D0 + TN * 4;                 // f32  [TN]  power-of-two scale of the edge's fp16 operand row
+constexpr int TBL_EM = TBL_SC + TN * 4;                 // f32x2[TN]  (edge weight, accumulator descale)
+constexpr int TBL_CD = TBL_EM + TN * 8;                 // f32  [TN][3] normalised difference (COORD)
+constexpr int TBL_ROWNODE = TBL_CD + TN * 12;           // int  [MAXR] node index of each tile row
+constexpr int TBL_BYTES = TBL_ROWNODE + MAXR * 4;
+constexpr int OFF_B2W5 = OFF_TBL + 2 * TBL_BYTES;       // float2 [128] (b2, w5)
+constexpr int OFF_TX = OFF_B2W5 + H * 8;                // f32 [TN][3] per-edge translation (COORD epilogue)
+constexpr int OFF_BAR = OFF_TX + TN * 12;               // mbarriers: w, mma[2]; tmem ptr
+constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;         // + alignment slack
+
+// ---------------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Bounded spin: a protocol bug must surface as a launch error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+  }
+  __trap();
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// 1-D bulk copy global -> shared through the TMA engine, completion on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+
+// Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
+// version=1 [46,48), layout_type=SWIZZLE_NONE [61,64).
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) |
+         (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor) for kind::f16: D=f32 [4,6)=1, A=B=f16 (0), both K-major,
+// N>>3 at [17,23), M>>4 at [24,29).
+__device__ __forceinline__ uint32_t umma_idesc(uint32_t M, uint32_t N) {
+  return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+#define TMEM_LD_X8(taddr, r)                                                                                   \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"                        \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) \
+               : "r"(taddr))
+#define TMEM_LD_X16(taddr, r)                                                                                    \
+  asm volatile(                                                                                                  \
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"   \
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),          \
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])     \
+      : "r"(taddr))
+__device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
+  uint32_t v;
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
+  return v;
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// fp32 -> fp16 hi/lo pair of two values
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __floats2half2_rn(a, b);
+  float2 back = __half22float2(h);
+  __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tile iteration: a CTA walks its work items (static round-robin) -> row groups -> 256-column chunks.
+// ---------------------------------------------------------------------------------------------------------
+struct Tile {
+  int b, nc, slot0, nrt, c0, ncc;
+  bool first_chunk, last_chunk;
+  const int* rows;
+};
+
+template <bool COORD>
+struct TileIter {
+  const Plan& plan;
+  int N, n_work, wi, rt, c0;
+  __device__ TileIter(const Plan& p, int N_) : plan(p), N(N_), wi(blockIdx.x), rt(0), c0(0) {
+    n_work = COORD ? *p.n_xmols : *p.n_items;
+  }
+  __device__ bool next(Tile& t) {
+    while (wi < n_work) {
+      int b, r_begin, r_count;
+      if (COORD) { b = plan.xmols[wi]; r_begin = 0; r_count = plan.nxr[b]; }
+      else { int4 it = plan.items[wi]; b = it.x; r_begin = it.y; r_count = it.z; }
+      const int nc = plan.nc[b];
+      int per = nc >= TN ? 1 : TN / nc;
+      if (per > MAXR) per = MAXR;
+      if (rt >= r_count || nc <= 0) { wi += gridDim.x; rt = 0; c0 = 0; continue; }
+      t.b = b; t.nc = nc; t.slot0 = r_begin + rt; t.nrt = min(per, r_count - rt);
+      t.c0 = c0; t.ncc = min(TN, nc - c0);
+      t.first_chunk = c0 == 0; t.last_chunk = c0 + TN >= nc;
+      t.rows = (COORD ? plan.xrowidx : plan.rowidx) + (size_t)b * N;
+      c0 += TN;
+      if (c0 >= nc) { c0 = 0; rt += per; }
+      return true;
+    }
+    return false;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// The kernel. 256 threads, 1 CTA / SM (persistent), all warps take every role in turn:
+//   tables(t) -> [wait MMA(t-1)] -> produce(t) -> issue MMA(t) (async, TMEM stage t&1) -> epilogue(t-1)
+// so the tensor core works on tile t while the SIMT/SFU pipes run the epilogue of tile t-1.
+// ---------------------------------------------------------------------------------------------------------
+template <bool COORD>
+__global__ void __launch_bounds__(256, 1) k_edge_tc(Geom gm, EdgeArgs a, const __half* __restrict__ w2tc) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = gm.N;
+
+  const uint32_t bar_w = sbase + OFF_BAR, bar_mma0 = sbase + OFF_BAR + 8;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 32);
+  float2* b2w5 = reinterpret_cast<float2*>(sm + OFF_B2W5);
+  float* txs = reinterpret_cast<float*>(sm + OFF_TX);
+
+  if (tid == 0) {
+    mbar_init(bar_w, 1);
+    mbar_init(bar_mma0, 1);
+    mbar_init(bar_mma0 + 8, 1);
+    fence_barrier_init();
+  }
+  if (tid < H) b2w5[tid] = make_float2(a.b2[tid], COORD ? a.w5[tid] : 0.f);
+  __syncthreads();
+  if (tid == 0) {                                      // W2 hi|lo tiles: one 64 KB TMA bulk copy
+    mbar_expect_tx(bar_w, 2 * W_BYTES);
+    bulk_g2s(sbase + OFF_WHI, w2tc, 2 * W_BYTES, bar_w);
+  }
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  // per-thread constants of the producer: this thread always owns k = kc*8 .. kc*8+7
+  const int kc = lane & 15, esub = lane >> 4;
+  float wdr[8], w0r[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) { wdr[q] = __ldg(a.wd + kc * 8 + q); w0r[q] = __ldg(a.w0 + kc * 8 + q); }
+
+  TileIter<COORD> iter(a.plan, N);
+  Tile cur, prev;
+  bool has_prev = false;
+  int t = 0;
+  float run = 0.f;       // GCL: row sum carried across column chunks (thread = channel); COORD: (row,dim) sum
+  bool w_ready = false;
+
+  auto epilogue = [&](const Tile& td, int buf, int stage) {
+    const uint8_t* tb = sm + OFF_TBL + buf * TBL_BYTES;
+    const float2* emds = reinterpret_cast<const float2*>(tb + TBL_EM);
+    const int* rownode = reinterpret_cast<const int*>(tb + TBL_ROWNODE);
+    const int q = warp & 3, hw = warp >> 2;
+    const size_t gb = (size_t)td.b * N;
+    if (!COORD) {
+      const int c = q * 32 + lane;
+      const float bias = b2w5[c].x;
+      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + stage * TN;
+      for (int rr = hw; rr < td.nrt; rr += 2) {
+        float acc = (td.nrt == 1 && !td.first_chunk) ? run : 0.f;
+        const int col0 = rr * td.ncc;
+        int jj = 0;
+        for (; jj + 8 <= td.ncc; jj += 8) {
+          uint32_t r[8];
+          TMEM_LD_X8(tlane + col0 + jj, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const float2 ed = emds[col0 + jj + u];
+            float m = silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias));
+            acc = fmaf(m, ed.x, acc);
+          }
+        }
+        for (; jj < td.ncc; ++jj) {
+          uint32_t r = tmem_ld_x1(tlane + col0 + jj);
+          tmem_ld_wait();
+          const float2 ed = emds[col0 + jj];
+          float m = silu_f(fmaf(__uint_as_float(r), ed.y, bias));
+          acc = fmaf(m, ed.x, acc);
+        }
+        if (td.nrt == 1) run = acc;
+        if (td.last_chunk) a.agg[(gb + rownode[rr]) * H + c] = acc / gm.normalization_factor;
+      }
+    } else {
+      const int Et = td.nrt * td.ncc;
+      const int e = hw * 128 + q * 32 + lane;
+      if (hw * 128 < Et) {                               // warp-uniform
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + stage * TN + hw * 128;
+        float phi = 0.f;
+        const float2 ed = emds[min(e, TN - 1)];
+#pragma unroll 1
+        for (int c0 = 0; c0 < H; c0 += 16) {
+          uint32_t r[16];
+          TMEM_LD_X16(tlane + c0, r);
+          tmem_ld_wait();
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float2 bw = b2w5[c0 + u];
+            phi = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bw.x)), bw.y, phi);
+          }
+        }
+        if (e < Et) {
+          const float* cd = reinterpret_cast<const float*>(tb + TBL_CD) + e * 3;
+          const float w = phi * ed.x;                    // egnn.py:107-109
+          txs[e * 3 + 0] = cd[0] * w; txs[e * 3 + 1] = cd[1] * w; txs[e * 3 + 2] = cd[2] * w;
+        }
+      }
+      __syncthreads();
+      if (tid < td.nrt * 3) {
+        const int rr = tid / 3, dim = tid - rr * 3;
+        float s = (td.nrt == 1 && !td.first_chunk) ? run : 0.f;
+        for (int jj = 0; jj < td.ncc; ++jj) s += txs[(rr * td.ncc + jj) * 3 + dim];
+        if (td.nrt == 1) run = s;
+        if (td.last_chunk) {
+          const int i = rownode[rr];
+          const float lm = a.linker_mask ? a.linker_mask[gb + i] : 1.f;
+          const float xv = a.x[(gb + i) * 3 + dim];
+          a.x_out[(gb + i) * 3 + dim] = (xv + (s / gm.normalization_factor) * lm) * a.nm[gb + i];   // egnn.py:110-124
+        }
+      }
+      __syncthreads();                                    // txs free for the next epilogue
+    }
+    tc_fence_before();
+  };
+
+  while (iter.next(cur)) {
+    const int buf = t & 1;
+    uint8_t* tb = sm + OFF_TBL + buf * TBL_BYTES;
+    const int Et = cur.nrt * cur.ncc;
+    const size_t gb = (size_t)cur.b * N;
+    // ---- per-edge tables -------------------------------------------------------------------------------
+    {
+      int* rowoff = reinterpret_cast<int*>(tb + TBL_ROWOFF);
+      int* coloff = reinterpret_cast<int*>(tb + TBL_COLOFF);
+      float* dv = reinterpret_cast<float*>(tb + TBL_D);
+      float* d0v = reinterpret_cast<float*>(tb + TBL_D0);
+      float* scv = reinterpret_cast<float*>(tb + TBL_SC);
+      float2* emds = reinterpret_cast<float2*>(tb + TBL_EM);
+      float* cds = reinterpret_cast<float*>(tb + TBL_CD);
+      int* rownode = reinterpret_cast<int*>(tb + TBL_ROWNODE);
+      const int e = tid;
+      if (e < Et) {
+        const int rr = e / cur.ncc, jj = e - rr * cur.ncc;
+        const int i = cur.rows[cur.slot0 + rr];
+        const int j = a.plan.colidx[gb + cur.c0 + jj];
+        const float* xi = a.x + (gb + i) * 3; const float* xj = a.x + (gb + j) * 3;
+        const float* yi = a.x0 + (gb + i) * 3; const float* yj = a.x0 + (gb + j) * 3;
+        const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+        const float d = dx * dx + dy * dy + dz * dz;                       // egnn.py:297-298
+        const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
+        const float d0 = ex * ex + ey * ey + ez * ez;                      // egnn.py:220
+        int ci = 0, cj = 0;
+        if (gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
+        rowoff[e] = (int)((gb + i) * 2 * H);
+        coloff[e] = (int)((gb + j) * 2 * H + H);
+        dv[e] = d; d0v[e] = d0;
+        // |silu(pre)| <= |pre| <= max|A_i| + max|B_j| + d max|wd| + d0 max|w0|: exact power-of-two scale that keeps
+        // the fp16 hi/lo operands of this edge below 2^14 (activations of diverging samples exceed fp16's 65504).
+        const float bound = a.ABmax[(gb + i) * 2] + a.ABmax[(gb + j) * 2 + 1] + d * a.wdmax + d0 * a.w0max;
+        float sc = 1.0f;
+        if (!(bound <= F16_TARGET)) {
+          const int ex = ((__float_as_int(bound) >> 23) & 0xff) - 127;
+          sc = __int_as_float(max(127 + 13 - ex, 1) << 23);
+        }
+        scv[e] = sc;
+        emds[e] = make_float2(edge_weight(gm.graph_type, a.edge_mask ? a.edge_mask + gb * N : nullptr, N, i, j, ci, cj, d0),
+                              a.w2_descale / sc);
+        if (COORD) {
+          const float inv = 1.0f / (sqrtf(d + 1e-8f) + gm.norm_constant);  // egnn.py:299-300
+          cds[e * 3 + 0] = dx * inv; cds[e * 3 + 1] = dy * inv; cds[e * 3 + 2] = dz * inv;
+        }
+      }
+      if (tid < cur.nrt) rownode[tid] = cur.rows[cur.slot0 + tid];
+    }
+    if (has_prev) mbar_wait(bar_mma0 + 8 * ((t - 1) & 1), ((t - 1) >> 1) & 1);   // MMA(t-1) done: B smem free
+    __syncthreads();
+    // ---- producer: first Linear + SiLU -> fp16 hi/lo operand tile -----------------------------------------
+    {
+      const int* rowoff = reinterpret_cast<const int*>(tb + TBL_ROWOFF);
+      const int* coloff = reinterpret_cast<const int*>(tb + TBL_COLOFF);
+      const float* dv = reinterpret_cast<const float*>(tb + TBL_D);
+      const float* d0v = reinterpret_cast<const float*>(tb + TBL_D0);
+      const float* scv = reinterpret_cast<const float*>(tb + TBL_SC);
+      uint8_t* bhi = sm + OFF_BHI + kc * B_LBO;
+      uint8_t* blo = sm + OFF_BLO + kc * B_LBO;
+#pragma unroll 2
+      for (int it = 0; it < TN / 16; ++it) {
+        const int e = 2 * (warp + 8 * it) + esub;
+        if (e < Et) {
+          const float* ap = a.AB + rowoff[e] + kc * 8;
+          const float* bp = a.AB + coloff[e] + kc * 8;
+          const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap)), a1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp)), b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+          const float d = dv[e], d0 = d0v[e], sc = scv[e];
+          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          float s[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) s[q] = silu_f(fmaf(d0, w0r[q], fmaf(d, wdr[q], av[q] + bv[q]))) * sc;   // egnn.py:49-50
+          uint4 hi, lo;
+          split2(s[0], s[1], hi.x, lo.x); split2(s[2], s[3], hi.y, lo.y);
+          split2(s[4], s[5], hi.z, lo.z); split2(s[6], s[7], hi.w, lo.w);
+          *reinterpret_cast<uint4*>(bhi + e * 16) = hi;
+          *reinterpret_cast<uint4*>(blo + e * 16) = lo;
+        }
+      }
+    }
+    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    // ---- MMA issue (one thread) --------------------------------------------------------------------------------
+    if (tid == 0) {
+      if (!w_ready) { mbar_wait(bar_w, 0); }
+      tc_fence_after();
+      const uint32_t whi = sbase + OFF_WHI, wlo = sbase + OFF_WLO, bhi = sbase + OFF_BHI, blo = sbase + OFF_BLO;
+      const int stage = t & 1;
+      if (!COORD) {
+        const uint32_t nmma = max(16, (Et + 15) & ~15);
+        const uint32_t idesc = umma_idesc(128, nmma);
+        const uint32_t dcol = tmem + stage * TN;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t a_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
+          const uint64_t b_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
+          umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
+          umma_f16(dcol, a_hi, b_lo, idesc, 1);
+          umma_f16(dcol, a_hi, b_hi, idesc, 1);
+        }
+      } else {
+        const uint32_t idesc = umma_idesc(128, 128);
+        for (int hh = 0; hh * 128 < Et; ++hh) {
+          const uint32_t dcol = tmem + stage * TN + hh * 128;
+          const uint32_t roff = hh * 128 * 16;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a_hi = umma_desc(bhi + roff + ks * 2 * B_LBO, B_LBO, SBO), a_lo = umma_desc(blo + roff + ks * 2 * B_LBO, B_LBO, SBO);
+            const uint64_t b_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), b_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
+            umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
+            umma_f16(dcol, a_hi, b_lo, idesc, 1);
+            umma_f16(dcol, a_hi, b_hi, idesc, 1);
+          }
+        }
+      }
+      umma_commit(bar_mma0 + 8 * stage);
+    }
+    w_ready = true;
+    // ---- epilogue of the previous tile (overlaps the MMA just issued) -------------------------------------------
+    if (has_prev) { tc_fence_after(); epilogue(prev, buf ^ 1, (t - 1) & 1); }
+    __syncthreads();              // tables[buf^1] may be rewritten by the next iteration
+    prev = cur; has_prev = true; ++t;
+  }
+  if (has_prev) {
+    mbar_wait(bar_mma0 + 8 * ((t - 1) & 1), ((t - 1) >> 1) & 1);
+    tc_fence_after();
+    epilogue(prev, (t - 1) & 1, (t - 1) & 1);
+  } else if (tid == 0) {
+    mbar_wait(bar_w, 0);          // never leave a bulk copy in flight behind an exiting CTA
+  }
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+inline dl_status configure() {
+  if (cudaFuncSetAttribute(k_edge_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_edge_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+    return DL_ERR_CUDA;
+  return DL_OK;
+}
+
+// edge_mlp.2 / coord_mlp.2 weight (out=128, in=128, row-major) -> [hi|lo][kc][out][8] fp16, scaled by the power of
+// two that puts max|W| in [2^13, 2^14). Returns the offset (in halves) inside `blob`; *descale = 1/scale.
+inline size_t pack_w2(const std::vector<float>& W, std::vector<__half>& blob, float* descale) {
+  while (blob.size() % 64) blob.push_back(__float2half(0.f));           // keep 128-byte alignment for the bulk copy
+  const size_t off = blob.size();
+  blob.resize(off + 2 * (size_t)KC * H * 8);
+  float mx = 0.f;
+  for (float v : W) mx = std::max(mx, std::fabs(v));
+  int ex = 0;
+  if (mx > 0.f && std::isfinite(mx)) { std::frexp(mx, &ex); ex -= 1; }   // mx in [2^ex, 2^(ex+1))
+  const int sh = std::min(std::max(13 - ex, -40), 40);
+  const float scale = std::ldexp(1.0f, sh);
+  *descale = std::ldexp(1.0f, -sh);
+  for (int kc = 0; kc < KC; ++kc)
+    for (int c = 0; c < H; ++c)
+      for (int u = 0; u < 8; ++u) {
+        const float v = W[(size_t)c * H + kc * 8 + u] * scale;
+        const __half hi = __float2half_rn(v);
+        const __half lo = __float2half_rn(v - __half2float(hi));
+        blob[off + ((size_t)kc * H + c) * 8 + u] = hi;
+        blob[off + (size_t)KC * H * 8 + ((size_t)kc * H + c) * 8 + u] = lo;
+      }
+  return off;
+}
+
+inline dl_status launch_edge_tc(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc, int num_sms,
+                                cudaStream_t st) {
+  const __half* w = reinterpret_cast<const __half*>(w2_tc);
+  if (coord) k_edge_tc<true><<<num_sms, 256, SMEM_BYTES, st>>>(gm, ea, w);
+  else k_edge_tc<false><<<num_sms, 256, SMEM_BYTES, st>>>(gm, ea, w);
+  return DL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Self test: one 128 x 256 x 128 3xFP16 UMMA chain against a CPU fp64 result. Exercises descriptors, the
+// canonical layout, TMEM addressing and the commit/wait protocol in isolation.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict__ A /*[2][kc][128][8]*/,
+                                                       const __half* __restrict__ Bm /*[2][kc][256][8]*/,
+                                                       float* __restrict__ D /*[128][256]*/) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar = sbase + OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 32);
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  // A -> W slots (pitch W_LBO), B -> activation slots (pitch B_LBO) with ordinary stores
+  for (int idx = tid; idx < 2 * KC * H; idx += 128) {
+    const int copy = idx / (KC * H), rem = idx % (KC * H), kcx = rem / H, row = rem % H;
+    *reinterpret_cast<uint4*>(sm + (copy ? OFF_WLO : OFF_WHI) + kcx * W_LBO + row * 16) =
+        *reinterpret_cast<const uint4*>(A + (size_t)idx * 8);
+  }
+  for (int idx = tid; idx < 2 * KC * TN; idx += 128) {
+    const int copy = idx / (KC * TN), rem = idx % (KC * TN), kcx = rem / TN, row = rem % TN;
+    *reinterpret_cast<uint4*>(sm + (copy ? OFF_BLO : OFF_BHI) + kcx * B_LBO + row * 16) =
+        *reinterpret_cast<const uint4*>(Bm + (size_t)idx * 8);
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc(128, 256);
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t a_hi = umma_desc(sbase + OFF_WHI + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(sbase + OFF_WLO + ks * 2 * W_LBO, W_LBO, SBO);
+      const uint64_t b_hi = umma_desc(sbase + OFF_BHI + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(sbase + OFF_BLO + ks * 2 * B_LBO, B_LBO, SBO);
+      umma_f16(tmem, a_lo, b_hi, idesc, ks > 0);
+      umma_f16(tmem, a_hi, b_lo, idesc, 1);
+      umma_f16(tmem, a_hi, b_hi, idesc, 1);
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < TN; c0 += 8) {
+    uint32_t r[8];
+    TMEM_LD_X8(tlane + c0, r);
+    tmem_ld_wait();
+    for (int u = 0; u < 8; ++u) D[(size_t)(warp * 32 + lane) * TN + c0 + u] = __uint_as_float(r[u]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_err) {
+  std::vector<float> A((size_t)H * H), Bv((size_t)TN * H);
+  uint32_t s = 12345u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : A) v = rnd() * 0.2f;
+  for (auto& v : Bv) v = rnd() * 3.0f;
+  auto pack = [&](const std::vector<float>& M, int rows) {
+    std::vector<__half> out(2 * (size_t)KC * rows * 8);
+    for (int kc = 0; kc < KC; ++kc)
+      for (int r = 0; r < rows; ++r)
+        for (int u = 0; u < 8; ++u) {
+          const float v = M[(size_t)r * H + kc * 8 + u];
+          const __half hi = __float2half_rn(v);
+          out[((size_t)kc * rows + r) * 8 + u] = hi;
+          out[(size_t)KC * rows * 8 + ((size_t)kc * rows + r) * 8 + u] = __float2half_rn(v - __half2float(hi));
+        }
+    return out;
+  };
+  std::vector<__half> Ap = pack(A, H), Bp = pack(Bv, TN);
+  __half *dA = nullptr, *dB = nullptr;
+  float* dD = nullptr;
+  if (cudaMalloc(&dA, Ap.size() * 2) != cudaSuccess || cudaMalloc(&dB, Bp.size() * 2) != cudaSuccess ||
+      cudaMalloc(&dD, (size_t)H * TN * 4) != cudaSuccess)
+    return DL_ERR_CUDA;
+  cudaMemcpy(dA, Ap.data(), Ap.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, Bp.data(), Bp.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, (size_t)H * TN * 4);
+  cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  k_umma_probe<<<1, 128, SMEM_BYTES>>>(dA, dB, dD);
+  cudaError_t err = cudaDeviceSynchronize();
+  std::vector<float> D((size_t)H * TN);
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  if (err != cudaSuccess) {
+    fprintf(stderr, "[dl selftest] k_umma_probe failed: %s\n", cudaGetErrorString(err));
+    return DL_ERR_CUDA;
+  }
+  double ma = 0, mr = 0, mref = 0;
+  for (int m = 0; m < H; ++m)
+    for (int n = 0; n < TN; ++n) {
+      double ref = 0;
+      for (int k = 0; k < H; ++k) ref += (double)A[(size_t)m * H + k] * (double)Bv[(size_t)n * H + k];
+      ma = std::max(ma, std::fabs(ref - (double)D[(size_t)m * TN + n]));
+      mref = std::max(mref, std::fabs(ref));
+    }
+  mr = ma / std::max(mref, 1e-30);
+  if (max_abs_err) *max_abs_err = (float)ma;
+  if (max_rel_err) *max_rel_err = (float)mr;
+  fprintf(stderr, "[dl selftest] 3xFP16 UMMA 128x256x128: max abs err %.3e (rel to max |ref| %.3e)\n", ma, mr);
+  return DL_OK;
+}
+
+}  // namespace tc
+}  // namespace dl

@@ -239,3 +239,28 @@ def test_full_size_forward_vs_oracle_sampled_molecules():
         want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t[idx], z[idx], batch['atom_mask'][idx],
                                     batch['linker_mask'][idx], em, batch['fragment_mask'][idx])
     assert rel_err(got[idx], want) <= REL_TOL
+
+
+def test_umma_selftest_3xfp16():
+    """tcgen05 building block in isolation: one 128x256x128 hi/lo-split UMMA chain vs fp64 on the host."""
+    import ctypes as C
+    from difflinker_b200 import _native
+    dyn, hp = helpers.build_dynamics(helpers.EXTRA_SPECS["small_fc"], 0)
+    eng = dyn.engine(0)
+    lib = _native.load_library()
+    ea, er = C.c_float(-1), C.c_float(-1)
+    st = lib.dl_selftest_tc(eng, C.byref(ea), C.byref(er))
+    assert st == 0, lib.dl_last_error()
+    assert 0 <= er.value < 2e-6, (ea.value, er.value)
+
+
+def test_simt_and_tcgen05_edge_paths_agree():
+    spec = synthetic.SPECS["cfg2_zinc_ragged"]
+    batch = collate(synthetic.make_items(spec, batch=16))
+    z, t = helpers.random_latent(batch, 5)
+    outs = {}
+    for impl in ("simt", "tcgen05"):
+        dyn, hp = helpers.build_dynamics(spec, 0, edge_impl=impl)
+        outs[impl] = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'],
+                             batch['fragment_mask'], dev())
+    assert rel_err(outs["tcgen05"], outs["simt"]) <= 2e-5
