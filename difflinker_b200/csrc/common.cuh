@@ -29,6 +29,10 @@ struct GclW {
   const void* W2_tc;   // fp16 hi/lo UMMA-canonical tiles of edge_mlp.2.weight (tcgen05 path)
   float w2_descale;    // 1 / (power-of-two scale applied to W2_tc)
   float wdmax, w0max;  // max|wd|, max|w0|: per-edge bound on the first-layer activations
+  const void* W1_tc;   // edge_mlp.0.weight[:, 0:2H] as two packed 128x128 fp16 hi/lo blocks (node kernel projections)
+  const void* W3_tc;   // node_mlp.0.weight as two packed blocks
+  const void* W4_tc;   // node_mlp.2.weight as one packed block
+  float w1_descale, w3_descale, w4_descale;
 };
 
 // Packed weights of one EquivariantUpdate (src/egnn.py:90-97).
@@ -44,6 +48,8 @@ struct EqW {
   const void* W2_tc;
   float w2_descale;
   float wdmax, w0max;
+  const void* W1_tc;   // coord_mlp.0.weight[:, 0:2H] as two packed blocks
+  float w1_descale;
 };
 
 // First-layer projection of an edge MLP applied per node: A = h W1a^T + b1, B = h W1b^T.

@@ -16,6 +16,7 @@
 #include "../../include/difflinker_b200.h"
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
+#include "kernels_node_tc.cuh"
 
 using namespace dl;
 
@@ -285,16 +286,39 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st);
       if (st2 != DL_OK) return st2;
 
-      NodeArgs na{};
-      na.h = ws.h; na.agg = ws.agg; na.nm = ws.nm; na.W3_t = w.W3_t; na.b3 = w.b3; na.W4_t = w.W4_t; na.b4 = w.b4;
-      if (s + 1 < S) {
-        na.proj1 = proj_of(e->gcl[l * S + s + 1]); na.AB1 = ws.ABg; na.ABmax1 = ws.ABgmax; na.AB2 = nullptr;
+      const bool last_sub = s + 1 >= S;
+      if (e->use_tc) {
+        tcn::NodeTcArgs ta{};
+        ta.h = ws.h; ta.agg = ws.agg; ta.nm = ws.nm;
+        ta.w3 = reinterpret_cast<const __half*>(w.W3_tc); ta.w4 = reinterpret_cast<const __half*>(w.W4_tc);
+        ta.b3 = w.b3; ta.b4 = w.b4; ta.w3_descale = w.w3_descale; ta.w4_descale = w.w4_descale;
+        if (!last_sub) {
+          const GclW& nx = e->gcl[l * S + s + 1];
+          ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[0] = nx.b1;
+          ta.p_descale[0] = nx.w1_descale; ta.AB[0] = ws.ABg; ta.ABmax[0] = ws.ABgmax;
+        } else {
+          const EqW& q = e->eq[l];
+          ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(q.W1_tc); ta.pb1[0] = q.b1;
+          ta.p_descale[0] = q.w1_descale; ta.AB[0] = ws.ABc; ta.ABmax[0] = ws.ABcmax;
+          if (l + 1 < L) {
+            const GclW& nx = e->gcl[(l + 1) * S];
+            ta.n_proj = 2; ta.pw[1] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[1] = nx.b1;
+            ta.p_descale[1] = nx.w1_descale; ta.AB[1] = ws.ABg; ta.ABmax[1] = ws.ABgmax;
+          }
+        }
+        tcn::k_node_tc<<<(n + tcn::TM - 1) / tcn::TM, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta);
       } else {
-        na.proj1 = proj_of(e->eq[l]); na.AB1 = ws.ABc; na.ABmax1 = ws.ABcmax;
-        if (l + 1 < L) { na.proj2 = proj_of(e->gcl[(l + 1) * S]); na.AB2 = ws.ABg; na.ABmax2 = ws.ABgmax; }
-        else na.AB2 = nullptr;
+        NodeArgs na{};
+        na.h = ws.h; na.agg = ws.agg; na.nm = ws.nm; na.W3_t = w.W3_t; na.b3 = w.b3; na.W4_t = w.W4_t; na.b4 = w.b4;
+        if (!last_sub) {
+          na.proj1 = proj_of(e->gcl[l * S + s + 1]); na.AB1 = ws.ABg; na.ABmax1 = ws.ABgmax; na.AB2 = nullptr;
+        } else {
+          na.proj1 = proj_of(e->eq[l]); na.AB1 = ws.ABc; na.ABmax1 = ws.ABcmax;
+          if (l + 1 < L) { na.proj2 = proj_of(e->gcl[(l + 1) * S]); na.AB2 = ws.ABg; na.ABmax2 = ws.ABgmax; }
+          else na.AB2 = nullptr;
+        }
+        k_node<<<node_blocks, 256, node_smem, st>>>(n, na);
       }
-      k_node<<<node_blocks, 256, node_smem, st>>>(n, na);
       LAUNCH_CHECK();
       e->launches += 1;
     }
@@ -392,7 +416,8 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaFuncSetAttribute(k_edge_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_edge_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   dl_status s = tc::configure();
-  if (s != DL_OK) { delete e; return s; }
+  if (s == DL_OK) s = tcn::configure_node();
+  if (s != DL_OK) { set_err("cudaFuncSetAttribute failed for the tcgen05 kernels"); delete e; return s; }
   *out = e;
   return DL_OK;
 }
@@ -449,7 +474,7 @@ dl_status dl_finalize_weights(dl_engine* e) {
   const int IN1 = 2 * H + 2;
   Packer pk;
   std::vector<__half> tcblob;
-  struct GOff { size_t W1a, W1b, b1, wd, w0, W2, b2, W3, b3, W4, b4, w5, tc; float descale, wdmax, w0max; };
+  struct GOff { size_t W1a, W1b, b1, wd, w0, W2, b2, W3, b3, W4, b4, w5, tc, tc1, tc3, tc4; float descale, wdmax, w0max, d1, d3, d4; };
   auto absmax = [](const std::vector<float>& v) { float m = 0.f; for (float x : v) m = std::max(m, std::fabs(x)); return m; };
   std::vector<GOff> goff(L * S), eoff(L);
   auto R = [&](const std::string& k) -> const std::vector<float>& { return e->raw[k]; };
@@ -476,6 +501,9 @@ dl_status dl_finalize_weights(dl_engine* e) {
       o.W4 = pk.add(transpose_block(R(p + "node_mlp.2.weight"), H, H, 0, H));
       o.b4 = pk.add(R(p + "node_mlp.2.bias"));
       o.tc = tc::pack_w2(R(p + "edge_mlp.2.weight"), tcblob, &o.descale);
+      o.tc1 = tcn::pack_blocks(W1, IN1, 2, tcblob, &o.d1);
+      o.tc3 = tcn::pack_blocks(R(p + "node_mlp.0.weight"), 2 * H, 2, tcblob, &o.d3);
+      o.tc4 = tcn::pack_blocks(R(p + "node_mlp.2.weight"), H, 1, tcblob, &o.d4);
       o.wdmax = absmax(column(W1, H, IN1, 2 * H)); o.w0max = absmax(column(W1, H, IN1, 2 * H + 1));
     }
     snprintf(buf, sizeof(buf), "dynamics.e_block_%d.gcl_equiv.", l);
@@ -491,6 +519,7 @@ dl_status dl_finalize_weights(dl_engine* e) {
     o.b2 = pk.add(R(p + "coord_mlp.2.bias"));
     o.w5 = pk.add(R(p + "coord_mlp.4.weight"));
     o.tc = tc::pack_w2(R(p + "coord_mlp.2.weight"), tcblob, &o.descale);
+    o.tc1 = tcn::pack_blocks(W1, IN1, 2, tcblob, &o.d1);
     o.wdmax = absmax(column(W1, H, IN1, 2 * H)); o.w0max = absmax(column(W1, H, IN1, 2 * H + 1));
   }
   if (e->wblob) { cudaFree(e->wblob); e->wblob = nullptr; }
@@ -507,12 +536,13 @@ dl_status dl_finalize_weights(dl_engine* e) {
   for (int i = 0; i < L * S; ++i) {
     const GOff& o = goff[i];
     e->gcl[i] = GclW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0, base + o.W2, base + o.b2,
-                     base + o.W3,  base + o.b3,  base + o.W4, base + o.b4, tbase + o.tc, o.descale, o.wdmax, o.w0max};
+                     base + o.W3,  base + o.b3,  base + o.W4, base + o.b4, tbase + o.tc, o.descale, o.wdmax, o.w0max,
+                     tbase + o.tc1, tbase + o.tc3, tbase + o.tc4, o.d1, o.d3, o.d4};
   }
   for (int l = 0; l < L; ++l) {
     const GOff& o = eoff[l];
     e->eq[l] = EqW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0,
-                   base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc, o.descale, o.wdmax, o.w0max};
+                   base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc, o.descale, o.wdmax, o.w0max, tbase + o.tc1, o.d1};
   }
   e->finalized = true;
   return DL_OK;
