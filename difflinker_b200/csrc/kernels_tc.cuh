@@ -31,35 +31,49 @@ namespace dl {
 namespace tc {
 
 constexpr bool AVAILABLE = true;
-constexpr int TN = 256;                    // edges per tile
+constexpr int TN = 128;                    // edges per tile (UMMA N for the GCL, UMMA M for the coord variant)
 constexpr int MAXR = 32;                   // rows per tile
 constexpr int KC = 16;                     // 16-byte chunks per K=128 row of fp16
 constexpr int W_LBO = H * 16;              // 2048 B: W slab pitch
-constexpr int B_LBO = TN * 16 + 16;        // 4112 B: activation slab pitch (+16 B: conflict-free producer stores)
+constexpr int B_LBO = TN * 16 + 16;        // 2064 B: activation slab pitch (+16 B: conflict-free producer stores)
 constexpr int SBO = 128;
 constexpr int W_BYTES = KC * W_LBO;        // 32 KB per fp16 copy
-constexpr int B_BYTES = KC * B_LBO;        // 65,792 B per fp16 copy
+constexpr int B_BYTES = KC * B_LBO;        // 33,024 B per fp16 copy
 constexpr float F16_TARGET = 16384.0f;     // operands are scaled by exact powers of two to stay below 2^14
+
+constexpr int N_STAGE = 2;                 // activation operand stages in shared memory
+constexpr int N_ACC = 4;                   // TMEM accumulator stages (4 x 128 columns) = table ring depth
+
+// warp roles of k_edge_tc (17 warps)
+constexpr int W_EPI = 0;                   // warps 0-3  : epilogue (warp % 4 = TMEM lane quarter)
+constexpr int W_MMA = 4;                   // warp  4    : MMA issuer (one thread), TMEM alloc/dealloc
+constexpr int W_TBL = 5;                   // warps 5-8  : per-edge table builders (run ahead of everyone)
+constexpr int W_PROD = 9;                  // warps 9-16 : producers (first Linear + SiLU -> fp16 operand tile)
+constexpr int N_PROD_WARPS = 8;
+constexpr int EDGE_TC_THREADS = 32 * (W_PROD + N_PROD_WARPS);   // 544
 
 // shared memory map (bytes from a 1024-aligned base)
 constexpr int OFF_WHI = 0;
 constexpr int OFF_WLO = OFF_WHI + W_BYTES;
-constexpr int OFF_BHI = OFF_WLO + W_BYTES;
-constexpr int OFF_BLO = OFF_BHI + B_BYTES;
-constexpr int OFF_TBL = OFF_BLO + B_BYTES;              // 2 x per-tile tables
-constexpr int TBL_ROWOFF = 0;                           // int  [TN]  AB offset (floats) of the edge's row node
-constexpr int TBL_COLOFF = TBL_ROWOFF + TN * 4;         // int  [TN]  AB offset of the column node's B half
-constexpr int TBL_D = TBL_COLOFF + TN * 4;              // f32  [TN]  |x_i-x_j|^2 of this block
-constexpr int TBL_D0 = TBL_D + TN * 4;                  // f32  [TN]  |x0_i-x0_j|^2 of the call's input
-constexpr int TBL_SC = TBL_D0 + TN * 4;                 // f32  [TN]  power-of-two scale of the edge's fp16 operand row
-constexpr int TBL_EM = TBL_SC + TN * 4;                 // f32x2[TN]  (edge weight, accumulator descale)
-constexpr int TBL_CD = TBL_EM + TN * 8;                 // f32  [TN][3] normalised difference (COORD)
-constexpr int TBL_ROWNODE = TBL_CD + TN * 12;           // int  [MAXR] node index of each tile row
+constexpr int OFF_ST = OFF_WLO + W_BYTES;                // N_STAGE x [hi | lo]
+constexpr int STAGE_BYTES = 2 * B_BYTES;
+constexpr int OFF_TBL = OFF_ST + N_STAGE * STAGE_BYTES;  // N_ACC x per-tile tables
+constexpr int TBL_HDR = 0;                               // int [16]: Et, nrt, ncc, flags(first|last<<1), gb_lo, gb_hi, end
+constexpr int TBL_ROWOFF = 64;                           // int  [TN]  AB offset (floats) of the edge's row node
+constexpr int TBL_COLOFF = TBL_ROWOFF + TN * 4;          // int  [TN]  AB offset of the column node's B half
+constexpr int TBL_D = TBL_COLOFF + TN * 4;               // f32  [TN]  |x_i-x_j|^2 of this block
+constexpr int TBL_D0 = TBL_D + TN * 4;                   // f32  [TN]  |x0_i-x0_j|^2 of the call's input
+constexpr int TBL_SC = TBL_D0 + TN * 4;                  // f32  [TN]  power-of-two scale of the edge's fp16 operand row
+constexpr int TBL_EM = TBL_SC + TN * 4;                  // f32x2[TN]  (edge weight, accumulator descale)
+constexpr int TBL_CD = TBL_EM + TN * 8;                  // f32  [TN][3] normalised difference (COORD)
+constexpr int TBL_ROWNODE = TBL_CD + TN * 12;            // int  [MAXR] node index of each tile row
 constexpr int TBL_BYTES = TBL_ROWNODE + MAXR * 4;
-constexpr int OFF_B2W5 = OFF_TBL + 2 * TBL_BYTES;       // float2 [128] (b2, w5)
-constexpr int OFF_TX = OFF_B2W5 + H * 8;                // f32 [TN][3] per-edge translation (COORD epilogue)
-constexpr int OFF_BAR = OFF_TX + TN * 12;               // mbarriers: w, mma[2]; tmem ptr
-constexpr int SMEM_BYTES = OFF_BAR + 64 + 1024;         // + alignment slack
+constexpr int OFF_B2W5 = OFF_TBL + N_ACC * TBL_BYTES;    // float2 [128] (b2, w5)
+constexpr int OFF_TX = OFF_B2W5 + H * 8;                 // f32 [TN][3] per-edge translation (COORD epilogue)
+constexpr int OFF_BAR = OFF_TX + TN * 12;                // mbarriers + tmem ptr
+constexpr int BAR_W = 0, BAR_FULL = 8, BAR_EMPTY = BAR_FULL + 8 * N_STAGE, BAR_TBL = BAR_EMPTY + 8 * N_STAGE,
+              BAR_TFULL = BAR_TBL + 8 * N_ACC, BAR_TEMPTY = BAR_TFULL + 8 * N_ACC, BAR_TMEMSLOT = BAR_TEMPTY + 8 * N_ACC;
+constexpr int SMEM_BYTES = OFF_BAR + BAR_TMEMSLOT + 16 + 1024;   // + alignment slack
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -86,6 +100,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (done) return;
   }
   __trap();
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void named_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -141,6 +161,11 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),          \
         "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])     \
       : "r"(taddr))
+#define TMEM_LD_X4(taddr, r) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" \
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr))
+#define TMEM_LD_X2(taddr, r) \
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0,%1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr))
 __device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
   uint32_t v;
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr));
@@ -156,9 +181,10 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   hi = *reinterpret_cast<uint32_t*>(&h);
   lo = *reinterpret_cast<uint32_t*>(&l);
 }
-
 // ---------------------------------------------------------------------------------------------------------
-// Tile iteration: a CTA walks its work items (static round-robin) -> row groups -> 256-column chunks.
+// Tile iteration (table warps only): a CTA walks its work items (static round-robin) -> row groups ->
+// 128-column chunks. A tile is whole rows x all live columns (or one row x a 128-column chunk when nc > 128), so
+// the segment sum over j never crosses CTAs.
 // ---------------------------------------------------------------------------------------------------------
 struct Tile {
   int b, nc, slot0, nrt, c0, ncc;
@@ -195,266 +221,327 @@ struct TileIter {
 };
 
 // ---------------------------------------------------------------------------------------------------------
-// The kernel. 256 threads, 1 CTA / SM (persistent), all warps take every role in turn:
-//   tables(t) -> [wait MMA(t-1)] -> produce(t) -> issue MMA(t) (async, TMEM stage t&1) -> epilogue(t-1)
-// so the tensor core works on tile t while the SIMT/SFU pipes run the epilogue of tile t-1.
+// The kernel: persistent, 1 CTA / SM, 17 warps in four roles connected by mbarrier rings.
+//
+//   table warps (4)  : walk the CTA's tile list; per edge (i,j): node offsets, d_ij, d0_ij, edge weight, operand
+//                      scale, normalised difference -> table ring slot a = t % 4          [tbl_full[a]]
+//   producers (8)    : A_i + B_j + d w_d + d0 w_0 -> SiLU -> fp16 hi/lo operand tile, stage s = t % 2
+//                      (register prefetch of the next item's A/B rows)                      [full[s]]
+//   MMA issuer (1 thr): 24 x tcgen05.mma (3xFP16, K=128) into TMEM accumulator a; commits     [empty[s], tfull[a]]
+//   epilogue (4)     : tcgen05.ld accumulator a, bias + SiLU + edge weight + segment sum        [tempty[a]]
+//
+// Every role works on a different tile at any moment, so L2 latency (producers), TMEM latency (epilogue) and
+// the tensor pipe overlap; the two SiLUs per edge-channel (MUFU) are the shared bottleneck by design.
 // ---------------------------------------------------------------------------------------------------------
 template <bool COORD>
-__global__ void __launch_bounds__(256, 1) k_edge_tc(Geom gm, EdgeArgs a, const __half* __restrict__ w2tc) {
+__global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArgs a, const __half* __restrict__ w2tc) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = gm.N;
 
-  const uint32_t bar_w = sbase + OFF_BAR, bar_mma0 = sbase + OFF_BAR + 8;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 32);
+  const uint32_t bars = sbase + OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + BAR_TMEMSLOT);
   float2* b2w5 = reinterpret_cast<float2*>(sm + OFF_B2W5);
-  float* txs = reinterpret_cast<float*>(sm + OFF_TX);
 
   if (tid == 0) {
-    mbar_init(bar_w, 1);
-    mbar_init(bar_mma0, 1);
-    mbar_init(bar_mma0 + 8, 1);
+    mbar_init(bars + BAR_W, 1);
+    for (int i = 0; i < N_STAGE; ++i) { mbar_init(bars + BAR_FULL + 8 * i, N_PROD_WARPS); mbar_init(bars + BAR_EMPTY + 8 * i, 1); }
+    for (int i = 0; i < N_ACC; ++i) {
+      mbar_init(bars + BAR_TBL + 8 * i, 4);
+      mbar_init(bars + BAR_TFULL + 8 * i, 1);
+      mbar_init(bars + BAR_TEMPTY + 8 * i, 4);
+    }
     fence_barrier_init();
   }
   if (tid < H) b2w5[tid] = make_float2(a.b2[tid], COORD ? a.w5[tid] : 0.f);
-  __syncthreads();
-  if (tid == 0) {                                      // W2 hi|lo tiles: one 64 KB TMA bulk copy
-    mbar_expect_tx(bar_w, 2 * W_BYTES);
-    bulk_g2s(sbase + OFF_WHI, w2tc, 2 * W_BYTES, bar_w);
-  }
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  // per-thread constants of the producer: this thread always owns k = kc*8 .. kc*8+7
-  const int kc = lane & 15, esub = lane >> 4;
-  float wdr[8], w0r[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) { wdr[q] = __ldg(a.wd + kc * 8 + q); w0r[q] = __ldg(a.w0 + kc * 8 + q); }
-
-  TileIter<COORD> iter(a.plan, N);
-  Tile cur, prev;
-  bool has_prev = false;
-  int t = 0;
-  float run = 0.f;       // GCL: row sum carried across column chunks (thread = channel); COORD: (row,dim) sum
-  bool w_ready = false;
-
-  auto epilogue = [&](const Tile& td, int buf, int stage) {
-    const uint8_t* tb = sm + OFF_TBL + buf * TBL_BYTES;
-    const float2* emds = reinterpret_cast<const float2*>(tb + TBL_EM);
-    const int* rownode = reinterpret_cast<const int*>(tb + TBL_ROWNODE);
-    const int q = warp & 3, hw = warp >> 2;
-    const size_t gb = (size_t)td.b * N;
-    if (!COORD) {
-      const int c = q * 32 + lane;
-      const float bias = b2w5[c].x;
-      const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + stage * TN;
-      for (int rr = hw; rr < td.nrt; rr += 2) {
-        float acc = (td.nrt == 1 && !td.first_chunk) ? run : 0.f;
-        const int col0 = rr * td.ncc;
-        int jj = 0;
-        for (; jj + 8 <= td.ncc; jj += 8) {
-          uint32_t r[8];
-          TMEM_LD_X8(tlane + col0 + jj, r);
-          tmem_ld_wait();
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float2 ed = emds[col0 + jj + u];
-            float m = silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias));
-            acc = fmaf(m, ed.x, acc);
+  if (warp >= W_TBL && warp < W_PROD) {
+    // =================================== table warps ===================================================================
+    const int e = (warp - W_TBL) * 32 + lane;            // one edge of the tile per thread
+    TileIter<COORD> iter(a.plan, N);
+    Tile cur;
+    for (int t = 0;; ++t) {
+      const int acc = t & (N_ACC - 1);
+      const bool more = iter.next(cur);
+      if (t >= N_ACC) mbar_wait(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1);   // slot's previous tile fully consumed
+      uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
+      int* hdr = reinterpret_cast<int*>(tb + TBL_HDR);
+      if (more) {
+        const int Et = cur.nrt * cur.ncc;
+        const size_t gb = (size_t)cur.b * N;
+        if (e == 0) {
+          hdr[0] = Et; hdr[1] = cur.nrt; hdr[2] = cur.ncc;
+          hdr[3] = (cur.first_chunk ? 1 : 0) | (cur.last_chunk ? 2 : 0);
+          hdr[4] = cur.b;
+        }
+        if (e < cur.nrt) reinterpret_cast<int*>(tb + TBL_ROWNODE)[e] = cur.rows[cur.slot0 + e];
+        if (e < Et) {
+          const int rr = e / cur.ncc, jj = e - rr * cur.ncc;
+          const int i = cur.rows[cur.slot0 + rr];
+          const int j = a.plan.colidx[gb + cur.c0 + jj];
+          const float* xi = a.x + (gb + i) * 3; const float* xj = a.x + (gb + j) * 3;
+          const float* yi = a.x0 + (gb + i) * 3; const float* yj = a.x0 + (gb + j) * 3;
+          const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+          const float d = dx * dx + dy * dy + dz * dz;                       // egnn.py:297-298
+          const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
+          const float d0 = ex * ex + ey * ey + ez * ez;                      // egnn.py:220
+          int ci = 0, cj = 0;
+          if (gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
+          reinterpret_cast<int*>(tb + TBL_ROWOFF)[e] = (int)((gb + i) * 2 * H);
+          reinterpret_cast<int*>(tb + TBL_COLOFF)[e] = (int)((gb + j) * 2 * H + H);
+          reinterpret_cast<float*>(tb + TBL_D)[e] = d;
+          reinterpret_cast<float*>(tb + TBL_D0)[e] = d0;
+          // |silu(pre)| <= |pre| <= max|A_i| + max|B_j| + d max|wd| + d0 max|w0|: exact power-of-two scale that keeps the
+          // fp16 hi/lo operands of this edge below 2^14 (activations of diverging samples exceed fp16's 65504).
+          const float bound = a.ABmax[(gb + i) * 2] + a.ABmax[(gb + j) * 2 + 1] + d * a.wdmax + d0 * a.w0max;
+          float sc = 1.0f;
+          if (!(bound <= F16_TARGET)) {
+            const int ex2 = ((__float_as_int(bound) >> 23) & 0xff) - 127;
+            sc = __int_as_float(max(127 + 13 - ex2, 1) << 23);
+          }
+          reinterpret_cast<float*>(tb + TBL_SC)[e] = sc;
+          reinterpret_cast<float2*>(tb + TBL_EM)[e] =
+              make_float2(edge_weight(gm.graph_type, a.edge_mask ? a.edge_mask + gb * N : nullptr, N, i, j, ci, cj, d0),
+                          a.w2_descale / sc);
+          if (COORD) {
+            const float inv = 1.0f / (sqrtf(d + 1e-8f) + gm.norm_constant);  // egnn.py:299-300
+            float* cds = reinterpret_cast<float*>(tb + TBL_CD);
+            cds[e * 3 + 0] = dx * inv; cds[e * 3 + 1] = dy * inv; cds[e * 3 + 2] = dz * inv;
           }
         }
-        for (; jj < td.ncc; ++jj) {
-          uint32_t r = tmem_ld_x1(tlane + col0 + jj);
-          tmem_ld_wait();
-          const float2 ed = emds[col0 + jj];
-          float m = silu_f(fmaf(__uint_as_float(r), ed.y, bias));
-          acc = fmaf(m, ed.x, acc);
-        }
-        if (td.nrt == 1) run = acc;
-        if (td.last_chunk) a.agg[(gb + rownode[rr]) * H + c] = acc / gm.normalization_factor;
+      } else if (e == 0) {
+        hdr[0] = 0;                                      // end marker travels through the whole pipeline
       }
-    } else {
-      const int Et = td.nrt * td.ncc;
-      const int e = hw * 128 + q * 32 + lane;
-      if (hw * 128 < Et) {                               // warp-uniform
-        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + stage * TN + hw * 128;
-        float phi = 0.f;
-        const float2 ed = emds[min(e, TN - 1)];
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + BAR_TBL + 8 * acc);
+      if (!more) break;
+    }
+  } else if (warp >= W_PROD) {
+    // =================================== producers =====================================================================
+    const int pw = warp - W_PROD;
+    const int kc = lane & 15, esub = lane >> 4;            // this thread always owns k = kc*8 .. kc*8+7
+    float wdr[8], w0r[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) { wdr[q] = __ldg(a.wd + kc * 8 + q); w0r[q] = __ldg(a.w0 + kc * 8 + q); }
+    for (int t = 0;; ++t) {
+      const int acc = t & (N_ACC - 1), s = t & (N_STAGE - 1);
+      mbar_wait(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1);
+      const uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
+      const int Et = reinterpret_cast<const int*>(tb + TBL_HDR)[0];
+      if (t >= N_STAGE) mbar_wait(bars + BAR_EMPTY + 8 * s, ((t - N_STAGE) / N_STAGE) & 1);   // MMA(t-2) has read this stage
+      if (Et > 0) {
+        const int* rowoff = reinterpret_cast<const int*>(tb + TBL_ROWOFF);
+        const int* coloff = reinterpret_cast<const int*>(tb + TBL_COLOFF);
+        const float* dv = reinterpret_cast<const float*>(tb + TBL_D);
+        const float* d0v = reinterpret_cast<const float*>(tb + TBL_D0);
+        const float* scv = reinterpret_cast<const float*>(tb + TBL_SC);
+        uint8_t* bhi = sm + OFF_ST + s * STAGE_BYTES + kc * B_LBO;
+        uint8_t* blo = bhi + B_BYTES;
+        constexpr int ITEMS = TN / (2 * N_PROD_WARPS);       // 8 edges per thread per tile
+        float4 pa0, pa1, pb0, pb1;                           // prefetched A_i / B_j chunks of the next item
+        {
+          const int e0 = min(2 * pw + esub, Et - 1);
+          const float* ap = a.AB + rowoff[e0] + kc * 8;
+          const float* bp = a.AB + coloff[e0] + kc * 8;
+          pa0 = __ldg(reinterpret_cast<const float4*>(ap)); pa1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+          pb0 = __ldg(reinterpret_cast<const float4*>(bp)); pb1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+        }
 #pragma unroll 1
-        for (int c0 = 0; c0 < H; c0 += 16) {
-          uint32_t r[16];
-          TMEM_LD_X16(tlane + c0, r);
-          tmem_ld_wait();
+        for (int it = 0; it < ITEMS; ++it) {
+          const int e = 2 * (pw + N_PROD_WARPS * it) + esub;
+          const float4 a0 = pa0, a1 = pa1, b0 = pb0, b1 = pb1;
+          if (it + 1 < ITEMS) {
+            const int en = min(e + 2 * N_PROD_WARPS, Et - 1);
+            const float* ap = a.AB + rowoff[en] + kc * 8;
+            const float* bp = a.AB + coloff[en] + kc * 8;
+            pa0 = __ldg(reinterpret_cast<const float4*>(ap)); pa1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+            pb0 = __ldg(reinterpret_cast<const float4*>(bp)); pb1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+          }
+          if (e < Et) {
+            const float d = dv[e], d0 = d0v[e], sc = scv[e];
+            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            float sv[8];
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const float2 bw = b2w5[c0 + u];
-            phi = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bw.x)), bw.y, phi);
+            for (int q = 0; q < 8; ++q) sv[q] = silu_f(fmaf(d0, w0r[q], fmaf(d, wdr[q], av[q] + bv[q]))) * sc;   // egnn.py:49-50
+            uint4 hi, lo;
+            split2(sv[0], sv[1], hi.x, lo.x); split2(sv[2], sv[3], hi.y, lo.y);
+            split2(sv[4], sv[5], hi.z, lo.z); split2(sv[6], sv[7], hi.w, lo.w);
+            *reinterpret_cast<uint4*>(bhi + e * 16) = hi;
+            *reinterpret_cast<uint4*>(blo + e * 16) = lo;
           }
         }
-        if (e < Et) {
-          const float* cd = reinterpret_cast<const float*>(tb + TBL_CD) + e * 3;
-          const float w = phi * ed.x;                    // egnn.py:107-109
-          txs[e * 3 + 0] = cd[0] * w; txs[e * 3 + 1] = cd[1] * w; txs[e * 3 + 2] = cd[2] * w;
-        }
+        fence_proxy_async();      // generic-proxy smem writes -> visible to the tensor core (async proxy)
       }
-      __syncthreads();
-      if (tid < td.nrt * 3) {
-        const int rr = tid / 3, dim = tid - rr * 3;
-        float s = (td.nrt == 1 && !td.first_chunk) ? run : 0.f;
-        for (int jj = 0; jj < td.ncc; ++jj) s += txs[(rr * td.ncc + jj) * 3 + dim];
-        if (td.nrt == 1) run = s;
-        if (td.last_chunk) {
-          const int i = rownode[rr];
-          const float lm = a.linker_mask ? a.linker_mask[gb + i] : 1.f;
-          const float xv = a.x[(gb + i) * 3 + dim];
-          a.x_out[(gb + i) * 3 + dim] = (xv + (s / gm.normalization_factor) * lm) * a.nm[gb + i];   // egnn.py:110-124
-        }
-      }
-      __syncthreads();                                    // txs free for the next epilogue
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + BAR_FULL + 8 * s);
+      if (Et <= 0) break;
     }
-    tc_fence_before();
-  };
-
-  while (iter.next(cur)) {
-    const int buf = t & 1;
-    uint8_t* tb = sm + OFF_TBL + buf * TBL_BYTES;
-    const int Et = cur.nrt * cur.ncc;
-    const size_t gb = (size_t)cur.b * N;
-    // ---- per-edge tables -------------------------------------------------------------------------------
-    {
-      int* rowoff = reinterpret_cast<int*>(tb + TBL_ROWOFF);
-      int* coloff = reinterpret_cast<int*>(tb + TBL_COLOFF);
-      float* dv = reinterpret_cast<float*>(tb + TBL_D);
-      float* d0v = reinterpret_cast<float*>(tb + TBL_D0);
-      float* scv = reinterpret_cast<float*>(tb + TBL_SC);
-      float2* emds = reinterpret_cast<float2*>(tb + TBL_EM);
-      float* cds = reinterpret_cast<float*>(tb + TBL_CD);
-      int* rownode = reinterpret_cast<int*>(tb + TBL_ROWNODE);
-      const int e = tid;
-      if (e < Et) {
-        const int rr = e / cur.ncc, jj = e - rr * cur.ncc;
-        const int i = cur.rows[cur.slot0 + rr];
-        const int j = a.plan.colidx[gb + cur.c0 + jj];
-        const float* xi = a.x + (gb + i) * 3; const float* xj = a.x + (gb + j) * 3;
-        const float* yi = a.x0 + (gb + i) * 3; const float* yj = a.x0 + (gb + j) * 3;
-        const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
-        const float d = dx * dx + dy * dy + dz * dz;                       // egnn.py:297-298
-        const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
-        const float d0 = ex * ex + ey * ey + ez * ez;                      // egnn.py:220
-        int ci = 0, cj = 0;
-        if (gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
-        rowoff[e] = (int)((gb + i) * 2 * H);
-        coloff[e] = (int)((gb + j) * 2 * H + H);
-        dv[e] = d; d0v[e] = d0;
-        // |silu(pre)| <= |pre| <= max|A_i| + max|B_j| + d max|wd| + d0 max|w0|: exact power-of-two scale that keeps
-        // the fp16 hi/lo operands of this edge below 2^14 (activations of diverging samples exceed fp16's 65504).
-        const float bound = a.ABmax[(gb + i) * 2] + a.ABmax[(gb + j) * 2 + 1] + d * a.wdmax + d0 * a.w0max;
-        float sc = 1.0f;
-        if (!(bound <= F16_TARGET)) {
-          const int ex = ((__float_as_int(bound) >> 23) & 0xff) - 127;
-          sc = __int_as_float(max(127 + 13 - ex, 1) << 23);
-        }
-        scv[e] = sc;
-        emds[e] = make_float2(edge_weight(gm.graph_type, a.edge_mask ? a.edge_mask + gb * N : nullptr, N, i, j, ci, cj, d0),
-                              a.w2_descale / sc);
-        if (COORD) {
-          const float inv = 1.0f / (sqrtf(d + 1e-8f) + gm.norm_constant);  // egnn.py:299-300
-          cds[e * 3 + 0] = dx * inv; cds[e * 3 + 1] = dy * inv; cds[e * 3 + 2] = dz * inv;
-        }
-      }
-      if (tid < cur.nrt) rownode[tid] = cur.rows[cur.slot0 + tid];
-    }
-    if (has_prev) mbar_wait(bar_mma0 + 8 * ((t - 1) & 1), ((t - 1) >> 1) & 1);   // MMA(t-1) done: B smem free
-    __syncthreads();
-    // ---- producer: first Linear + SiLU -> fp16 hi/lo operand tile -----------------------------------------
-    {
-      const int* rowoff = reinterpret_cast<const int*>(tb + TBL_ROWOFF);
-      const int* coloff = reinterpret_cast<const int*>(tb + TBL_COLOFF);
-      const float* dv = reinterpret_cast<const float*>(tb + TBL_D);
-      const float* d0v = reinterpret_cast<const float*>(tb + TBL_D0);
-      const float* scv = reinterpret_cast<const float*>(tb + TBL_SC);
-      uint8_t* bhi = sm + OFF_BHI + kc * B_LBO;
-      uint8_t* blo = sm + OFF_BLO + kc * B_LBO;
-#pragma unroll 2
-      for (int it = 0; it < TN / 16; ++it) {
-        const int e = 2 * (warp + 8 * it) + esub;
-        if (e < Et) {
-          const float* ap = a.AB + rowoff[e] + kc * 8;
-          const float* bp = a.AB + coloff[e] + kc * 8;
-          const float4 a0 = __ldg(reinterpret_cast<const float4*>(ap)), a1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
-          const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp)), b1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
-          const float d = dv[e], d0 = d0v[e], sc = scv[e];
-          const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-          float s[8];
-#pragma unroll
-          for (int q = 0; q < 8; ++q) s[q] = silu_f(fmaf(d0, w0r[q], fmaf(d, wdr[q], av[q] + bv[q]))) * sc;   // egnn.py:49-50
-          uint4 hi, lo;
-          split2(s[0], s[1], hi.x, lo.x); split2(s[2], s[3], hi.y, lo.y);
-          split2(s[4], s[5], hi.z, lo.z); split2(s[6], s[7], hi.w, lo.w);
-          *reinterpret_cast<uint4*>(bhi + e * 16) = hi;
-          *reinterpret_cast<uint4*>(blo + e * 16) = lo;
-        }
-      }
-    }
-    fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-    tc_fence_before();
-    __syncthreads();
-    // ---- MMA issue (one thread) --------------------------------------------------------------------------------
-    if (tid == 0) {
-      if (!w_ready) { mbar_wait(bar_w, 0); }
-      tc_fence_after();
-      const uint32_t whi = sbase + OFF_WHI, wlo = sbase + OFF_WLO, bhi = sbase + OFF_BHI, blo = sbase + OFF_BLO;
-      const int stage = t & 1;
-      if (!COORD) {
-        const uint32_t nmma = max(16, (Et + 15) & ~15);
-        const uint32_t idesc = umma_idesc(128, nmma);
-        const uint32_t dcol = tmem + stage * TN;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t a_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
-          const uint64_t b_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
-          umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
-          umma_f16(dcol, a_hi, b_lo, idesc, 1);
-          umma_f16(dcol, a_hi, b_hi, idesc, 1);
-        }
-      } else {
-        const uint32_t idesc = umma_idesc(128, 128);
-        for (int hh = 0; hh * 128 < Et; ++hh) {
-          const uint32_t dcol = tmem + stage * TN + hh * 128;
-          const uint32_t roff = hh * 128 * 16;
+  } else if (warp == W_MMA) {
+    // =================================== MMA issuer =====================================================================
+    if (lane == 0) {
+      mbar_expect_tx(bars + BAR_W, 2 * W_BYTES);           // W2 hi|lo tiles: one 64 KB TMA bulk copy, resident for the launch
+      bulk_g2s(sbase + OFF_WHI, w2tc, 2 * W_BYTES, bars + BAR_W);
+      mbar_wait(bars + BAR_W, 0);
+      const uint32_t whi = sbase + OFF_WHI, wlo = sbase + OFF_WLO;
+      for (int t = 0;; ++t) {
+        const int acc = t & (N_ACC - 1), s = t & (N_STAGE - 1);
+        mbar_wait(bars + BAR_FULL + 8 * s, (t / N_STAGE) & 1);
+        const int Et = reinterpret_cast<const int*>(sm + OFF_TBL + acc * TBL_BYTES + TBL_HDR)[0];
+        if (Et <= 0) { mbar_arrive(bars + BAR_TFULL + 8 * acc); break; }
+        if (t >= N_ACC) mbar_wait(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1);   // epilogue(t-4) drained this accumulator
+        tc_fence_after();
+        const uint32_t bhi = sbase + OFF_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
+        const uint32_t dcol = tmem + acc * TN;
+        if (!COORD) {
+          const uint32_t idesc = umma_idesc(128, max(16, (Et + 15) & ~15));
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t a_hi = umma_desc(bhi + roff + ks * 2 * B_LBO, B_LBO, SBO), a_lo = umma_desc(blo + roff + ks * 2 * B_LBO, B_LBO, SBO);
+            const uint64_t a_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
+            const uint64_t b_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
+            umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
+            umma_f16(dcol, a_hi, b_lo, idesc, 1);
+            umma_f16(dcol, a_hi, b_hi, idesc, 1);
+          }
+        } else {
+          const uint32_t idesc = umma_idesc(128, 128);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), a_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
             const uint64_t b_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), b_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
             umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
             umma_f16(dcol, a_hi, b_lo, idesc, 1);
             umma_f16(dcol, a_hi, b_hi, idesc, 1);
           }
         }
+        umma_commit(bars + BAR_EMPTY + 8 * s);             // operand stage reusable once these MMAs have read it
+        umma_commit(bars + BAR_TFULL + 8 * acc);           // accumulator ready for the epilogue
       }
-      umma_commit(bar_mma0 + 8 * stage);
     }
-    w_ready = true;
-    // ---- epilogue of the previous tile (overlaps the MMA just issued) -------------------------------------------
-    if (has_prev) { tc_fence_after(); epilogue(prev, buf ^ 1, (t - 1) & 1); }
-    __syncthreads();              // tables[buf^1] may be rewritten by the next iteration
-    prev = cur; has_prev = true; ++t;
+  } else {
+    // =================================== epilogue warps ==================================================================
+    const int q = warp & 3;                                // TMEM lane quarter of this warp
+    float* txs = reinterpret_cast<float*>(sm + OFF_TX);
+    float run = 0.f;   // GCL: row sum carried across column chunks (thread = channel); COORD: (row,dim) running sum
+    for (int t = 0;; ++t) {
+      const int acc = t & (N_ACC - 1);
+      mbar_wait(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1);
+      mbar_wait(bars + BAR_TFULL + 8 * acc, (t / N_ACC) & 1);
+      tc_fence_after();
+      const uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
+      const int* hdr = reinterpret_cast<const int*>(tb + TBL_HDR);
+      const int Et = hdr[0];
+      if (Et <= 0) break;
+      const int nrt = hdr[1], ncc = hdr[2];
+      const bool first_chunk = hdr[3] & 1, last_chunk = hdr[3] & 2;
+      const size_t gb = (size_t)hdr[4] * N;
+      const float2* emds = reinterpret_cast<const float2*>(tb + TBL_EM);
+      const int* rownode = reinterpret_cast<const int*>(tb + TBL_ROWNODE);
+      if (!COORD) {
+        const int c = q * 32 + lane;
+        const float bias = b2w5[c].x;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + acc * TN;
+        for (int rr = 0; rr < nrt; ++rr) {
+          float accv = (nrt == 1 && !first_chunk) ? run : 0.f;
+          const int col0 = rr * ncc;
+          int jj = 0;
+          for (; jj + 16 <= ncc; jj += 16) {
+            uint32_t r[16];
+            TMEM_LD_X16(tlane + col0 + jj, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float2 ed = emds[col0 + jj + u];
+              accv = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+            }
+          }
+          if (ncc - jj >= 8) {
+            uint32_t r[8];
+            TMEM_LD_X8(tlane + col0 + jj, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float2 ed = emds[col0 + jj + u];
+              accv = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+            }
+            jj += 8;
+          }
+          if (ncc - jj >= 4) {
+            uint32_t r[4];
+            TMEM_LD_X4(tlane + col0 + jj, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float2 ed = emds[col0 + jj + u];
+              accv = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+            }
+            jj += 4;
+          }
+          for (; jj < ncc; ++jj) {
+            const uint32_t r = tmem_ld_x1(tlane + col0 + jj);
+            tmem_ld_wait();
+            const float2 ed = emds[col0 + jj];
+            accv = fmaf(silu_f(fmaf(__uint_as_float(r), ed.y, bias)), ed.x, accv);
+          }
+          if (nrt == 1) run = accv;
+          if (last_chunk) a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + BAR_TEMPTY + 8 * acc);
+      } else {
+        const int e = q * 32 + lane;
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + acc * TN;
+        if (q * 32 < Et) {                                 // warp-uniform
+          const float2 ed = emds[min(e, Et - 1)];
+          float phi = 0.f;
+#pragma unroll 1
+          for (int c0 = 0; c0 < H; c0 += 16) {
+            uint32_t r[16];
+            TMEM_LD_X16(tlane + c0, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 16; ++u) {
+              const float2 bw = b2w5[c0 + u];
+              phi = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bw.x)), bw.y, phi);       // coord_mlp.2 + .4
+            }
+          }
+          if (e < Et) {
+            const float* cd = reinterpret_cast<const float*>(tb + TBL_CD) + e * 3;
+            const float w = phi * ed.x;                    // egnn.py:107-109
+            txs[e * 3 + 0] = cd[0] * w; txs[e * 3 + 1] = cd[1] * w; txs[e * 3 + 2] = cd[2] * w;
+          }
+        }
+        tc_fence_before();
+        named_sync(2, 128);                                // all four epilogue warps: txs complete
+        const int et = warp * 32 + lane;                   // epilogue-group thread id 0..127
+        if (et < nrt * 3) {
+          const int rr = et / 3, dim = et - rr * 3;
+          float sacc = (nrt == 1 && !first_chunk) ? run : 0.f;
+          for (int jj = 0; jj < ncc; ++jj) sacc += txs[(rr * ncc + jj) * 3 + dim];
+          if (nrt == 1) run = sacc;
+          if (last_chunk) {
+            const int i = rownode[rr];
+            const float lm = a.linker_mask ? a.linker_mask[gb + i] : 1.f;
+            const float xv = a.x[(gb + i) * 3 + dim];
+            a.x_out[(gb + i) * 3 + dim] = (xv + (sacc / gm.normalization_factor) * lm) * a.nm[gb + i];   // egnn.py:110-124
+          }
+        }
+        named_sync(2, 128);                                // txs and the table slot may be reused
+        if (lane == 0) mbar_arrive(bars + BAR_TEMPTY + 8 * acc);
+      }
+    }
   }
-  if (has_prev) {
-    mbar_wait(bar_mma0 + 8 * ((t - 1) & 1), ((t - 1) >> 1) & 1);
-    tc_fence_after();
-    epilogue(prev, (t - 1) & 1, (t - 1) & 1);
-  } else if (tid == 0) {
-    mbar_wait(bar_w, 0);          // never leave a bulk copy in flight behind an exiting CTA
-  }
+  tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 512);
+  if (warp == W_MMA) tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -495,8 +582,8 @@ inline size_t pack_w2(const std::vector<float>& W, std::vector<__half>& blob, fl
 inline dl_status launch_edge_tc(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc, int num_sms,
                                 cudaStream_t st) {
   const __half* w = reinterpret_cast<const __half*>(w2_tc);
-  if (coord) k_edge_tc<true><<<num_sms, 256, SMEM_BYTES, st>>>(gm, ea, w);
-  else k_edge_tc<false><<<num_sms, 256, SMEM_BYTES, st>>>(gm, ea, w);
+  if (coord) k_edge_tc<true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w);
+  else k_edge_tc<false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w);
   return DL_OK;
 }
 
@@ -504,6 +591,10 @@ inline dl_status launch_edge_tc(const Geom& gm, const EdgeArgs& ea, bool coord, 
 // Self test: one 128 x 256 x 128 3xFP16 UMMA chain against a CPU fp64 result. Exercises descriptors, the
 // canonical layout, TMEM addressing and the commit/wait protocol in isolation.
 // ---------------------------------------------------------------------------------------------------------
+constexpr int PN = 256;                          // probe: B operand rows (UMMA N = 256)
+constexpr int P_LBO = PN * 16 + 16;
+constexpr int P_OFF_BHI = 2 * W_BYTES, P_OFF_BLO = P_OFF_BHI + KC * P_LBO, P_OFF_BAR = P_OFF_BLO + KC * P_LBO;
+constexpr int P_SMEM_BYTES = P_OFF_BAR + 64 + 1024;
 __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict__ A /*[2][kc][128][8]*/,
                                                        const __half* __restrict__ Bm /*[2][kc][256][8]*/,
                                                        float* __restrict__ D /*[128][256]*/) {
@@ -511,18 +602,18 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t bar = sbase + OFF_BAR;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + 32);
+  const uint32_t bar = sbase + P_OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P_OFF_BAR + 32);
   if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
-  // A -> W slots (pitch W_LBO), B -> activation slots (pitch B_LBO) with ordinary stores
+  // A -> W slots (pitch W_LBO), B -> activation slots (pitch P_LBO) with ordinary stores
   for (int idx = tid; idx < 2 * KC * H; idx += 128) {
     const int copy = idx / (KC * H), rem = idx % (KC * H), kcx = rem / H, row = rem % H;
     *reinterpret_cast<uint4*>(sm + (copy ? OFF_WLO : OFF_WHI) + kcx * W_LBO + row * 16) =
         *reinterpret_cast<const uint4*>(A + (size_t)idx * 8);
   }
-  for (int idx = tid; idx < 2 * KC * TN; idx += 128) {
-    const int copy = idx / (KC * TN), rem = idx % (KC * TN), kcx = rem / TN, row = rem % TN;
-    *reinterpret_cast<uint4*>(sm + (copy ? OFF_BLO : OFF_BHI) + kcx * B_LBO + row * 16) =
+  for (int idx = tid; idx < 2 * KC * PN; idx += 128) {
+    const int copy = idx / (KC * PN), rem = idx % (KC * PN), kcx = rem / PN, row = rem % PN;
+    *reinterpret_cast<uint4*>(sm + (copy ? P_OFF_BLO : P_OFF_BHI) + kcx * P_LBO + row * 16) =
         *reinterpret_cast<const uint4*>(Bm + (size_t)idx * 8);
   }
   fence_proxy_async();
@@ -535,7 +626,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
     const uint32_t idesc = umma_idesc(128, 256);
     for (int ks = 0; ks < 8; ++ks) {
       const uint64_t a_hi = umma_desc(sbase + OFF_WHI + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(sbase + OFF_WLO + ks * 2 * W_LBO, W_LBO, SBO);
-      const uint64_t b_hi = umma_desc(sbase + OFF_BHI + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(sbase + OFF_BLO + ks * 2 * B_LBO, B_LBO, SBO);
+      const uint64_t b_hi = umma_desc(sbase + P_OFF_BHI + ks * 2 * P_LBO, P_LBO, SBO), b_lo = umma_desc(sbase + P_OFF_BLO + ks * 2 * P_LBO, P_LBO, SBO);
       umma_f16(tmem, a_lo, b_hi, idesc, ks > 0);
       umma_f16(tmem, a_hi, b_lo, idesc, 1);
       umma_f16(tmem, a_hi, b_hi, idesc, 1);
@@ -545,11 +636,11 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
   mbar_wait(bar, 0);
   tc_fence_after();
   const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
-  for (int c0 = 0; c0 < TN; c0 += 8) {
+  for (int c0 = 0; c0 < PN; c0 += 8) {
     uint32_t r[8];
     TMEM_LD_X8(tlane + c0, r);
     tmem_ld_wait();
-    for (int u = 0; u < 8; ++u) D[(size_t)(warp * 32 + lane) * TN + c0 + u] = __uint_as_float(r[u]);
+    for (int u = 0; u < 8; ++u) D[(size_t)(warp * 32 + lane) * PN + c0 + u] = __uint_as_float(r[u]);
   }
   tc_fence_before();
   __syncthreads();
@@ -557,7 +648,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
 }
 
 inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_err) {
-  std::vector<float> A((size_t)H * H), Bv((size_t)TN * H);
+  std::vector<float> A((size_t)H * H), Bv((size_t)PN * H);
   uint32_t s = 12345u;
   auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
   for (auto& v : A) v = rnd() * 0.2f;
@@ -574,19 +665,19 @@ inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_er
         }
     return out;
   };
-  std::vector<__half> Ap = pack(A, H), Bp = pack(Bv, TN);
+  std::vector<__half> Ap = pack(A, H), Bp = pack(Bv, PN);
   __half *dA = nullptr, *dB = nullptr;
   float* dD = nullptr;
   if (cudaMalloc(&dA, Ap.size() * 2) != cudaSuccess || cudaMalloc(&dB, Bp.size() * 2) != cudaSuccess ||
-      cudaMalloc(&dD, (size_t)H * TN * 4) != cudaSuccess)
+      cudaMalloc(&dD, (size_t)H * PN * 4) != cudaSuccess)
     return DL_ERR_CUDA;
   cudaMemcpy(dA, Ap.data(), Ap.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, Bp.data(), Bp.size() * 2, cudaMemcpyHostToDevice);
-  cudaMemset(dD, 0, (size_t)H * TN * 4);
-  cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  k_umma_probe<<<1, 128, SMEM_BYTES>>>(dA, dB, dD);
+  cudaMemset(dD, 0, (size_t)H * PN * 4);
+  cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+  k_umma_probe<<<1, 128, P_SMEM_BYTES>>>(dA, dB, dD);
   cudaError_t err = cudaDeviceSynchronize();
-  std::vector<float> D((size_t)H * TN);
+  std::vector<float> D((size_t)H * PN);
   cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
   cudaFree(dA); cudaFree(dB); cudaFree(dD);
   if (err != cudaSuccess) {
@@ -595,10 +686,10 @@ inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_er
   }
   double ma = 0, mr = 0, mref = 0;
   for (int m = 0; m < H; ++m)
-    for (int n = 0; n < TN; ++n) {
+    for (int n = 0; n < PN; ++n) {
       double ref = 0;
       for (int k = 0; k < H; ++k) ref += (double)A[(size_t)m * H + k] * (double)Bv[(size_t)n * H + k];
-      ma = std::max(ma, std::fabs(ref - (double)D[(size_t)m * TN + n]));
+      ma = std::max(ma, std::fabs(ref - (double)D[(size_t)m * PN + n]));
       mref = std::max(mref, std::fabs(ref));
     }
   mr = ma / std::max(mref, 1e-30);
