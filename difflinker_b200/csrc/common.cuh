@@ -9,9 +9,24 @@ constexpr int H = 128;         // hidden_nf (configs/*.yml `nf: 128`), compile-t
 constexpr int MAX_DIN = 32;    // F + C + 1 upper bound
 constexpr int MAX_XHD = 16;    // 3 + F upper bound (threads per node in k_finish)
 
-// silu(x) = x * sigmoid(x) (nn.SiLU, reference src/lightning.py:23-27). ex2.approx + fast divide:
-// ~2 ulp each, far inside the 1e-4 end-to-end tolerance (DESIGN.md "numerics").
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+// silu(x) = x * sigmoid(x) (nn.SiLU, reference src/lightning.py:23-27) = x / (1 + 2^(-x log2 e)).
+// Raw ex2.approx / rcp.approx (2 MUFU + 3 FP32 ops; ~2 ulp each, far inside the 1e-4 end-to-end tolerance,
+// DESIGN.md "numerics"); the libdevice wrappers (__expf, __fdividef) add range-fixup instructions that this
+// path does not need: x -> -inf gives 2^(+inf) = inf, rcp(inf) = 0, x*0 = -0; x -> +inf gives x * 1.
+__device__ __forceinline__ float silu_f(float x) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(x * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return x * r;
+}
+
+// u / (1 + 2^u) for u = -log2(e)*x: equals -log2(e) * silu(x); callers fold the -ln(2) into a downstream constant.
+__device__ __forceinline__ float usig_f(float u) {
+  float t, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(u));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + t));
+  return u * r;
+}
 
 // Packed fp32 weights of one GCL (src/egnn.py:19-30). *_t = k-major ("transposed") [K][128].
 struct GclW {

@@ -748,6 +748,7 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr;
   cudaStream_t st = e->loop_stream;
+  if (e->use_tc && getenv("DL_PROFILE_EDGE")) tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
   for (int i = 0; i < 2; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;
   if (cudaEventRecord(e->ev_t0, st) != cudaSuccess) return -1.f;
   for (int i = 0; i < reps; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;

@@ -10,7 +10,7 @@
 // epilogue reads its own accumulator row, applies bias/SiLU/residual/mask and writes the next operand row.
 // Same 3xFP16 numerics and exact power-of-two range scaling as the edge kernel (kernels_tc.cuh): every operand
 // row is scaled so |x| < 2^14 using the row's own maximum; the descale is a per-thread scalar.
-// Weights stream through a 2-stage ring of K=64 half-blocks (2 x 16 KB cp.async.bulk each) fed by a dedicated
+// Weights stream through a 3-stage ring of K=64 half-blocks (2 x 16 KB cp.async.bulk each) fed by a dedicated
 // loader thread; the MMA issuer thread only waits on the ring's full barriers.
 #pragma once
 #include "kernels_tc.cuh"
@@ -29,8 +29,9 @@ constexpr int BLOCK_BYTES = 2 * W_BYTES;       // one packed 128x128 block: [hi 
 
 constexpr int N_OFF_XA = 0;                    // hi | lo
 constexpr int N_OFF_XB = N_OFF_XA + 2 * X_BYTES;
-constexpr int N_OFF_WS = N_OFF_XB + 2 * X_BYTES;        // 2 stages
-constexpr int N_OFF_BAR = N_OFF_WS + 2 * STAGE_BYTES;   // full[2], empty[2], acc[4]; tmem slot
+constexpr int N_OFF_WS = N_OFF_XB + 2 * X_BYTES;        // N_RING stages
+constexpr int N_RING = 3;                      // ring depth: 96 KB of weights in flight per CTA
+constexpr int N_OFF_BAR = N_OFF_WS + N_RING * STAGE_BYTES;   // full[3], empty[3], acc[4]; tmem slot
 constexpr int N_SMEM_BYTES = N_OFF_BAR + 128 + 1024;
 
 struct NodeTcArgs {
@@ -77,19 +78,20 @@ __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 128;"
 
 __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, NodeTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // keep the pointer derived from the __shared__ array (no integer round trip) so accesses compile to LDS/STS
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   const int tid = threadIdx.x, warp = tid >> 5;
   const int g = blockIdx.x * TM + tid;
   const bool live = g < n_total;
 
-  const uint32_t bar_full = sbase + N_OFF_BAR, bar_empty = bar_full + 16, bar_acc = bar_full + 32;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + N_OFF_BAR + 64);
+  const uint32_t bar_full = sbase + N_OFF_BAR, bar_empty = bar_full + 8 * N_RING, bar_acc = bar_empty + 8 * N_RING;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + N_OFF_BAR + 8 * (2 * N_RING + 4));
   uint8_t* xa_hi = sm + N_OFF_XA; uint8_t* xa_lo = xa_hi + X_BYTES;
   uint8_t* xb_hi = sm + N_OFF_XB; uint8_t* xb_lo = xb_hi + X_BYTES;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < N_RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 4; ++i) mbar_init(bar_acc + 8 * i, 1);
     fence_barrier_init();
   }
@@ -108,8 +110,8 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   if (warp == 4) {
     if (tid == 128) {
     for (int i = 0; i < n_half; ++i) {
-      const int s = i & 1, blk = i >> 1, hf = i & 1;
-      if (i >= 2) mbar_wait(bar_empty + 8 * s, ((i - 2) >> 1) & 1);
+      const int s = i % N_RING, blk = i >> 1, hf = i & 1;
+      if (i >= N_RING) mbar_wait(bar_empty + 8 * s, ((i - N_RING) / N_RING) & 1);
       const __half* base = blk < 2 ? a.w3 + (size_t)blk * (BLOCK_BYTES / 2)
                            : blk == 2 ? a.w4
                                       : a.pw[(blk - 3) >> 1] + (size_t)((blk - 3) & 1) * (BLOCK_BYTES / 2);
@@ -166,8 +168,8 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     // xhi_of[j]: operand hi base for half-block j of this GEMM (lo = hi + X_BYTES); kc offset = 8*(j&1)
     tc_fence_after();
     for (int j = 0; j < nh; ++j) {
-      const int i = i0 + j, s = i & 1;
-      mbar_wait(bar_full + 8 * s, (i >> 1) & 1);
+      const int i = i0 + j, s = i % N_RING;
+      mbar_wait(bar_full + 8 * s, (i / N_RING) & 1);
       tc_fence_after();
       const uint32_t xh = smem_u32(xhi_of[j]) + (8 * (j & 1)) * X_LBO, xl = xh + X_BYTES;
       const uint32_t wh = sbase + N_OFF_WS + s * STAGE_BYTES, wl = wh + HALF_BYTES;

@@ -44,13 +44,15 @@ constexpr float F16_TARGET = 16384.0f;     // operands are scaled by exact power
 constexpr int N_STAGE = 2;                 // activation operand stages in shared memory
 constexpr int N_ACC = 4;                   // TMEM accumulator stages (4 x 128 columns) = table ring depth
 
-// warp roles of k_edge_tc (17 warps)
-constexpr int W_EPI = 0;                   // warps 0-3  : epilogue (warp % 4 = TMEM lane quarter)
-constexpr int W_MMA = 4;                   // warp  4    : MMA issuer (one thread), TMEM alloc/dealloc
-constexpr int W_TBL = 5;                   // warps 5-8  : per-edge table builders (run ahead of everyone)
-constexpr int W_PROD = 9;                  // warps 9-16 : producers (first Linear + SiLU -> fp16 operand tile)
+// warp roles of k_edge_tc (19 warps)
+constexpr int W_EPI = 0;                   // warps 0-7  : epilogue (warp % 4 = TMEM lane quarter, warp / 4 = row parity)
+constexpr int N_EPI_WARPS = 8;
+constexpr int W_MMA = 8;                   // warp  8    : MMA issuer (one thread), TMEM alloc/dealloc
+constexpr int W_TBL = 9;                   // warps 9-10 : per-edge table builders (run ahead of everyone)
+constexpr int N_TBL_WARPS = 2;
+constexpr int W_PROD = 11;                 // warps 11-18: producers (first Linear + SiLU -> fp16 operand tile)
 constexpr int N_PROD_WARPS = 8;
-constexpr int EDGE_TC_THREADS = 32 * (W_PROD + N_PROD_WARPS);   // 544
+constexpr int EDGE_TC_THREADS = 32 * (W_PROD + N_PROD_WARPS);   // 608
 
 // shared memory map (bytes from a 1024-aligned base)
 constexpr int OFF_WHI = 0;
@@ -106,6 +108,23 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 }
 __device__ __forceinline__ void named_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+// Same, for roles that run far ahead of (or lag behind) the critical path: back off between polls so the spin does
+// not steal issue slots from the producer / epilogue warps sharing the scheduler.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; spin < (1u << 24); ++spin) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (done) return;
+    __nanosleep(64);
+  }
+  __trap();
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -233,25 +252,44 @@ struct TileIter {
 // Every role works on a different tile at any moment, so L2 latency (producers), TMEM latency (epilogue) and
 // the tensor pipe overlap; the two SiLUs per edge-channel (MUFU) are the shared bottleneck by design.
 // ---------------------------------------------------------------------------------------------------------
-template <bool COORD>
-__global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArgs a, const __half* __restrict__ w2tc) {
+// PROF = true adds clock64() accounting per role (wait vs work cycles) into `prof` (16 x u64 per CTA); debug only.
+template <bool COORD, bool PROF = false>
+__global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArgs a, const __half* __restrict__ w2tc,
+                                                                unsigned long long* __restrict__ prof = nullptr) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // keep the pointer derived from the __shared__ array (no integer round trip) so accesses compile to LDS/STS
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = gm.N;
 
   const uint32_t bars = sbase + OFF_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + OFF_BAR + BAR_TMEMSLOT);
+  unsigned long long pc[4] = {0, 0, 0, 0};               // PROF: [0..2] wait cycles by barrier kind, [3] tiles
+  const long long t_begin = PROF ? clock64() : 0;
+  auto wait_on = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (PROF) { const long long c0 = clock64(); mbar_wait(bar, parity); pc[slot] += (unsigned long long)(clock64() - c0); }
+    else mbar_wait(bar, parity);
+  };
+  auto wait_relaxed = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (PROF) { const long long c0 = clock64(); mbar_wait_relaxed(bar, parity); pc[slot] += (unsigned long long)(clock64() - c0); }
+    else mbar_wait_relaxed(bar, parity);
+  };
+  auto prof_flush = [&](int base) {
+    if (PROF && lane == 0) {
+      unsigned long long* o = prof + (size_t)blockIdx.x * 16 + base;
+      o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = (unsigned long long)(clock64() - t_begin);
+    }
+  };
   float2* b2w5 = reinterpret_cast<float2*>(sm + OFF_B2W5);
 
   if (tid == 0) {
     mbar_init(bars + BAR_W, 1);
     for (int i = 0; i < N_STAGE; ++i) { mbar_init(bars + BAR_FULL + 8 * i, N_PROD_WARPS); mbar_init(bars + BAR_EMPTY + 8 * i, 1); }
     for (int i = 0; i < N_ACC; ++i) {
-      mbar_init(bars + BAR_TBL + 8 * i, 4);
+      mbar_init(bars + BAR_TBL + 8 * i, N_TBL_WARPS);
       mbar_init(bars + BAR_TFULL + 8 * i, 1);
-      mbar_init(bars + BAR_TEMPTY + 8 * i, 4);
+      mbar_init(bars + BAR_TEMPTY + 8 * i, COORD ? 4 : N_EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -264,26 +302,30 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
 
   if (warp >= W_TBL && warp < W_PROD) {
     // =================================== table warps ===================================================================
-    const int e = (warp - W_TBL) * 32 + lane;            // one edge of the tile per thread
+    const int e_first = (warp - W_TBL) * 32 + lane;      // this thread builds edges e_first and e_first + 64
     TileIter<COORD> iter(a.plan, N);
     Tile cur;
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1);
       const bool more = iter.next(cur);
-      if (t >= N_ACC) mbar_wait(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1);   // slot's previous tile fully consumed
+      if (t >= N_ACC) wait_relaxed(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1, 0);   // slot's previous tile fully consumed
       uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
       int* hdr = reinterpret_cast<int*>(tb + TBL_HDR);
       if (more) {
         const int Et = cur.nrt * cur.ncc;
         const size_t gb = (size_t)cur.b * N;
-        if (e == 0) {
+        if (e_first == 0) {
           hdr[0] = Et; hdr[1] = cur.nrt; hdr[2] = cur.ncc;
           hdr[3] = (cur.first_chunk ? 1 : 0) | (cur.last_chunk ? 2 : 0);
           hdr[4] = cur.b;
         }
-        if (e < cur.nrt) reinterpret_cast<int*>(tb + TBL_ROWNODE)[e] = cur.rows[cur.slot0 + e];
-        if (e < Et) {
-          const int rr = e / cur.ncc, jj = e - rr * cur.ncc;
+        if (e_first < cur.nrt) reinterpret_cast<int*>(tb + TBL_ROWNODE)[e_first] = cur.rows[cur.slot0 + e_first];
+        bool any_rescale = false;
+#pragma unroll
+        for (int rep = 0; rep < TN / (32 * N_TBL_WARPS); ++rep) {
+          const int e = e_first + rep * 32 * N_TBL_WARPS;
+          const int ev = min(e, Et - 1);                   // slots past Et mirror the last edge: producers may prefetch them
+          const int rr = ev / cur.ncc, jj = ev - rr * cur.ncc;
           const int i = cur.rows[cur.slot0 + rr];
           const int j = a.plan.colidx[gb + cur.c0 + jj];
           const float* xi = a.x + (gb + i) * 3; const float* xj = a.x + (gb + j) * 3;
@@ -307,22 +349,29 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             sc = __int_as_float(max(127 + 13 - ex2, 1) << 23);
           }
           reinterpret_cast<float*>(tb + TBL_SC)[e] = sc;
+          any_rescale |= (sc != 1.0f);
+          // GCL epilogue works in the log2 domain: u = -log2(e) * (D*descale + b2) is one FMA, sigmoid = 1/(1+2^u), and
+          // the -ln(2) that turns u*sigmoid back into silu rides on the edge weight (one rounding of a constant).
+          const float ew = edge_weight(gm.graph_type, a.edge_mask ? a.edge_mask + gb * N : nullptr, N, i, j, ci, cj, d0);
           reinterpret_cast<float2*>(tb + TBL_EM)[e] =
-              make_float2(edge_weight(gm.graph_type, a.edge_mask ? a.edge_mask + gb * N : nullptr, N, i, j, ci, cj, d0),
-                          a.w2_descale / sc);
+              COORD ? make_float2(ew, a.w2_descale / sc)
+                    : make_float2(ew * -0.6931471805599453f, (a.w2_descale / sc) * -1.4426950408889634f);
           if (COORD) {
             const float inv = 1.0f / (sqrtf(d + 1e-8f) + gm.norm_constant);  // egnn.py:299-300
             float* cds = reinterpret_cast<float*>(tb + TBL_CD);
             cds[e * 3 + 0] = dx * inv; cds[e * 3 + 1] = dy * inv; cds[e * 3 + 2] = dz * inv;
           }
         }
-      } else if (e == 0) {
+        any_rescale = __any_sync(0xffffffffu, any_rescale);
+        if (lane == 0) hdr[5 + (warp - W_TBL)] = any_rescale ? 1 : 0;   // tile-level flag: producers skip the scale multiply
+      } else if (e_first == 0) {
         hdr[0] = 0;                                      // end marker travels through the whole pipeline
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + BAR_TBL + 8 * acc);
       if (!more) break;
     }
+    if (warp == W_TBL) prof_flush(0);
   } else if (warp >= W_PROD) {
     // =================================== producers =====================================================================
     const int pw = warp - W_PROD;
@@ -332,10 +381,10 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
     for (int q = 0; q < 8; ++q) { wdr[q] = __ldg(a.wd + kc * 8 + q); w0r[q] = __ldg(a.w0 + kc * 8 + q); }
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1), s = t & (N_STAGE - 1);
-      mbar_wait(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1);
+      wait_on(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1, 0);
       const uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
       const int Et = reinterpret_cast<const int*>(tb + TBL_HDR)[0];
-      if (t >= N_STAGE) mbar_wait(bars + BAR_EMPTY + 8 * s, ((t - N_STAGE) / N_STAGE) & 1);   // MMA(t-2) has read this stage
+      if (t >= N_STAGE) wait_on(bars + BAR_EMPTY + 8 * s, ((t - N_STAGE) / N_STAGE) & 1, 1);   // MMA(t-2) has read this stage
       if (Et > 0) {
         const int* rowoff = reinterpret_cast<const int*>(tb + TBL_ROWOFF);
         const int* coloff = reinterpret_cast<const int*>(tb + TBL_COLOFF);
@@ -344,33 +393,44 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         const float* scv = reinterpret_cast<const float*>(tb + TBL_SC);
         uint8_t* bhi = sm + OFF_ST + s * STAGE_BYTES + kc * B_LBO;
         uint8_t* blo = bhi + B_BYTES;
+        const bool rescale = (reinterpret_cast<const int*>(tb + TBL_HDR)[5] | reinterpret_cast<const int*>(tb + TBL_HDR)[6]) != 0;
         constexpr int ITEMS = TN / (2 * N_PROD_WARPS);       // 8 edges per thread per tile
-        float4 pa0, pa1, pb0, pb1;                           // prefetched A_i / B_j chunks of the next item
-        {
-          const int e0 = min(2 * pw + esub, Et - 1);
-          const float* ap = a.AB + rowoff[e0] + kc * 8;
-          const float* bp = a.AB + coloff[e0] + kc * 8;
-          pa0 = __ldg(reinterpret_cast<const float4*>(ap)); pa1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
-          pb0 = __ldg(reinterpret_cast<const float4*>(bp)); pb1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+        // Two items of A_i / B_j chunks are kept in flight in registers (L1 is ~5 KB next to 222 KB of shared
+        // memory, so these loads are L2 round trips). Table slots past Et mirror the last edge: no clamping here.
+        float4 pa[2][2], pb[2][2];
+        const int e_base = 2 * pw + esub;
+#pragma unroll
+        for (int pf = 0; pf < 2; ++pf) {
+          const int en = e_base + 2 * N_PROD_WARPS * pf;
+          const float* ap = a.AB + rowoff[en] + kc * 8;
+          const float* bp = a.AB + coloff[en] + kc * 8;
+          pa[pf][0] = __ldg(reinterpret_cast<const float4*>(ap)); pa[pf][1] = __ldg(reinterpret_cast<const float4*>(ap + 4));
+          pb[pf][0] = __ldg(reinterpret_cast<const float4*>(bp)); pb[pf][1] = __ldg(reinterpret_cast<const float4*>(bp + 4));
         }
-#pragma unroll 1
+#pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-          const int e = 2 * (pw + N_PROD_WARPS * it) + esub;
-          const float4 a0 = pa0, a1 = pa1, b0 = pb0, b1 = pb1;
-          if (it + 1 < ITEMS) {
-            const int en = min(e + 2 * N_PROD_WARPS, Et - 1);
+          const int e = e_base + 2 * N_PROD_WARPS * it;
+          const int slot = it & 1;
+          const float4 a0 = pa[slot][0], a1 = pa[slot][1], b0 = pb[slot][0], b1 = pb[slot][1];
+          if (it + 2 < ITEMS) {
+            const int en = e + 4 * N_PROD_WARPS;
             const float* ap = a.AB + rowoff[en] + kc * 8;
             const float* bp = a.AB + coloff[en] + kc * 8;
-            pa0 = __ldg(reinterpret_cast<const float4*>(ap)); pa1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
-            pb0 = __ldg(reinterpret_cast<const float4*>(bp)); pb1 = __ldg(reinterpret_cast<const float4*>(bp + 4));
+            pa[slot][0] = __ldg(reinterpret_cast<const float4*>(ap)); pa[slot][1] = __ldg(reinterpret_cast<const float4*>(ap + 4));
+            pb[slot][0] = __ldg(reinterpret_cast<const float4*>(bp)); pb[slot][1] = __ldg(reinterpret_cast<const float4*>(bp + 4));
           }
           if (e < Et) {
-            const float d = dv[e], d0 = d0v[e], sc = scv[e];
+            const float d = dv[e], d0 = d0v[e];
             const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
             const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
             float sv[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) sv[q] = silu_f(fmaf(d0, w0r[q], fmaf(d, wdr[q], av[q] + bv[q]))) * sc;   // egnn.py:49-50
+            for (int q = 0; q < 8; ++q) sv[q] = silu_f(fmaf(d0, w0r[q], fmaf(d, wdr[q], av[q] + bv[q])));   // egnn.py:49-50
+            if (rescale) {                                 // rare: diverging samples only (tile-uniform)
+              const float sc = scv[e];
+#pragma unroll
+              for (int q = 0; q < 8; ++q) sv[q] *= sc;
+            }
             uint4 hi, lo;
             split2(sv[0], sv[1], hi.x, lo.x); split2(sv[2], sv[3], hi.y, lo.y);
             split2(sv[4], sv[5], hi.z, lo.z); split2(sv[6], sv[7], hi.w, lo.w);
@@ -384,6 +444,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
       if (lane == 0) mbar_arrive(bars + BAR_FULL + 8 * s);
       if (Et <= 0) break;
     }
+    if (warp == W_PROD) prof_flush(4);
   } else if (warp == W_MMA) {
     // =================================== MMA issuer =====================================================================
     if (lane == 0) {
@@ -393,10 +454,10 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
       const uint32_t whi = sbase + OFF_WHI, wlo = sbase + OFF_WLO;
       for (int t = 0;; ++t) {
         const int acc = t & (N_ACC - 1), s = t & (N_STAGE - 1);
-        mbar_wait(bars + BAR_FULL + 8 * s, (t / N_STAGE) & 1);
+        wait_relaxed(bars + BAR_FULL + 8 * s, (t / N_STAGE) & 1, 0);
         const int Et = reinterpret_cast<const int*>(sm + OFF_TBL + acc * TBL_BYTES + TBL_HDR)[0];
         if (Et <= 0) { mbar_arrive(bars + BAR_TFULL + 8 * acc); break; }
-        if (t >= N_ACC) mbar_wait(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1);   // epilogue(t-4) drained this accumulator
+        if (t >= N_ACC) wait_on(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1, 1);   // epilogue(t-4) drained this accumulator
         tc_fence_after();
         const uint32_t bhi = sbase + OFF_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
         const uint32_t dcol = tmem + acc * TN;
@@ -423,17 +484,21 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         }
         umma_commit(bars + BAR_EMPTY + 8 * s);             // operand stage reusable once these MMAs have read it
         umma_commit(bars + BAR_TFULL + 8 * acc);           // accumulator ready for the epilogue
+        pc[2] += 1;
       }
+      prof_flush(8);
     }
   } else {
     // =================================== epilogue warps ==================================================================
     const int q = warp & 3;                                // TMEM lane quarter of this warp
+    const int hw = warp >> 2;                              // GCL: this warp takes the tile rows with (rr + t) % 2 == hw
+    if (COORD && hw != 0) goto edge_tc_done;               // coord variant: lanes are edges, 4 warps cover the tile
     float* txs = reinterpret_cast<float*>(sm + OFF_TX);
     float run = 0.f;   // GCL: row sum carried across column chunks (thread = channel); COORD: (row,dim) running sum
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1);
-      mbar_wait(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1);
-      mbar_wait(bars + BAR_TFULL + 8 * acc, (t / N_ACC) & 1);
+      wait_on(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1, 0);
+      wait_on(bars + BAR_TFULL + 8 * acc, (t / N_ACC) & 1, 1);
       tc_fence_after();
       const uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
       const int* hdr = reinterpret_cast<const int*>(tb + TBL_HDR);
@@ -446,9 +511,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
       const int* rownode = reinterpret_cast<const int*>(tb + TBL_ROWNODE);
       if (!COORD) {
         const int c = q * 32 + lane;
-        const float bias = b2w5[c].x;
+        const float bias = b2w5[c].x * -1.4426950408889634f;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + acc * TN;
-        for (int rr = 0; rr < nrt; ++rr) {
+        for (int rr = (nrt == 1 ? hw : ((hw + t) & 1)); rr < nrt; rr += 2) {   // single-row (chunked) tiles: half 0 only
           float accv = (nrt == 1 && !first_chunk) ? run : 0.f;
           const int col0 = rr * ncc;
           int jj = 0;
@@ -459,7 +524,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
 #pragma unroll
             for (int u = 0; u < 16; ++u) {
               const float2 ed = emds[col0 + jj + u];
-              accv = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+              accv = fmaf(usig_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
             }
           }
           if (ncc - jj >= 8) {
@@ -469,7 +534,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
               const float2 ed = emds[col0 + jj + u];
-              accv = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+              accv = fmaf(usig_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
             }
             jj += 8;
           }
@@ -480,7 +545,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float2 ed = emds[col0 + jj + u];
-              accv = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+              accv = fmaf(usig_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
             }
             jj += 4;
           }
@@ -488,7 +553,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             const uint32_t r = tmem_ld_x1(tlane + col0 + jj);
             tmem_ld_wait();
             const float2 ed = emds[col0 + jj];
-            accv = fmaf(silu_f(fmaf(__uint_as_float(r), ed.y, bias)), ed.x, accv);
+            accv = fmaf(usig_f(fmaf(__uint_as_float(r), ed.y, bias)), ed.x, accv);
           }
           if (nrt == 1) run = accv;
           if (last_chunk) a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
@@ -538,7 +603,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         if (lane == 0) mbar_arrive(bars + BAR_TEMPTY + 8 * acc);
       }
     }
+    if (warp == W_EPI) prof_flush(12);
   }
+edge_tc_done:
   tc_fence_before();
   __syncthreads();
   if (warp == W_MMA) tmem_dealloc(tmem, 512);
@@ -548,8 +615,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
 // Host side
 // ---------------------------------------------------------------------------------------------------------
 inline dl_status configure() {
-  if (cudaFuncSetAttribute(k_edge_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_edge_tc<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+  if (cudaFuncSetAttribute(k_edge_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_edge_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_edge_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
     return DL_ERR_CUDA;
   return DL_OK;
 }
@@ -582,8 +650,28 @@ inline size_t pack_w2(const std::vector<float>& W, std::vector<__half>& blob, fl
 inline dl_status launch_edge_tc(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc, int num_sms,
                                 cudaStream_t st) {
   const __half* w = reinterpret_cast<const __half*>(w2_tc);
-  if (coord) k_edge_tc<true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w);
-  else k_edge_tc<false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w);
+  if (coord) k_edge_tc<true, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+  else k_edge_tc<false, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+  return DL_OK;
+}
+
+// Debug: one profiled GCL launch; prints per-role wait/total cycles averaged over CTAs to stderr.
+inline dl_status profile_edge_tc(const Geom& gm, const EdgeArgs& ea, const void* w2_tc, int num_sms, cudaStream_t st) {
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, (size_t)num_sms * 16 * 8) != cudaSuccess) return DL_ERR_CUDA;
+  cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
+  k_edge_tc<false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
+  std::vector<unsigned long long> h((size_t)num_sms * 16);
+  cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  double avg[16] = {0};
+  for (int b = 0; b < num_sms; ++b) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)b * 16 + i] / num_sms;
+  fprintf(stderr, "[dl prof] cycles per CTA (avg over %d): tiles %.1f\n", num_sms, avg[10]);
+  fprintf(stderr, "[dl prof]  table   : wait tempty %.0f | total %.0f\n", avg[0], avg[3]);
+  fprintf(stderr, "[dl prof]  producer: wait tbl %.0f, wait empty %.0f | total %.0f\n", avg[4], avg[5], avg[7]);
+  fprintf(stderr, "[dl prof]  mma     : wait full %.0f, wait tempty %.0f | total %.0f\n", avg[8], avg[9], avg[11]);
+  fprintf(stderr, "[dl prof]  epilogue: wait tbl %.0f, wait tfull %.0f | total %.0f\n", avg[12], avg[13], avg[15]);
   return DL_OK;
 }
 
@@ -599,7 +687,8 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
                                                        const __half* __restrict__ Bm /*[2][kc][256][8]*/,
                                                        float* __restrict__ D /*[128][256]*/) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  // keep the pointer derived from the __shared__ array (no integer round trip) so accesses compile to LDS/STS
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t bar = sbase + P_OFF_BAR;
