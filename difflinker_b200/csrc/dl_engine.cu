@@ -306,7 +306,11 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
             ta.p_descale[1] = nx.w1_descale; ta.AB[1] = ws.ABg; ta.ABmax[1] = ws.ABgmax;
           }
         }
-        tcn::k_node_tc<<<(n + tcn::TM - 1) / tcn::TM, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta);
+        static int node_prof_left = getenv("DL_PROFILE_NODE") ? 3 : 0;
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        if (node_prof_left > 0) cudaStreamIsCapturing(st, &cap);
+        if (node_prof_left > 0 && cap == cudaStreamCaptureStatusNone) { --node_prof_left; tcn::profile_node(n, ta, st); }
+        else tcn::k_node_tc<<<(n + tcn::TM - 1) / tcn::TM, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
       } else {
         NodeArgs na{};
         na.h = ws.h; na.agg = ws.agg; na.nm = ws.nm; na.W3_t = w.W3_t; na.b3 = w.b3; na.W4_t = w.W4_t; na.b4 = w.b4;
@@ -749,6 +753,21 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr;
   cudaStream_t st = e->loop_stream;
   if (e->use_tc && getenv("DL_PROFILE_EDGE")) tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
+  if (e->use_tc && getenv("DL_PROFILE_NODE")) {
+    for (int np = 1; np <= (e->cfg.n_layers > 1 ? 2 : 1); ++np) {
+      tcn::NodeTcArgs ta{};
+      ta.h = ws.h; ta.agg = ws.agg; ta.nm = ws.nm;
+      ta.w3 = reinterpret_cast<const __half*>(w.W3_tc); ta.w4 = reinterpret_cast<const __half*>(w.W4_tc);
+      ta.b3 = w.b3; ta.b4 = w.b4; ta.w3_descale = w.w3_descale; ta.w4_descale = w.w4_descale;
+      const EqW& q = e->eq[0];
+      ta.n_proj = np; ta.pw[0] = reinterpret_cast<const __half*>(q.W1_tc); ta.pb1[0] = q.b1;
+      ta.p_descale[0] = q.w1_descale; ta.AB[0] = ws.ABc; ta.ABmax[0] = ws.ABcmax;
+      const GclW& nx = e->gcl[e->cfg.n_layers > 1 ? e->cfg.inv_sublayers : 0];
+      ta.pw[1] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[1] = nx.b1;
+      ta.p_descale[1] = nx.w1_descale; ta.AB[1] = ws.ABg; ta.ABmax[1] = ws.ABgmax;
+      tcn::profile_node(e->last_B * e->last_N, ta, st);
+    }
+  }
   for (int i = 0; i < 2; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;
   if (cudaEventRecord(e->ev_t0, st) != cudaSuccess) return -1.f;
   for (int i = 0; i < reps; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;
