@@ -38,7 +38,10 @@ constexpr int N_OFF_WS = N_OFF_XB + 2 * X_BYTES;
 constexpr int N_OFF_MISC = N_OFF_WS + N_RING * STAGE_BYTES;   // nm[128] f32, nodemax[2][128] i32, tilemax i32
 constexpr int N_OFF_BAR = N_OFF_MISC + 128 * 4 * 3 + 16;      // full[2], empty[2], acc[4]; tmem slot
 constexpr int N_SMEM_BYTES = N_OFF_BAR + 128 + 1024;
-constexpr int NODE_TC_THREADS = 160;           // warps 0-3: thread c = output channel c = TMEM lane c; warp 4: weight loader
+constexpr int NW = 16;                         // worker warps: warp w serves TMEM lane quarter w % 4 and node columns
+constexpr int NPART = NW / 4;                  //   [part*CW, (part+1)*CW) with part = w / 4 -- 4 warps per scheduler
+constexpr int CW = TM / NPART;                 //   hide each other's TMEM / shared / global latencies
+constexpr int NODE_TC_THREADS = 32 * (NW + 1); // + 1 weight-loader warp
 
 struct NodeTcArgs {
   float* h;              // (n,128) in/out
@@ -65,7 +68,7 @@ __device__ __forceinline__ float pow2_scale_for(float bound) {
   return sc;
 }
 
-__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory"); }
 
 // one value of channel c, node n -> fp16 hi/lo operand tile
 __device__ __forceinline__ void store_elem(uint8_t* xhi, uint8_t* xlo, int c, int n, float v) {
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     fence_barrier_init();
     *tilemax = 0;
   }
-  if (tid < TM) nms[tid] = tid < n_live ? a.nm[g0 + tid] : 0.f;
+  if (tid < TM) nms[tid] = tid < n_live ? a.nm[g0 + tid] : 0.f;   // (tid < TM are workers of part 0)
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -113,7 +116,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
 
   // ---- weight loader: a dedicated warp streams the half-blocks through the ring; it never joins the workers'
   //      barriers (the ring's empty barriers are released by MMA completion, which needs the workers) ---------------
-  if (warp == 4) {
+  if (warp == NW) {
     if (lane == 0) {
       for (int i = 0; i < n_half; ++i) {
         const int s = i % N_RING, blk = i >> 1, hf = i & 1;
@@ -131,18 +134,20 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     return;
   }
 
-  const int c = tid;                                   // this thread's output channel = TMEM lane
-  const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+  const int c = tid & (TM - 1);                        // this thread's output channel = TMEM lane
+  const int part = tid >> 7;                           // which CW-wide slice of the node columns this thread serves
+  const int ncol0 = part * CW;
+  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ncol0;
 
   // ---- operand rows: h -> XA, agg -> XB; coalesced row loads (one row per warp iteration) -----------------------------
   auto load_rows = [&](float scale) -> float {
     float mx = 0.f;
 #pragma unroll 1
-    for (int rb = 0; rb < TM / 4; rb += 8) {             // 8 rows per warp per batch: 16 x 16-byte loads in flight per lane
-      float4 hv[8], av[8];
+    for (int rb = 0; rb < TM / NW; rb += 4) {            // 4 rows per warp per batch: 8 x 16-byte loads in flight per lane
+      float4 hv[4], av[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = warp + 4 * (rb + j);
+      for (int j = 0; j < 4; ++j) {
+        const int r = warp + NW * (rb + j);
         hv[j] = make_float4(0, 0, 0, 0); av[j] = hv[j];
         if (r < n_live) {
           hv[j] = *reinterpret_cast<const float4*>(a.h + (size_t)(g0 + r) * H + lane * 4);
@@ -150,8 +155,8 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
         }
       }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = warp + 4 * (rb + j);
+      for (int j = 0; j < 4; ++j) {
+        const int r = warp + NW * (rb + j);
         mx = fmaxf(mx, fmaxf(fmaxf(fabsf(hv[j].x), fabsf(hv[j].y)), fmaxf(fabsf(hv[j].z), fabsf(hv[j].w))));
         mx = fmaxf(mx, fmaxf(fmaxf(fabsf(av[j].x), fabsf(av[j].y)), fmaxf(fabsf(av[j].z), fabsf(av[j].w))));
         const int off = (lane >> 1) * X_LBO + r * 16 + (lane & 1) * 8;     // channels 4*lane..4*lane+3 of row r
@@ -224,14 +229,14 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
       uint32_t r[2][16];
       TMEM_LD_X16(trow, r[0]);
 #pragma unroll
-      for (int k = 0; k < TM / 16; ++k) {
+      for (int k = 0; k < CW / 16; ++k) {
         tmem_ld_wait();
-        if (k + 1 < TM / 16) TMEM_LD_X16(trow + (k + 1) * 16, r[(k + 1) & 1]);
+        if (k + 1 < CW / 16) TMEM_LD_X16(trow + (k + 1) * 16, r[(k + 1) & 1]);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const float v = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
           mx = fmaxf(mx, fabsf(v));                    // |silu(v)| <= |v|
-          store_elem(xb_hi, xb_lo, c, k * 16 + u, silu_f(v) * scale);
+          store_elem(xb_hi, xb_lo, c, ncol0 + k * 16 + u, silu_f(v) * scale);
         }
       }
       return mx;
@@ -261,19 +266,22 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     uint32_t r[2][16];
     float hv[2][16];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) hv[0][u] = (u < n_live) ? hcol[(size_t)u * H] : 0.f;
+    for (int u = 0; u < 16; ++u) hv[0][u] = (ncol0 + u < n_live) ? hcol[(size_t)(ncol0 + u) * H] : 0.f;
     TMEM_LD_X16(trow + 128, r[0]);
 #pragma unroll
-    for (int k = 0; k < TM / 16; ++k) {
+    for (int k = 0; k < CW / 16; ++k) {
       tmem_ld_wait();
-      if (k + 1 < TM / 16) {
+      if (k + 1 < CW / 16) {
         TMEM_LD_X16(trow + 128 + (k + 1) * 16, r[(k + 1) & 1]);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) hv[(k + 1) & 1][u] = ((k + 1) * 16 + u < n_live) ? hcol[(size_t)((k + 1) * 16 + u) * H] : 0.f;
+        for (int u = 0; u < 16; ++u) {
+          const int nn = ncol0 + (k + 1) * 16 + u;
+          hv[(k + 1) & 1][u] = (nn < n_live) ? hcol[(size_t)nn * H] : 0.f;
+        }
       }
 #pragma unroll
       for (int u = 0; u < 16; ++u) {
-        const int n = k * 16 + u;
+        const int n = ncol0 + k * 16 + u;
         const float o = (hv[k & 1][u] + fmaf(__uint_as_float(r[k & 1][u]), ds, bias)) * nms[n];     // egnn.py:71,78-79
         if (n < n_live) hcol[(size_t)n * H] = o;
         mx = fmaxf(mx, fabsf(o));
@@ -282,7 +290,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     }
     s3 = pow2_scale_for(tile_max(mx));
     if (s3 != 1.0f) {                                  // rare: rewrite h' scaled (own global writes, program order)
-      for (int n = 0; n < TM; ++n) store_elem(xa_hi, xa_lo, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
+      for (int n = ncol0; n < ncol0 + CW; ++n) store_elem(xa_hi, xa_lo, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
     }
   }
   fence_proxy_async();
@@ -313,12 +321,12 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
       uint32_t r[2][16];
       TMEM_LD_X16(trow + accn * 128, r[0]);
 #pragma unroll
-      for (int k = 0; k < TM / 16; ++k) {
+      for (int k = 0; k < CW / 16; ++k) {
         tmem_ld_wait();
-        if (k + 1 < TM / 16) TMEM_LD_X16(trow + accn * 128 + (k + 1) * 16, r[(k + 1) & 1]);
+        if (k + 1 < CW / 16) TMEM_LD_X16(trow + accn * 128 + (k + 1) * 16, r[(k + 1) & 1]);
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const int n = k * 16 + u;
+          const int n = ncol0 + k * 16 + u;
           const float o = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
           if (n < n_live) { abcol[(size_t)n * 2 * H] = o; mx = fmaxf(mx, fabsf(o)); }
         }
