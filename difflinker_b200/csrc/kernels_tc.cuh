@@ -44,15 +44,17 @@ constexpr float F16_TARGET = 16384.0f;     // operands are scaled by exact power
 constexpr int N_STAGE = 2;                 // activation operand stages in shared memory
 constexpr int N_ACC = 4;                   // TMEM accumulator stages (4 x 128 columns) = table ring depth
 
-// warp roles of k_edge_tc (19 warps)
-constexpr int W_EPI = 0;                   // warps 0-7  : epilogue (warp % 4 = TMEM lane quarter, warp / 4 = row parity)
+// warp roles of k_edge_tc: 28 warps = 7 warpgroups; registers are re-balanced per warpgroup with setmaxnreg
+// (launch: 72/thread; producers grow to 88, epilogue shrinks to 56, the MMA/table group to 40 -- 64,512 in total).
+constexpr int W_EPI = 0;                   // warps 0-7   (WG 0,1): epilogue (warp % 4 = TMEM lane quarter, warp / 4 = row parity)
 constexpr int N_EPI_WARPS = 8;
-constexpr int W_MMA = 8;                   // warp  8    : MMA issuer (one thread), TMEM alloc/dealloc
-constexpr int W_TBL = 9;                   // warps 9-10 : per-edge table builders (run ahead of everyone)
-constexpr int N_TBL_WARPS = 2;
-constexpr int W_PROD = 11;                 // warps 11-18: producers (first Linear + SiLU -> fp16 operand tile)
-constexpr int N_PROD_WARPS = 8;
-constexpr int EDGE_TC_THREADS = 32 * (W_PROD + N_PROD_WARPS);   // 608
+constexpr int W_MMA = 8;                   // warp  8     (WG 2)  : MMA issuer (one thread), TMEM alloc/dealloc
+constexpr int W_TBL = 9;                   // warps 9-11  (WG 2)  : per-edge table builders (run ahead of everyone)
+constexpr int N_TBL_WARPS = 3;
+constexpr int W_PROD = 12;                 // warps 12-27 (WG 3-6): producers (first Linear + SiLU -> fp16 operand tile)
+constexpr int N_PROD_WARPS = 16;
+constexpr int EDGE_TC_THREADS = 32 * (W_PROD + N_PROD_WARPS);   // 896
+constexpr int REGS_EPI = 56, REGS_CTRL = 40, REGS_PROD = 88;
 
 // shared memory map (bytes from a 1024-aligned base)
 constexpr int OFF_WHI = 0;
@@ -215,8 +217,13 @@ template <bool COORD>
 struct TileIter {
   const Plan& plan;
   int N, n_work, wi, rt, c0;
-  __device__ TileIter(const Plan& p, int N_) : plan(p), N(N_), wi(blockIdx.x), rt(0), c0(0) {
-    n_work = COORD ? *p.n_xmols : *p.n_items;
+  // blocked distribution: CTA c owns the contiguous work items [lo, hi) -- consecutive tiles then mostly belong to the
+  // same molecule, so the table warps' and producers' L2 lines are reused while they are hot.
+  __device__ TileIter(const Plan& p, int N_) : plan(p), N(N_), rt(0), c0(0) {
+    const int total = COORD ? *p.n_xmols : *p.n_items;
+    const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
+    wi = c * per + min(c, extra);
+    n_work = wi + per + (c < extra ? 1 : 0);
   }
   __device__ bool next(Tile& t) {
     while (wi < n_work) {
@@ -226,7 +233,7 @@ struct TileIter {
       const int nc = plan.nc[b];
       int per = nc >= TN ? 1 : TN / nc;
       if (per > MAXR) per = MAXR;
-      if (rt >= r_count || nc <= 0) { wi += gridDim.x; rt = 0; c0 = 0; continue; }
+      if (rt >= r_count || nc <= 0) { wi += 1; rt = 0; c0 = 0; continue; }
       t.b = b; t.nc = nc; t.slot0 = r_begin + rt; t.nrt = min(per, r_count - rt);
       t.c0 = c0; t.ncc = min(TN, nc - c0);
       t.first_chunk = c0 == 0; t.last_chunk = c0 + TN >= nc;
@@ -287,7 +294,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
     mbar_init(bars + BAR_W, 1);
     for (int i = 0; i < N_STAGE; ++i) { mbar_init(bars + BAR_FULL + 8 * i, N_PROD_WARPS); mbar_init(bars + BAR_EMPTY + 8 * i, 1); }
     for (int i = 0; i < N_ACC; ++i) {
-      mbar_init(bars + BAR_TBL + 8 * i, N_TBL_WARPS);
+      mbar_init(bars + BAR_TBL + 8 * i, 1);
       mbar_init(bars + BAR_TFULL + 8 * i, 1);
       mbar_init(bars + BAR_TEMPTY + 8 * i, COORD ? 4 : N_EPI_WARPS);
     }
@@ -300,30 +307,36 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= W_TBL && warp < W_PROD) {
+  // Register re-balancing happens at the top of each role branch (warpgroup-aligned: every warp of a group runs the
+  // same setmaxnreg; ptxas allocates each branch against the budget set by the instruction that dominates it).
+  if (warp >= W_MMA && warp < W_PROD) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_CTRL));
+  if (warp >= W_TBL && warp < W_TBL + N_TBL_WARPS) {
     // =================================== table warps ===================================================================
-    const int e_first = (warp - W_TBL) * 32 + lane;      // this thread builds edges e_first and e_first + 64
+    // Tile-parallel: table warp k builds the tables of tiles t = k, k+3, ... on its own (4 edges per lane), so the
+    // three warps overlap their dependent L2 round trips (index -> coordinates / maxima / mask) across tiles.
+    const int tw = warp - W_TBL;
     TileIter<COORD> iter(a.plan, N);
     Tile cur;
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1);
       const bool more = iter.next(cur);
+      if (t % N_TBL_WARPS != tw) { if (!more) break; continue; }
       if (t >= N_ACC) wait_relaxed(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1, 0);   // slot's previous tile fully consumed
       uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
       int* hdr = reinterpret_cast<int*>(tb + TBL_HDR);
       if (more) {
         const int Et = cur.nrt * cur.ncc;
         const size_t gb = (size_t)cur.b * N;
-        if (e_first == 0) {
+        if (lane == 0) {
           hdr[0] = Et; hdr[1] = cur.nrt; hdr[2] = cur.ncc;
           hdr[3] = (cur.first_chunk ? 1 : 0) | (cur.last_chunk ? 2 : 0);
           hdr[4] = cur.b;
         }
-        if (e_first < cur.nrt) reinterpret_cast<int*>(tb + TBL_ROWNODE)[e_first] = cur.rows[cur.slot0 + e_first];
+        if (lane < cur.nrt) reinterpret_cast<int*>(tb + TBL_ROWNODE)[lane] = cur.rows[cur.slot0 + lane];
         bool any_rescale = false;
-#pragma unroll
-        for (int rep = 0; rep < TN / (32 * N_TBL_WARPS); ++rep) {
-          const int e = e_first + rep * 32 * N_TBL_WARPS;
+#pragma unroll 2
+        for (int e = lane; e < TN; e += 32) {
           const int ev = min(e, Et - 1);                   // slots past Et mirror the last edge: producers may prefetch them
           const int rr = ev / cur.ncc, jj = ev - rr * cur.ncc;
           const int i = cur.rows[cur.slot0 + rr];
@@ -363,8 +376,8 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
           }
         }
         any_rescale = __any_sync(0xffffffffu, any_rescale);
-        if (lane == 0) hdr[5 + (warp - W_TBL)] = any_rescale ? 1 : 0;   // tile-level flag: producers skip the scale multiply
-      } else if (e_first == 0) {
+        if (lane == 0) hdr[5] = any_rescale ? 1 : 0;       // tile-level flag: producers skip the scale multiply
+      } else if (lane == 0) {
         hdr[0] = 0;                                      // end marker travels through the whole pipeline
       }
       __syncwarp();
@@ -372,8 +385,53 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
       if (!more) break;
     }
     if (warp == W_TBL) prof_flush(0);
+  } else if (warp == W_MMA) {
+    // =================================== MMA issuer =====================================================================
+    if (lane == 0) {
+      mbar_expect_tx(bars + BAR_W, 2 * W_BYTES);           // W2 hi|lo tiles: one 64 KB TMA bulk copy, resident for the launch
+      bulk_g2s(sbase + OFF_WHI, w2tc, 2 * W_BYTES, bars + BAR_W);
+      mbar_wait(bars + BAR_W, 0);
+      const uint32_t whi = sbase + OFF_WHI, wlo = sbase + OFF_WLO;
+      for (int t = 0;; ++t) {
+        const int acc = t & (N_ACC - 1), s = t & (N_STAGE - 1);
+        wait_relaxed(bars + BAR_FULL + 8 * s, (t / N_STAGE) & 1, 0);
+        const int Et = reinterpret_cast<const int*>(sm + OFF_TBL + acc * TBL_BYTES + TBL_HDR)[0];
+        if (Et <= 0) { mbar_arrive(bars + BAR_TFULL + 8 * acc); break; }
+        if (t >= N_ACC) wait_on(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1, 1);   // epilogue(t-4) drained this accumulator
+        tc_fence_after();
+        const uint32_t bhi = sbase + OFF_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
+        const uint32_t dcol = tmem + acc * TN;
+        if (!COORD) {
+          const uint32_t idesc = umma_idesc(128, max(16, (Et + 15) & ~15));
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
+            const uint64_t b_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
+            umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
+            umma_f16(dcol, a_hi, b_lo, idesc, 1);
+            umma_f16(dcol, a_hi, b_hi, idesc, 1);
+          }
+        } else {
+          const uint32_t idesc = umma_idesc(128, 128);
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t a_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), a_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
+            const uint64_t b_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), b_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
+            umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
+            umma_f16(dcol, a_hi, b_lo, idesc, 1);
+            umma_f16(dcol, a_hi, b_hi, idesc, 1);
+          }
+        }
+        umma_commit(bars + BAR_EMPTY + 8 * s);             // operand stage reusable once these MMAs have read it
+        umma_commit(bars + BAR_TFULL + 8 * acc);           // accumulator ready for the epilogue
+        pc[2] += 1;
+      }
+      prof_flush(8);
+    }
+  }
   } else if (warp >= W_PROD) {
     // =================================== producers =====================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     const int pw = warp - W_PROD;
     const int kc = lane & 15, esub = lane >> 4;            // this thread always owns k = kc*8 .. kc*8+7
     float wdr[8], w0r[8];
@@ -393,7 +451,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         const float* scv = reinterpret_cast<const float*>(tb + TBL_SC);
         uint8_t* bhi = sm + OFF_ST + s * STAGE_BYTES + kc * B_LBO;
         uint8_t* blo = bhi + B_BYTES;
-        const bool rescale = (reinterpret_cast<const int*>(tb + TBL_HDR)[5] | reinterpret_cast<const int*>(tb + TBL_HDR)[6]) != 0;
+        const bool rescale = reinterpret_cast<const int*>(tb + TBL_HDR)[5] != 0;
         constexpr int ITEMS = TN / (2 * N_PROD_WARPS);       // 8 edges per thread per tile
         // Two items of A_i / B_j chunks are kept in flight in registers (L1 is ~5 KB next to 222 KB of shared
         // memory, so these loads are L2 round trips). Table slots past Et mirror the last edge: no clamping here.
@@ -445,51 +503,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
       if (Et <= 0) break;
     }
     if (warp == W_PROD) prof_flush(4);
-  } else if (warp == W_MMA) {
-    // =================================== MMA issuer =====================================================================
-    if (lane == 0) {
-      mbar_expect_tx(bars + BAR_W, 2 * W_BYTES);           // W2 hi|lo tiles: one 64 KB TMA bulk copy, resident for the launch
-      bulk_g2s(sbase + OFF_WHI, w2tc, 2 * W_BYTES, bars + BAR_W);
-      mbar_wait(bars + BAR_W, 0);
-      const uint32_t whi = sbase + OFF_WHI, wlo = sbase + OFF_WLO;
-      for (int t = 0;; ++t) {
-        const int acc = t & (N_ACC - 1), s = t & (N_STAGE - 1);
-        wait_relaxed(bars + BAR_FULL + 8 * s, (t / N_STAGE) & 1, 0);
-        const int Et = reinterpret_cast<const int*>(sm + OFF_TBL + acc * TBL_BYTES + TBL_HDR)[0];
-        if (Et <= 0) { mbar_arrive(bars + BAR_TFULL + 8 * acc); break; }
-        if (t >= N_ACC) wait_on(bars + BAR_TEMPTY + 8 * acc, ((t - N_ACC) / N_ACC) & 1, 1);   // epilogue(t-4) drained this accumulator
-        tc_fence_after();
-        const uint32_t bhi = sbase + OFF_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
-        const uint32_t dcol = tmem + acc * TN;
-        if (!COORD) {
-          const uint32_t idesc = umma_idesc(128, max(16, (Et + 15) & ~15));
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t a_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
-            const uint64_t b_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
-            umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
-            umma_f16(dcol, a_hi, b_lo, idesc, 1);
-            umma_f16(dcol, a_hi, b_hi, idesc, 1);
-          }
-        } else {
-          const uint32_t idesc = umma_idesc(128, 128);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint64_t a_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), a_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
-            const uint64_t b_hi = umma_desc(whi + ks * 2 * W_LBO, W_LBO, SBO), b_lo = umma_desc(wlo + ks * 2 * W_LBO, W_LBO, SBO);
-            umma_f16(dcol, a_lo, b_hi, idesc, ks > 0);
-            umma_f16(dcol, a_hi, b_lo, idesc, 1);
-            umma_f16(dcol, a_hi, b_hi, idesc, 1);
-          }
-        }
-        umma_commit(bars + BAR_EMPTY + 8 * s);             // operand stage reusable once these MMAs have read it
-        umma_commit(bars + BAR_TFULL + 8 * acc);           // accumulator ready for the epilogue
-        pc[2] += 1;
-      }
-      prof_flush(8);
-    }
   } else {
     // =================================== epilogue warps ==================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS_EPI));
     const int q = warp & 3;                                // TMEM lane quarter of this warp
     const int hw = warp >> 2;                              // GCL: this warp takes the tile rows with (rr + t) % 2 == hw
     if (COORD && hw != 0) goto edge_tc_done;               // coord variant: lanes are edges, 4 warps cover the tile
