@@ -45,8 +45,9 @@ struct Workspace {
         *agg = nullptr, *z = nullptr, *ABgmax = nullptr, *ABcmax = nullptr;
   int* cls = nullptr;
   int *rowidx = nullptr, *colidx = nullptr, *xrowidx = nullptr, *nr = nullptr, *nc = nullptr, *nxr = nullptr,
-      *n_items = nullptr, *xmols = nullptr, *n_xmols = nullptr;
+      *n_items = nullptr, *xmols = nullptr, *n_xmols = nullptr, *n_xitems = nullptr;
   int4* items = nullptr;
+  int4* xitems = nullptr;
   int* tile_ctr = nullptr;
   void* tc_scratch = nullptr;
   std::vector<void*> allocs;
@@ -174,7 +175,7 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   WSA(nm, n); WSA(x0, n * 3); WSA(xa, n * 3); WSA(xb, n * 3); WSA(h, n * H); WSA(ABg, n * 2 * H); WSA(ABc, n * 2 * H);
   WSA(agg, n * H); WSA(z, n * xd); WSA(cls, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
   WSA(rowidx, n); WSA(colidx, n); WSA(xrowidx, n); WSA(nr, B); WSA(nc, B); WSA(nxr, B); WSA(n_items, 1);
-  WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(tile_ctr, 64);
+  WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(xitems, n); WSA(n_xitems, 1); WSA(tile_ctr, 64);
 #undef WSA
   ws.B = B; ws.N = N;
   return DL_OK;
@@ -184,6 +185,7 @@ Plan make_plan(const Workspace& ws) {
   Plan p;
   p.rowidx = ws.rowidx; p.colidx = ws.colidx; p.xrowidx = ws.xrowidx; p.nr = ws.nr; p.nc = ws.nc; p.nxr = ws.nxr;
   p.items = ws.items; p.n_items = ws.n_items; p.xmols = ws.xmols; p.n_xmols = ws.n_xmols;
+  p.xitems = ws.xitems; p.n_xitems = ws.n_xitems;
   return p;
 }
 
@@ -215,7 +217,7 @@ dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const 
   const int tile_edges = e->use_tc ? tc::TN : ET;
   const int max_rows = e->use_tc ? tc::MAXR : MAXR;
   k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols,
-                                ws.n_xmols);
+                                ws.n_xmols, ws.xitems, ws.n_xitems);
   LAUNCH_CHECK();
   e->launches += 2;
   return DL_OK;

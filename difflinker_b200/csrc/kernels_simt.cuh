@@ -61,9 +61,10 @@ __global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edg
 // complete rows (so the segment sum over j never crosses CTAs and stays order-deterministic).
 __global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __restrict__ nr,
                              const int* __restrict__ nc, const int* __restrict__ nxr, int4* __restrict__ items,
-                             int* __restrict__ n_items, int* __restrict__ xmols, int* __restrict__ n_xmols) {
+                             int* __restrict__ n_items, int* __restrict__ xmols, int* __restrict__ n_xmols,
+                             int4* __restrict__ xitems, int* __restrict__ n_xitems) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  int cnt = 0, xc = 0;
+  int cnt = 0, xc = 0, xi = 0;
   for (int b = 0; b < B; ++b) {
     int r = nr[b], c = nc[b];
     if (r > 0 && c > 0) {
@@ -71,10 +72,16 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __r
       if (per > max_rows) per = max_rows;
       for (int r0 = 0; r0 < r; r0 += per) items[cnt++] = make_int4(b, r0, min(per, r - r0), 0);
     }
-    if (nxr[b] > 0 && c > 0) xmols[xc++] = b;
+    if (nxr[b] > 0 && c > 0) {
+      xmols[xc++] = b;
+      int per = c >= tile_edges ? 1 : tile_edges / c;
+      if (per > max_rows) per = max_rows;
+      for (int r0 = 0; r0 < nxr[b]; r0 += per) xitems[xi++] = make_int4(b, r0, min(per, nxr[b] - r0), 0);
+    }
   }
   *n_items = cnt;
   *n_xmols = xc;
+  *n_xitems = xi;
 }
 
 // ------------------------------------------------------------------------------------------------

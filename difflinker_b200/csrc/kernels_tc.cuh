@@ -54,7 +54,7 @@ constexpr int N_TBL_WARPS = 3;
 constexpr int W_PROD = 12;                 // warps 12-27 (WG 3-6): producers (first Linear + SiLU -> fp16 operand tile)
 constexpr int N_PROD_WARPS = 16;
 constexpr int EDGE_TC_THREADS = 32 * (W_PROD + N_PROD_WARPS);   // 896
-constexpr int REGS_EPI = 56, REGS_CTRL = 40, REGS_PROD = 88;
+constexpr int REGS_EPI = 48, REGS_CTRL = 56, REGS_PROD = 88;
 
 // shared memory map (bytes from a 1024-aligned base)
 constexpr int OFF_WHI = 0;
@@ -220,16 +220,15 @@ struct TileIter {
   // blocked distribution: CTA c owns the contiguous work items [lo, hi) -- consecutive tiles then mostly belong to the
   // same molecule, so the table warps' and producers' L2 lines are reused while they are hot.
   __device__ TileIter(const Plan& p, int N_) : plan(p), N(N_), rt(0), c0(0) {
-    const int total = COORD ? *p.n_xmols : *p.n_items;
+    const int total = COORD ? *p.n_xitems : *p.n_items;
     const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
     wi = c * per + min(c, extra);
     n_work = wi + per + (c < extra ? 1 : 0);
   }
   __device__ bool next(Tile& t) {
     while (wi < n_work) {
-      int b, r_begin, r_count;
-      if (COORD) { b = plan.xmols[wi]; r_begin = 0; r_count = plan.nxr[b]; }
-      else { int4 it = plan.items[wi]; b = it.x; r_begin = it.y; r_count = it.z; }
+      const int4 it = COORD ? plan.xitems[wi] : plan.items[wi];
+      const int b = it.x, r_begin = it.y, r_count = it.z;
       const int nc = plan.nc[b];
       int per = nc >= TN ? 1 : TN / nc;
       if (per > MAXR) per = MAXR;
@@ -335,7 +334,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         }
         if (lane < cur.nrt) reinterpret_cast<int*>(tb + TBL_ROWNODE)[lane] = cur.rows[cur.slot0 + lane];
         bool any_rescale = false;
-#pragma unroll 2
+#pragma unroll
         for (int e = lane; e < TN; e += 32) {
           const int ev = min(e, Et - 1);                   // slots past Et mirror the last edge: producers may prefetch them
           const int rr = ev / cur.ncc, jj = ev - rr * cur.ncc;
