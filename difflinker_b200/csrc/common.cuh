@@ -28,6 +28,24 @@ __device__ __forceinline__ float usig_f(float u) {
   return u * r;
 }
 
+// ---- packed fp32x2 arithmetic (sm_100: FADD2 / FMUL2 / FFMA2 halve the issue slots of the SiLU pipelines) ----------
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Two sigmoids for three MUFU ops: 1/a and 1/b from ONE reciprocal of the product, (1/(ab))*b and (1/(ab))*a.
+// The exponent is clamped at 63 so the product stays finite (a, b <= 1 + 2^63); that only alters silu for
+// x < -43.7, where |silu(x)| < 5e-18.
+__device__ __forceinline__ float2 sigmoid_pair_log2(float2 u) {
+  const float2 den = __fadd2_rn(make_float2(ex2_approx(fminf(u.x, 63.0f)), ex2_approx(fminf(u.y, 63.0f))), make_float2(1.0f, 1.0f));
+  const float r = rcp_approx(den.x * den.y);
+  return __fmul2_rn(make_float2(r, r), make_float2(den.y, den.x));
+}
+// (u0, u1) -> (u0/(1+2^u0), u1/(1+2^u1)): two sigmoids in the log2 domain
+__device__ __forceinline__ float2 usig2(float2 u) { return __fmul2_rn(u, sigmoid_pair_log2(u)); }
+// (x0, x1) -> (silu(x0), silu(x1))
+__device__ __forceinline__ float2 silu2(float2 x) {
+  return __fmul2_rn(x, sigmoid_pair_log2(__fmul2_rn(x, make_float2(-1.4426950408889634f, -1.4426950408889634f))));
+}
+
 // Packed fp32 weights of one GCL (src/egnn.py:19-30). *_t = k-major ("transposed") [K][128].
 struct GclW {
   const float* W1a_t;  // [128][128]  edge_mlp.0.weight[:, 0:H]^T     (h_row part)

@@ -194,6 +194,14 @@ __device__ __forceinline__ uint32_t tmem_ld_x1(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// fp32 pair -> fp16x2 hi and lo words (packed subtract)
+__device__ __forceinline__ void split2v(float2 v, uint32_t& hi, uint32_t& lo) {
+  __half2 h = __float22half2_rn(v);
+  float2 back = __half22float2(h);
+  __half2 l = __float22half2_rn(__fadd2_rn(v, make_float2(-back.x, -back.y)));
+  hi = *reinterpret_cast<uint32_t*>(&h);
+  lo = *reinterpret_cast<uint32_t*>(&l);
+}
 // fp32 -> fp16 hi/lo pair of two values
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
   __half2 h = __floats2half2_rn(a, b);
@@ -433,9 +441,12 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS_PROD));
     const int pw = warp - W_PROD;
     const int kc = lane & 15, esub = lane >> 4;            // this thread always owns k = kc*8 .. kc*8+7
-    float wdr[8], w0r[8];
+    float2 wdr[4], w0r[4];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) { wdr[q] = __ldg(a.wd + kc * 8 + q); w0r[q] = __ldg(a.w0 + kc * 8 + q); }
+    for (int q = 0; q < 4; ++q) {
+      wdr[q] = make_float2(__ldg(a.wd + kc * 8 + 2 * q), __ldg(a.wd + kc * 8 + 2 * q + 1));
+      w0r[q] = make_float2(__ldg(a.w0 + kc * 8 + 2 * q), __ldg(a.w0 + kc * 8 + 2 * q + 1));
+    }
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1), s = t & (N_STAGE - 1);
       wait_on(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1, 0);
@@ -478,19 +489,21 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
           }
           if (e < Et) {
             const float d = dv[e], d0 = d0v[e];
-            const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-            const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-            float sv[8];
+            const float2 dd = make_float2(d, d), dd0 = make_float2(d0, d0);
+            const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+            const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+            float2 sv[4];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) sv[q] = silu_f(fmaf(d0, w0r[q], fmaf(d, wdr[q], av[q] + bv[q])));   // egnn.py:49-50
+            for (int q = 0; q < 4; ++q)                     // egnn.py:49-50, two channels per packed instruction
+              sv[q] = silu2(__ffma2_rn(dd0, w0r[q], __ffma2_rn(dd, wdr[q], __fadd2_rn(av[q], bv[q]))));
             if (rescale) {                                 // rare: diverging samples only (tile-uniform)
               const float sc = scv[e];
 #pragma unroll
-              for (int q = 0; q < 8; ++q) sv[q] *= sc;
+              for (int q = 0; q < 4; ++q) sv[q] = __fmul2_rn(sv[q], make_float2(sc, sc));
             }
             uint4 hi, lo;
-            split2(sv[0], sv[1], hi.x, lo.x); split2(sv[2], sv[3], hi.y, lo.y);
-            split2(sv[4], sv[5], hi.z, lo.z); split2(sv[6], sv[7], hi.w, lo.w);
+            split2v(sv[0], hi.x, lo.x); split2v(sv[1], hi.y, lo.y);
+            split2v(sv[2], hi.z, lo.z); split2v(sv[3], hi.w, lo.w);
             *reinterpret_cast<uint4*>(bhi + e * 16) = hi;
             *reinterpret_cast<uint4*>(blo + e * 16) = lo;
           }
@@ -529,7 +542,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         const float bias = b2w5[c].x * -1.4426950408889634f;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + acc * TN;
         for (int rr = (nrt == 1 ? hw : ((hw + t) & 1)); rr < nrt; rr += 2) {   // single-row (chunked) tiles: half 0 only
-          float accv = (nrt == 1 && !first_chunk) ? run : 0.f;
+          float2 acc2 = make_float2((nrt == 1 && !first_chunk) ? run : 0.f, 0.f);   // (even, odd) column partial sums
           const int col0 = rr * ncc;
           int jj = 0;
           for (; jj + 16 <= ncc; jj += 16) {
@@ -537,9 +550,11 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             TMEM_LD_X16(tlane + col0 + jj, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float2 ed = emds[col0 + jj + u];
-              accv = fmaf(usig_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+            for (int u = 0; u < 16; u += 2) {
+              const float2 e0 = emds[col0 + jj + u], e1 = emds[col0 + jj + u + 1];
+              const float2 uu = __ffma2_rn(make_float2(__uint_as_float(r[u]), __uint_as_float(r[u + 1])),
+                                           make_float2(e0.y, e1.y), make_float2(bias, bias));
+              acc2 = __ffma2_rn(usig2(uu), make_float2(e0.x, e1.x), acc2);
             }
           }
           if (ncc - jj >= 8) {
@@ -547,9 +562,11 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             TMEM_LD_X8(tlane + col0 + jj, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float2 ed = emds[col0 + jj + u];
-              accv = fmaf(usig_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+            for (int u = 0; u < 8; u += 2) {
+              const float2 e0 = emds[col0 + jj + u], e1 = emds[col0 + jj + u + 1];
+              const float2 uu = __ffma2_rn(make_float2(__uint_as_float(r[u]), __uint_as_float(r[u + 1])),
+                                           make_float2(e0.y, e1.y), make_float2(bias, bias));
+              acc2 = __ffma2_rn(usig2(uu), make_float2(e0.x, e1.x), acc2);
             }
             jj += 8;
           }
@@ -558,9 +575,11 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             TMEM_LD_X4(tlane + col0 + jj, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float2 ed = emds[col0 + jj + u];
-              accv = fmaf(usig_f(fmaf(__uint_as_float(r[u]), ed.y, bias)), ed.x, accv);
+            for (int u = 0; u < 4; u += 2) {
+              const float2 e0 = emds[col0 + jj + u], e1 = emds[col0 + jj + u + 1];
+              const float2 uu = __ffma2_rn(make_float2(__uint_as_float(r[u]), __uint_as_float(r[u + 1])),
+                                           make_float2(e0.y, e1.y), make_float2(bias, bias));
+              acc2 = __ffma2_rn(usig2(uu), make_float2(e0.x, e1.x), acc2);
             }
             jj += 4;
           }
@@ -568,8 +587,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             const uint32_t r = tmem_ld_x1(tlane + col0 + jj);
             tmem_ld_wait();
             const float2 ed = emds[col0 + jj];
-            accv = fmaf(usig_f(fmaf(__uint_as_float(r), ed.y, bias)), ed.x, accv);
+            acc2.x = fmaf(usig_f(fmaf(__uint_as_float(r), ed.y, bias)), ed.x, acc2.x);
           }
+          const float accv = acc2.x + acc2.y;
           if (nrt == 1) run = accv;
           if (last_chunk) a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
         }
@@ -581,18 +601,21 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + acc * TN;
         if (q * 32 < Et) {                                 // warp-uniform
           const float2 ed = emds[min(e, Et - 1)];
-          float phi = 0.f;
+          float2 phi2 = make_float2(0.f, 0.f);
 #pragma unroll 1
           for (int c0 = 0; c0 < H; c0 += 16) {
             uint32_t r[16];
             TMEM_LD_X16(tlane + c0, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int u = 0; u < 16; ++u) {
-              const float2 bw = b2w5[c0 + u];
-              phi = fmaf(silu_f(fmaf(__uint_as_float(r[u]), ed.y, bw.x)), bw.y, phi);       // coord_mlp.2 + .4
+            for (int u = 0; u < 16; u += 2) {
+              const float2 w0 = b2w5[c0 + u], w1 = b2w5[c0 + u + 1];
+              const float2 v = __ffma2_rn(make_float2(__uint_as_float(r[u]), __uint_as_float(r[u + 1])),
+                                          make_float2(ed.y, ed.y), make_float2(w0.x, w1.x));
+              phi2 = __ffma2_rn(silu2(v), make_float2(w0.y, w1.y), phi2);                  // coord_mlp.2 + .4
             }
           }
+          const float phi = phi2.x + phi2.y;
           if (e < Et) {
             const float* cd = reinterpret_cast<const float*>(tb + TBL_CD) + e * 3;
             const float w = phi * ed.x;                    // egnn.py:107-109
