@@ -100,11 +100,11 @@ struct Plan {
   const int* nr;       // [B]
   const int* nc;       // [B]
   const int* nxr;      // [B]
-  const int4* items;   // GCL work items (b, first row slot, row count, 0)
+  const int4* items;   // GCL work items (b, first row slot, row count, live column count nc)
   const int* n_items;  // [1]
   const int* xmols;    // molecules with nxr > 0 (coordinate-update work items of the SIMT kernel)
   const int* n_xmols;  // [1]
-  const int4* xitems;  // coordinate-update work items of the tcgen05 kernel: (b, first xrow slot, row count, 0)
+  const int4* xitems;  // coordinate-update work items of the tcgen05 kernel: (b, first xrow slot, row count, nc)
   const int* n_xitems; // [1]
 };
 

@@ -44,6 +44,7 @@ struct Workspace {
   float *nm = nullptr, *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *ABg = nullptr, *ABc = nullptr,
         *agg = nullptr, *z = nullptr, *ABgmax = nullptr, *ABcmax = nullptr;
   int* cls = nullptr;
+  float4 *x04 = nullptr, *xa4 = nullptr, *xb4 = nullptr;
   int *rowidx = nullptr, *colidx = nullptr, *xrowidx = nullptr, *nr = nullptr, *nc = nullptr, *nxr = nullptr,
       *n_items = nullptr, *xmols = nullptr, *n_xmols = nullptr, *n_xitems = nullptr;
   int4* items = nullptr;
@@ -173,7 +174,7 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   dl_status s;
 #define WSA(field, cnt) if ((s = dev_alloc(ws, &ws.field, (cnt))) != DL_OK) return s
   WSA(nm, n); WSA(x0, n * 3); WSA(xa, n * 3); WSA(xb, n * 3); WSA(h, n * H); WSA(ABg, n * 2 * H); WSA(ABc, n * 2 * H);
-  WSA(agg, n * H); WSA(z, n * xd); WSA(cls, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
+  WSA(agg, n * H); WSA(z, n * xd); WSA(cls, n); WSA(x04, n); WSA(xa4, n); WSA(xb4, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
   WSA(rowidx, n); WSA(colidx, n); WSA(xrowidx, n); WSA(nr, B); WSA(nc, B); WSA(nxr, B); WSA(n_items, 1);
   WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(xitems, n); WSA(n_xitems, 1); WSA(tile_ctr, 64);
 #undef WSA
@@ -265,7 +266,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   pa.node_mask = io.node_mask; pa.linker_mask = io.linker_mask;
   pa.t = io.t; pa.t_numel = io.t_numel; pa.context = io.context;
   pa.We_t = e->We_t; pa.be = e->be; pa.proj = proj_of(e->gcl[0]);
-  pa.nm = ws.nm; pa.x0 = ws.x0; pa.x = ws.xa; pa.cls = ws.cls; pa.h = ws.h; pa.AB = ws.ABg; pa.ABmax = ws.ABgmax;
+  pa.nm = ws.nm; pa.x0 = ws.x0; pa.x = ws.xa; pa.x04 = e->use_tc ? ws.x04 : nullptr; pa.x4 = e->use_tc ? ws.xa4 : nullptr; pa.cls = ws.cls; pa.h = ws.h; pa.AB = ws.ABg; pa.ABmax = ws.ABgmax;
   pa.coef = io.sampler ? e->coef_dev : nullptr;
   pa.step_prep = io.sampler ? e->step_ctr : nullptr;
   pa.step_fin = io.sampler ? e->step_ctr + 1 : nullptr;
@@ -275,6 +276,8 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
 
   float* xin = ws.xa;
   float* xout = ws.xb;
+  float4* xin4 = ws.xa4;
+  float4* xout4 = ws.xb4;
   const Plan plan = make_plan(ws);
   e->last_edge_mask = io.edge_mask; e->last_linker_mask = io.linker_mask; e->last_B = B; e->last_N = N;
   for (int l = 0; l < L; ++l) {
@@ -282,7 +285,8 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       const GclW& w = e->gcl[l * S + s];
       EdgeArgs ea{};
       ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
-      ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+      ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = nullptr;
+      ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
       ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
       ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr;
       dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st);
@@ -328,18 +332,20 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       LAUNCH_CHECK();
       e->launches += 1;
     }
-    k_copy_x<<<(n * 3 + 255) / 256, 256, 0, st>>>(n * 3, xin, xout);
+    k_copy_x<<<(n * 3 + 255) / 256, 256, 0, st>>>(n * 3, xin, xout, e->use_tc ? xin4 : nullptr, xout4);
     LAUNCH_CHECK();
     e->launches += 1;
     const EqW& w = e->eq[l];
     EdgeArgs ea{};
     ea.AB = ws.ABc; ea.ABmax = ws.ABcmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
-    ea.x = xin; ea.x0 = ws.x0; ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+    ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = xout4;
+    ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
     ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = w.w5;
     ea.plan = plan; ea.agg = nullptr; ea.x_out = xout;
     dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st);
     if (st2 != DL_OK) return st2;
     std::swap(xin, xout);
+    std::swap(xin4, xout4);
   }
 
   FinishArgs fa{};
@@ -750,7 +756,7 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   const GclW& w = e->gcl[0];
   EdgeArgs ea{};
   ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
-  ea.x = ws.xa; ea.x0 = ws.x0; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
+  ea.x = ws.xa; ea.x0 = ws.x0; ea.x4 = ws.xa4; ea.x04 = ws.x04; ea.x4_out = nullptr; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
   ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr;
   cudaStream_t st = e->loop_stream;

@@ -70,13 +70,13 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __r
     if (r > 0 && c > 0) {
       int per = c >= tile_edges ? 1 : tile_edges / c;
       if (per > max_rows) per = max_rows;
-      for (int r0 = 0; r0 < r; r0 += per) items[cnt++] = make_int4(b, r0, min(per, r - r0), 0);
+      for (int r0 = 0; r0 < r; r0 += per) items[cnt++] = make_int4(b, r0, min(per, r - r0), c);
     }
     if (nxr[b] > 0 && c > 0) {
       xmols[xc++] = b;
       int per = c >= tile_edges ? 1 : tile_edges / c;
       if (per > max_rows) per = max_rows;
-      for (int r0 = 0; r0 < nxr[b]; r0 += per) xitems[xi++] = make_int4(b, r0, min(per, nxr[b] - r0), 0);
+      for (int r0 = 0; r0 < nxr[b]; r0 += per) xitems[xi++] = make_int4(b, r0, min(per, nxr[b] - r0), c);
     }
   }
   *n_items = cnt;
@@ -179,6 +179,8 @@ struct PrepArgs {
   float* nm;                // out (B*N)
   float* x0;                // out (B*N,3)
   float* x;                 // out (B*N,3)
+  float4* x04;              // out (B*N) padded copies (x0 | x) for 16-byte gathers in the tcgen05 table warps; may be null
+  float4* x4;
   int* cls;                 // out (B*N) node class for pocket graphs: 0 invalid, 1 ligand, 2 pocket
   float* h;                 // out (B*N,128)
   float* AB;                // out (B*N,256)
@@ -227,6 +229,10 @@ __global__ void __launch_bounds__(256) k_prep(Geom gm, PrepArgs a) {
         float v = a.xh[(size_t)g * xd + d] * m;
         a.x0[(size_t)g * 3 + d] = v;
         a.x[(size_t)g * 3 + d] = v;
+        if (a.x4 != nullptr) {
+          reinterpret_cast<float*>(a.x04 + g)[d] = v;
+          reinterpret_cast<float*>(a.x4 + g)[d] = v;
+        }
       }
       if (gm.graph_type != 0) {
         // egnn.py:566-570: ligand = (linker | fragment_only) & valid ; pocket = pocket_only & valid
@@ -371,6 +377,9 @@ struct EdgeArgs {
   float w2_descale, wdmax, w0max;
   const float* x;           // (B*N,3) current coordinates
   const float* x0;          // (B*N,3) input coordinates (d0)
+  const float4* x4;         // (B*N) padded copies of x / x0 (tcgen05 path)
+  const float4* x04;
+  float4* x4_out;
   const int8_t* edge_mask;  // (B*N*N) or null
   const int* cls;           // (B*N) pocket classes (graph_type != 0)
   const float* nm;          // (B*N)
@@ -561,9 +570,11 @@ __global__ void __launch_bounds__(256, 1) k_edge_simt(Geom gm, EdgeArgs a) {
 
 // Rows the coordinate update does not touch keep x (x is already masked: (x + 0)*nm == x).
 // Runs before k_edge<COORD> writes the updated rows into the same buffer.
-__global__ void k_copy_x(int n3, const float* __restrict__ src, float* __restrict__ dst) {
+__global__ void k_copy_x(int n3, const float* __restrict__ src, float* __restrict__ dst, const float4* __restrict__ src4,
+                         float4* __restrict__ dst4) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n3) dst[i] = src[i];
+  if (src4 != nullptr && i * 3 < n3) dst4[i] = src4[i];
 }
 
 // ------------------------------------------------------------------------------------------------

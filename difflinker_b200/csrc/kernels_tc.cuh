@@ -221,30 +221,42 @@ struct Tile {
   const int* rows;
 };
 
+// Warp-synchronous (all 32 lanes of a table warp call it together): the CTA's contiguous slice of the work-item
+// list is read 32 items at a time with one coalesced load and served from registers by shuffles, so walking the
+// list costs no dependent global round trip per tile (items carry their molecule's live column count).
 template <bool COORD>
 struct TileIter {
-  const Plan& plan;
-  int N, n_work, wi, rt, c0;
-  // blocked distribution: CTA c owns the contiguous work items [lo, hi) -- consecutive tiles then mostly belong to the
-  // same molecule, so the table warps' and producers' L2 lines are reused while they are hot.
-  __device__ TileIter(const Plan& p, int N_) : plan(p), N(N_), rt(0), c0(0) {
+  const int4* list;
+  const int* rowlist;
+  int N, wi_end, wi, rt, c0, cache_base, lane;
+  int4 cache;
+  __device__ TileIter(const Plan& p, int N_) : N(N_), rt(0), c0(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31) {
+    // blocked distribution: CTA c owns the contiguous work items [lo, hi) -- consecutive tiles then mostly belong to
+    // the same molecule, so the table warps' and producers' L2 lines are reused while they are hot.
+    list = COORD ? p.xitems : p.items;
+    rowlist = COORD ? p.xrowidx : p.rowidx;
     const int total = COORD ? *p.n_xitems : *p.n_items;
     const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
     wi = c * per + min(c, extra);
-    n_work = wi + per + (c < extra ? 1 : 0);
+    wi_end = wi + per + (c < extra ? 1 : 0);
+    cache = make_int4(0, 0, 0, 0);
   }
   __device__ bool next(Tile& t) {
-    while (wi < n_work) {
-      const int4 it = COORD ? plan.xitems[wi] : plan.items[wi];
-      const int b = it.x, r_begin = it.y, r_count = it.z;
-      const int nc = plan.nc[b];
-      int per = nc >= TN ? 1 : TN / nc;
+    while (wi < wi_end) {
+      if (wi - cache_base >= 32) {                        // refill (warp-uniform)
+        cache_base = wi;
+        cache = list[min(wi + lane, wi_end - 1)];
+      }
+      const int src = wi - cache_base;
+      const int b = __shfl_sync(0xffffffffu, cache.x, src), r_begin = __shfl_sync(0xffffffffu, cache.y, src);
+      const int r_count = __shfl_sync(0xffffffffu, cache.z, src), nc = __shfl_sync(0xffffffffu, cache.w, src);
+      int per = nc >= TN ? 1 : TN / max(nc, 1);
       if (per > MAXR) per = MAXR;
       if (rt >= r_count || nc <= 0) { wi += 1; rt = 0; c0 = 0; continue; }
       t.b = b; t.nc = nc; t.slot0 = r_begin + rt; t.nrt = min(per, r_count - rt);
       t.c0 = c0; t.ncc = min(TN, nc - c0);
       t.first_chunk = c0 == 0; t.last_chunk = c0 + TN >= nc;
-      t.rows = (COORD ? plan.xrowidx : plan.rowidx) + (size_t)b * N;
+      t.rows = rowlist + (size_t)b * N;
       c0 += TN;
       if (c0 >= nc) { c0 = 0; rt += per; }
       return true;
@@ -348,11 +360,10 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
           const int rr = ev / cur.ncc, jj = ev - rr * cur.ncc;
           const int i = cur.rows[cur.slot0 + rr];
           const int j = a.plan.colidx[gb + cur.c0 + jj];
-          const float* xi = a.x + (gb + i) * 3; const float* xj = a.x + (gb + j) * 3;
-          const float* yi = a.x0 + (gb + i) * 3; const float* yj = a.x0 + (gb + j) * 3;
-          const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+          const float4 xi = a.x4[gb + i], xj = a.x4[gb + j], yi = a.x04[gb + i], yj = a.x04[gb + j];   // 16-byte gathers
+          const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
           const float d = dx * dx + dy * dy + dz * dz;                       // egnn.py:297-298
-          const float ex = yi[0] - yj[0], ey = yi[1] - yj[1], ez = yi[2] - yj[2];
+          const float ex = yi.x - yj.x, ey = yi.y - yj.y, ez = yi.z - yj.z;
           const float d0 = ex * ex + ey * ey + ez * ez;                      // egnn.py:220
           int ci = 0, cj = 0;
           if (gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
@@ -634,7 +645,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             const int i = rownode[rr];
             const float lm = a.linker_mask ? a.linker_mask[gb + i] : 1.f;
             const float xv = a.x[(gb + i) * 3 + dim];
-            a.x_out[(gb + i) * 3 + dim] = (xv + (sacc / gm.normalization_factor) * lm) * a.nm[gb + i];   // egnn.py:110-124
+            const float xn = (xv + (sacc / gm.normalization_factor) * lm) * a.nm[gb + i];                 // egnn.py:110-124
+            a.x_out[(gb + i) * 3 + dim] = xn;
+            reinterpret_cast<float*>(a.x4_out + gb + i)[dim] = xn;
           }
         }
         named_sync(2, 128);                                // txs and the table slot may be reused
