@@ -474,30 +474,38 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         uint8_t* blo = bhi + B_BYTES;
         const bool rescale = reinterpret_cast<const int*>(tb + TBL_HDR)[5] != 0;
         constexpr int ITEMS = TN / (2 * N_PROD_WARPS);       // 8 edges per thread per tile
-        // Two items of A_i / B_j chunks are kept in flight in registers (L1 is ~5 KB next to 222 KB of shared
-        // memory, so these loads are L2 round trips). Table slots past Et mirror the last edge: no clamping here.
-        float4 pa[2][2], pb[2][2];
-        const int e_base = 2 * pw + esub;
+        // Two B_j chunks are kept in flight in registers (L1 is ~5 KB next to 222 KB of shared memory, so these
+        // loads are L2 round trips). Table slots past Et mirror the last edge: no clamping here.
+        // A thread takes ITEMS consecutive edges of the tile: they share the row (almost always), so the A_i chunk is
+        // loaded once and only the B_j chunks stream -- L2->SM traffic of this role drops from 64 to ~40 bytes/item.
+        float4 pa0, pa1, pb[2][2];
+        const int e_base = ITEMS * (2 * pw + esub);
+        int ro_cur = rowoff[e_base];
+        {
+          const float* ap = a.AB + ro_cur + kc * 8;
+          pa0 = __ldg(reinterpret_cast<const float4*>(ap)); pa1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+        }
 #pragma unroll
         for (int pf = 0; pf < 2; ++pf) {
-          const int en = e_base + 2 * N_PROD_WARPS * pf;
-          const float* ap = a.AB + rowoff[en] + kc * 8;
-          const float* bp = a.AB + coloff[en] + kc * 8;
-          pa[pf][0] = __ldg(reinterpret_cast<const float4*>(ap)); pa[pf][1] = __ldg(reinterpret_cast<const float4*>(ap + 4));
+          const float* bp = a.AB + coloff[e_base + pf] + kc * 8;
           pb[pf][0] = __ldg(reinterpret_cast<const float4*>(bp)); pb[pf][1] = __ldg(reinterpret_cast<const float4*>(bp + 4));
         }
 #pragma unroll
         for (int it = 0; it < ITEMS; ++it) {
-          const int e = e_base + 2 * N_PROD_WARPS * it;
+          const int e = e_base + it;
           const int slot = it & 1;
-          const float4 a0 = pa[slot][0], a1 = pa[slot][1], b0 = pb[slot][0], b1 = pb[slot][1];
+          const float4 b0 = pb[slot][0], b1 = pb[slot][1];
           if (it + 2 < ITEMS) {
-            const int en = e + 4 * N_PROD_WARPS;
-            const float* ap = a.AB + rowoff[en] + kc * 8;
-            const float* bp = a.AB + coloff[en] + kc * 8;
-            pa[slot][0] = __ldg(reinterpret_cast<const float4*>(ap)); pa[slot][1] = __ldg(reinterpret_cast<const float4*>(ap + 4));
+            const float* bp = a.AB + coloff[e + 2] + kc * 8;
             pb[slot][0] = __ldg(reinterpret_cast<const float4*>(bp)); pb[slot][1] = __ldg(reinterpret_cast<const float4*>(bp + 4));
           }
+          const int ro = rowoff[e];
+          if (ro != ro_cur) {                              // row boundary inside this thread's run (rare): reload A_i
+            ro_cur = ro;
+            const float* ap = a.AB + ro + kc * 8;
+            pa0 = __ldg(reinterpret_cast<const float4*>(ap)); pa1 = __ldg(reinterpret_cast<const float4*>(ap + 4));
+          }
+          const float4 a0 = pa0, a1 = pa1;
           if (e < Et) {
             const float d = dv[e], d0 = d0v[e];
             const float2 dd = make_float2(d, d), dd0 = make_float2(d0, d0);
