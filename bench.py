@@ -33,6 +33,9 @@ def parse_args():
     ap.add_argument("--workload", default="cfg2_zinc")
     ap.add_argument("--edge-impl", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--T", type=int, default=None, help="override the number of reverse steps (debug only)")
+    ap.add_argument("--coord-gain", type=float, default=None,
+                    help="scale of coord_mlp.4 on top of the default init; default 100 (SURVEY 8c) for N <= 64, 1 above: "
+                         "with 100 and hundreds of neighbours the random-weight dynamics blow up to |x| ~ 5e3 within steps")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -200,8 +203,9 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     torch.manual_seed(0)
+    coord_gain = args.coord_gain if args.coord_gain is not None else (100.0 if spec.N <= 64 else 1.0)
     ddpm = DDPM(**hp, edge_impl=args.edge_impl)
-    synthetic.init_reference_like_weights(ddpm)
+    synthetic.init_reference_like_weights(ddpm, coord_gain=coord_gain)
     ddpm = ddpm.to(dev)
     if world > 1:
         broadcast_module_weights(ddpm, src=0, device=dev)       # the only collective on the path
@@ -295,11 +299,14 @@ def main():
     # ---------------- roofline of the dominant kernel (GCL edge kernel) ------------------------------------
     peaks = measured_peaks()
     H = 128
-    n_valid = spec.N                                                     # roofline workloads are unpadded
-    edge_flops = spec.B * (2 * H * H * n_valid * n_valid + 10 * H * n_valid * n_valid)
+    # algorithmic work of one forward, from the actual masks of the batch (ragged workloads included)
+    hb = host_batches[args.warmup]
+    n_b = hb['atom_mask'].reshape(spec.B, -1).sum(1).tolist()
+    l_b = hb['linker_mask'].reshape(spec.B, -1).sum(1).tolist()
+    edge_flops = sum((2 * H * H + 10 * H) * n * n for n in n_b)          # GCL edge kernel: second Linear + first layer/mask/sum
     ms_gcl = float(lib.dl_time_edge_kernel(eng, 20))
     fwd_ms = (sum(loop_ms) / len(loop_ms)) / (T + 1)
-    flops_fwd = spec.B * synthetic.flops_alg(n_valid, spec.l_max, spec)
+    flops_fwd = sum(synthetic.flops_alg(int(n), int(l), spec) for n, l in zip(n_b, l_b))
     bytes_fwd = spec.B * synthetic.bytes_alg(spec.N, spec)
     roofline = None
     if ms_gcl and ms_gcl > 0:
@@ -326,7 +333,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec.name, "B": spec.B, "N": spec.N, "n_layers": spec.L, "T": T, "hidden_nf": 128,
-                       "edge_impl": args.edge_impl, "l2": "working set per step (noise slab + activations) streams "
+                       "edge_impl": args.edge_impl, "coord_gain": coord_gain, "l2": "working set per step (noise slab + activations) streams "
                        "through; each step consumes a fresh 226 MB noise tensor > L2"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "forward": forward,
             "cpu_baseline": cpu, "loop_ms_device": loop_ms,

@@ -264,3 +264,63 @@ def test_simt_and_tcgen05_edge_paths_agree():
         outs[impl] = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'],
                              batch['fragment_mask'], dev())
     assert rel_err(outs["tcgen05"], outs["simt"]) <= 2e-5
+
+
+def test_pockets_full_size_slice_vs_oracle():
+    """BASELINE configs[3] shape (N=300: 22 fragment + 270 pocket + 8 linker atoms, FC-10A-4A cut-off graph, L=6),
+    a 3-molecule slice against the oracle's O((BN)^2) adjacency construction (egnn.py:565-596)."""
+    spec = synthetic.SPECS["cfg4_pockets"]
+    dyn, hp = helpers.build_dynamics(spec, 0)
+    batch = collate(synthetic.make_items(spec, batch=3))
+    z, t = helpers.random_latent(batch, 11)
+    ctx = helpers.context_of(batch, spec)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'],
+                                    batch['linker_mask'], batch['edge_mask'], ctx)
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], ctx, dev())
+    assert rel_err(got[..., :3], want[..., :3]) <= REL_TOL
+    assert rel_err(got[..., 3:], want[..., 3:]) <= REL_TOL
+
+
+@pytest.mark.parametrize("N", [128, 512])
+def test_sweep_sizes_vs_oracle(N):
+    """BASELINE configs[4] padded-N sweep end points (rows spanning 1 and 4 column chunks of the edge tile)."""
+    spec = synthetic.SPECS[f"cfg5_sweep_N{N}"]
+    spec2 = synthetic.WorkloadSpec(spec.name, B=2, N=N, n_min=N, l_min=8, l_max=8, F=8, L=2, T=10, seed=5)
+    dyn, hp = helpers.build_dynamics(spec2, 0)
+    batch = collate(synthetic.make_items(spec2))
+    z, t = helpers.random_latent(batch, 13)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'],
+                                    batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'])
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], batch['fragment_mask'], dev())
+    assert rel_err(got[..., :3], want[..., :3]) <= REL_TOL
+    assert rel_err(got[..., 3:], want[..., 3:]) <= REL_TOL
+
+
+def test_chain_T500_cfg1_vs_oracle():
+    """The headline chain length (T=500) on the small plumbing batch: 501 fused forwards against the oracle loop with
+    the same injected noise -- error must not accumulate beyond the 1e-4 tolerance."""
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    ddpm, hp = helpers.build_ddpm(spec, 0, diffusion_steps=500)
+    data = collate(synthetic.make_items(spec))
+    tpl = create_templates_for_linker_generation(data, data['linker_mask'].sum(1).view(-1).int())
+    B, N = tpl['positions'].shape[:2]
+    from difflinker_b200 import utils
+    x = utils.remove_partial_mean_with_mask(tpl['positions'], tpl['atom_mask'], tpl['fragment_mask'])
+    noise = helpers.noise_tensor(4242, 500, B, N, spec.F)
+    d = dev()
+    mv = lambda v: v.to(d)
+    chain = ddpm.edm.sample_chain(x=mv(x), h=mv(tpl['one_hot']), node_mask=mv(tpl['atom_mask']),
+                                  fragment_mask=mv(tpl['fragment_mask']), linker_mask=mv(tpl['linker_mask']),
+                                  edge_mask=mv(tpl['edge_mask']), context=mv(tpl['fragment_mask']), keep_frames=1,
+                                  noise=mv(noise)).cpu()
+    gam = orc.gamma_table(hp['diffusion_noise_schedule'], 500, hp['diffusion_noise_precision'])
+    with torch.no_grad():
+        want = orc.edm_sample_chain(ddpm.edm.dynamics.state_dict(), helpers.oracle_cfg(hp), gam, 500, x, tpl['one_hot'],
+                                    tpl['atom_mask'], tpl['fragment_mask'], tpl['linker_mask'], tpl['edge_mask'],
+                                    tpl['fragment_mask'], keep_frames=1, norm_values=tuple(hp['normalize_factors']),
+                                    noise_fn=helpers.seeded_noise(4242))
+    assert torch.equal(chain[0][..., 3:], want[0][..., 3:]), "atom types differ"
+    lm = tpl['linker_mask']
+    assert rel_err(chain[0][..., :3] * lm, want[0][..., :3] * lm) <= REL_TOL
