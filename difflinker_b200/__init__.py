@@ -9,7 +9,7 @@ All arithmetic of the path runs in libdifflinker_b200.so (csrc/, C-ABI in includ
 """
 from .batching import collate, create_templates_for_linker_generation  # noqa: F401
 from .ddpm import DDPM, accelerate  # noqa: F401
-from .edm import EDM  # noqa: F401
+from .edm import EDM, InpaintingEDM  # noqa: F401
 from .egnn import Dynamics, DynamicsWithPockets  # noqa: F401
 from .noise import PredefinedNoiseSchedule  # noqa: F401
 from .utils import FoundNaNException  # noqa: F401

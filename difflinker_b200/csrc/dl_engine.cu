@@ -42,7 +42,7 @@ namespace {
 struct Workspace {
   int B = 0, N = 0;
   float *nm = nullptr, *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *ABg = nullptr, *ABc = nullptr,
-        *agg = nullptr, *z = nullptr, *ABgmax = nullptr, *ABcmax = nullptr;
+        *agg = nullptr, *z = nullptr, *ABgmax = nullptr, *ABcmax = nullptr, *eps = nullptr;
   int* cls = nullptr;
   float4 *x04 = nullptr, *xa4 = nullptr, *xb4 = nullptr;
   int *rowidx = nullptr, *colidx = nullptr, *xrowidx = nullptr, *nr = nullptr, *nc = nullptr, *nxr = nullptr,
@@ -174,7 +174,7 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   dl_status s;
 #define WSA(field, cnt) if ((s = dev_alloc(ws, &ws.field, (cnt))) != DL_OK) return s
   WSA(nm, n); WSA(x0, n * 3); WSA(xa, n * 3); WSA(xb, n * 3); WSA(h, n * H); WSA(ABg, n * 2 * H); WSA(ABc, n * 2 * H);
-  WSA(agg, n * H); WSA(z, n * xd); WSA(cls, n); WSA(x04, n); WSA(xa4, n); WSA(xb4, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
+  WSA(agg, n * H); WSA(z, n * xd); WSA(eps, n * xd); WSA(cls, n); WSA(x04, n); WSA(xa4, n); WSA(xb4, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
   WSA(rowidx, n); WSA(colidx, n); WSA(xrowidx, n); WSA(nr, B); WSA(nc, B); WSA(nxr, B); WSA(n_items, 1);
   WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(xitems, n); WSA(n_xitems, 1); WSA(tile_ctr, 64);
 #undef WSA
@@ -231,7 +231,8 @@ struct FwdIO {
   const int8_t* node_mask = nullptr; const float* linker_mask = nullptr; const int8_t* edge_mask = nullptr;
   const float* context = nullptr; int* nan_flags = nullptr;
   // sampler mode
-  bool sampler = false; const float* fragment_mask = nullptr; const float* noise = nullptr; float* chain = nullptr;
+  bool sampler = false; bool inpaint = false; const float* xh0 = nullptr; const float* upd_linker_mask = nullptr;
+  const float* fragment_mask = nullptr; const float* noise = nullptr; float* chain = nullptr;
   int T = 0; float norm0 = 1.f, norm1 = 1.f, bias1 = 0.f;
 };
 
@@ -350,15 +351,32 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
 
   FinishArgs fa{};
   fa.h = ws.h; fa.x = xin; fa.x0 = ws.x0; fa.nm = ws.nm; fa.Wo = e->Wo; fa.bo = e->bo;
-  fa.out = io.sampler ? nullptr : io.out; fa.nan_flags = io.nan_flags;
-  if (io.sampler) {
+  fa.nan_flags = io.nan_flags;
+  const bool fused_update = io.sampler && !io.inpaint;
+  fa.out = fused_update ? nullptr : (io.sampler ? ws.eps : io.out);
+  if (fused_update) {
     fa.z = ws.z; fa.fragment_mask = io.fragment_mask; fa.linker_mask = io.linker_mask; fa.noise = io.noise;
     fa.coef = e->coef_dev; fa.step_fin = e->step_ctr + 1; fa.step_prep = e->step_ctr; fa.T = io.T;
     fa.norm0 = io.norm0; fa.norm1 = io.norm1; fa.bias1 = io.bias1; fa.chain = io.chain;
+  } else if (io.sampler) {
+    fa.tag_step = e->step_ctr + 1;
   }
   k_finish<<<(n + 15) / 16, 256, 0, st>>>(gm, fa);
   LAUNCH_CHECK();
   e->launches += 1;
+  if (e->cfg.centering || io.inpaint) {
+    // per-molecule stage of inpainting models: centring of the velocity (egnn.py:444-445) and, in the sampler,
+    // the whole reverse step incl. the centre-of-mass projection (edm.py:549-612)
+    InpaintArgs ia{};
+    ia.mode = io.inpaint ? 1 : 0;
+    ia.eps = io.inpaint ? ws.eps : io.out; ia.nm = ws.nm; ia.z = ws.z; ia.xh0 = io.xh0;
+    ia.fragment_mask = io.fragment_mask; ia.linker_mask = io.upd_linker_mask; ia.noise = io.noise; ia.coef = e->coef_dev;
+    ia.step_prep = e->step_ctr; ia.step_fin = e->step_ctr + 1; ia.T = io.T;
+    ia.norm0 = io.norm0; ia.norm1 = io.norm1; ia.bias1 = io.bias1; ia.chain = io.chain;
+    k_inpaint<<<B, 256, 0, st>>>(gm, ia);
+    LAUNCH_CHECK();
+    e->launches += 1;
+  }
   return DL_OK;
 }
 
@@ -568,7 +586,6 @@ dl_status dl_dynamics_forward(dl_engine* e, int32_t B, int32_t N, const float* t
   if (!xh || !node_mask || !out) { set_err("xh/node_mask/out must not be null"); return DL_ERR_INVALID; }
   if (e->cfg.condition_time && (!t || (t_numel != 1 && t_numel != B))) { set_err("t must hold 1 or B values"); return DL_ERR_INVALID; }
   if (e->cfg.context_node_nf > 0 && !context) { set_err("context required (context_node_nf=%d)", e->cfg.context_node_nf); return DL_ERR_INVALID; }
-  if (e->cfg.centering) { set_err("centering (inpainting models) is not implemented yet"); return DL_ERR_UNSUPPORTED; }
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if ((s = ensure_workspace(e, B, N)) != DL_OK) return s;
@@ -625,8 +642,9 @@ dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, i
                           int32_t* nan_flags, void* stream) {
   dl_status s = check_shapes(e, B, N);
   if (s != DL_OK) return s;
-  if (sampler != DL_SAMPLER_LINKER) { set_err("inpainting sampler is not implemented yet"); return DL_ERR_UNSUPPORTED; }
-  if (e->cfg.centering) { set_err("centering (inpainting models) is not implemented yet"); return DL_ERR_UNSUPPORTED; }
+  if (sampler != DL_SAMPLER_LINKER && sampler != DL_SAMPLER_INPAINT) { set_err("unknown sampler %d", sampler); return DL_ERR_INVALID; }
+  const bool inpaint = sampler == DL_SAMPLER_INPAINT;
+  if (inpaint != (e->cfg.centering != 0)) { set_err("the inpainting sampler needs a model built with centering=1 (and vice versa)"); return DL_ERR_INVALID; }
   if (!xh || !node_mask || !fragment_mask || !linker_mask || !noise || !coef || !norm || !chain) {
     set_err("null argument"); return DL_ERR_INVALID;
   }
@@ -654,13 +672,20 @@ dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, i
   const int n = B * N, xd = 3 + e->cfg.in_node_nf;
   // frames that no reverse step is the last writer of stay zero, as torch.zeros in edm.py:143
   CK(cudaMemsetAsync(chain, 0, (size_t)keep_frames * n * xd * sizeof(float), st));
-  k_init_z<<<(n * xd + 255) / 256, 256, 0, st>>>(n, xd, xh, fragment_mask, linker_mask, noise, e->ws.z);
-  LAUNCH_CHECK();
-  e->launches += 1;
-  if ((s = build_plan(e, B, N, node_mask, linker_mask, edge_mask, st)) != DL_OK) return s;
+  if (inpaint) {
+    // z_T = COM-free masked noise on every atom (edm.py:565); the caller's slab 0 is already masked and projected
+    CK(cudaMemcpyAsync(e->ws.z, noise, (size_t)n * xd * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  } else {
+    k_init_z<<<(n * xd + 255) / 256, 256, 0, st>>>(n, xd, xh, fragment_mask, linker_mask, noise, e->ws.z);
+    LAUNCH_CHECK();
+    e->launches += 1;
+  }
+  // inpainting: the dynamics see linker_mask=None (edm.py:632), so every live row gets a coordinate update
+  if ((s = build_plan(e, B, N, node_mask, inpaint ? nullptr : linker_mask, edge_mask, st)) != DL_OK) return s;
 
   FwdIO io;
-  io.sampler = true; io.node_mask = node_mask; io.linker_mask = linker_mask; io.edge_mask = edge_mask;
+  io.sampler = true; io.inpaint = inpaint; io.xh0 = xh; io.upd_linker_mask = linker_mask;
+  io.node_mask = node_mask; io.linker_mask = inpaint ? nullptr : linker_mask; io.edge_mask = edge_mask;
   io.context = context; io.nan_flags = nan_flags; io.fragment_mask = fragment_mask; io.noise = noise;
   io.chain = chain; io.T = T; io.norm0 = norm[0]; io.norm1 = norm[1]; io.bias1 = norm[2];
 
@@ -711,9 +736,10 @@ dl_status dl_sample_chain_host(dl_engine* e, int32_t sampler, int32_t B, int32_t
   const size_t n = (size_t)B * N;
   const int xd = 3 + e->cfg.in_node_nf, C = e->cfg.context_node_nf;
   const bool has_em = edge_mask && e->cfg.graph_type == DL_GRAPH_FC;
+  const size_t n_slabs = sampler == DL_SAMPLER_INPAINT ? (size_t)2 * T + 3 : (size_t)T + 2;
   const size_t o_xh = 0, o_nm = o_xh + align256(n * xd * 4), o_fm = o_nm + align256(n), o_lm = o_fm + align256(n * 4),
                o_em = o_lm + align256(n * 4), o_ctx = o_em + align256(has_em ? n * N : 1),
-               o_nz = o_ctx + align256(n * std::max(C, 1) * 4), o_ch = o_nz + align256((size_t)(T + 2) * n * xd * 4),
+               o_nz = o_ctx + align256(n * std::max(C, 1) * 4), o_ch = o_nz + align256((size_t)n_slabs * n * xd * 4),
                o_fl = o_ch + align256((size_t)keep_frames * n * xd * 4), total = o_fl + align256(B * 4);
   if ((s = stage_reserve(e, total)) != DL_OK) return s;
   char* d = e->stage.buf;
@@ -724,7 +750,7 @@ dl_status dl_sample_chain_host(dl_engine* e, int32_t sampler, int32_t B, int32_t
   CK(cudaMemcpyAsync(d + o_lm, linker_mask, n * 4, cudaMemcpyHostToDevice, st));
   if (has_em) CK(cudaMemcpyAsync(d + o_em, edge_mask, n * N, cudaMemcpyHostToDevice, st));
   if (context) CK(cudaMemcpyAsync(d + o_ctx, context, n * C * 4, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(d + o_nz, noise, (size_t)(T + 2) * n * xd * 4, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(d + o_nz, noise, n_slabs * n * xd * 4, cudaMemcpyHostToDevice, st));
   s = dl_sample_chain(e, sampler, B, N, T, keep_frames, (const float*)(d + o_xh), (const int8_t*)(d + o_nm),
                       (const float*)(d + o_fm), (const float*)(d + o_lm), has_em ? (const int8_t*)(d + o_em) : nullptr,
                       context ? (const float*)(d + o_ctx) : nullptr, (const float*)(d + o_nz), coef, norm,

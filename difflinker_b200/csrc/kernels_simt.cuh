@@ -600,6 +600,7 @@ struct FinishArgs {
   int T;
   float norm0, norm1, bias1;
   float* chain;          // (keep,B*N,3+F)
+  const int* tag_step;   // non-sampler mode inside the inpainting loop: step counter used to tag NaN flags (or null)
 };
 
 __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
@@ -612,6 +613,8 @@ __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
   if (a.z != nullptr) {
     step = *a.step_fin;
     if (blockIdx.x == 0 && tid == 0) *a.step_prep = step + 1;
+  } else if (a.tag_step != nullptr) {
+    step = *a.tag_step;
   }
   const bool act = g < n_total && d < xd;
   float e = 0.f;
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
       // bit0: NaN in vel, bit1: NaN in h (utils.py:274-282); bits 8.. = 1 + index of the first failing
       // reverse step. Later steps do not add bits: the reference raises at the first failing step.
       const int bits = d < 3 ? 1 : 2;
-      const int tag = (a.z != nullptr ? step + 1 : 0) << 8;
+      const int tag = ((a.z != nullptr || a.tag_step != nullptr) ? step + 1 : 0) << 8;
       int* p = a.nan_flags + g / gm.N;
       const int old = atomicCAS(p, 0, bits | tag);
       if (old != 0 && (old & ~0xff) == tag) atomicOr(p, bits);
@@ -686,6 +689,127 @@ __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
       a.chain[(size_t)g * xd + d] = o;                                        // chain[0], edm.py:174
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Per-molecule stage of inpainting models (one CTA per molecule; deterministic tree reductions):
+//   mode 0: Dynamics.forward with centering=True -- vel -= mean_valid(vel) * node_mask  (egnn.py:444-445, utils.py:56-63)
+//   mode 1: one reverse step of InpaintingEDM.sample_chain (edm.py:549-612): centred eps, p(z_s|z_t) on all atoms,
+//           q(z_s|z_t,x) on the fragment atoms, recombination, centre-of-mass projection, chain frame;
+//           the last row does sample_p_xh_given_z0 / sample_q_xh_given_z0_and_x (edm.py:689-721).
+// Noise slabs arrive already masked and COM-projected (utils.py:158-168): slab 0 = init, 1+2r / 2+2r = step r
+// (all atoms / fragment atoms), 2T+1 / 2T+2 = final draws.
+// ------------------------------------------------------------------------------------------------
+struct InpaintArgs {
+  int mode;
+  float* eps;               // (B*N,3+F) raw dynamics output (k_finish); mode 0: centred in place
+  const float* nm;          // (B*N)
+  float* z;                 // (B*N,3+F)
+  const float* xh0;         // (B*N,3+F) normalised input (fragments are re-noised from it)
+  const float* fragment_mask; const float* linker_mask;
+  const float* noise;
+  const float* coef;
+  int* step_prep; const int* step_fin;
+  int T;
+  float norm0, norm1, bias1;
+  float* chain;
+};
+
+__device__ __forceinline__ float block_sum_256(float v, float* red) {
+  // fixed-shape tree: warp shuffles then 8 partials summed in order by every thread
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < 8; ++w) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(256) k_inpaint(Geom gm, InpaintArgs a) {
+  __shared__ float red[8];
+  __shared__ float means[4];
+  const int b = blockIdx.x, tid = threadIdx.x, N = gm.N, xd = 3 + gm.F;
+  const size_t g0 = (size_t)b * N;
+  int step = 0;
+  if (a.mode == 1) step = *a.step_fin;
+  // number of valid atoms and mean velocity
+  float cnt = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
+  for (int n = tid; n < N; n += 256) {
+    const float m = a.nm[g0 + n];
+    cnt += m;
+    sx += a.eps[(g0 + n) * xd + 0]; sy += a.eps[(g0 + n) * xd + 1]; sz += a.eps[(g0 + n) * xd + 2];
+  }
+  cnt = block_sum_256(cnt, red);
+  sx = block_sum_256(sx, red); sy = block_sum_256(sy, red); sz = block_sum_256(sz, red);
+  const float mvx = sx / cnt, mvy = sy / cnt, mvz = sz / cnt;        // utils.py:60-61
+  if (a.mode == 0) {
+    for (int n = tid; n < N; n += 256) {
+      const float m = a.nm[g0 + n];
+      a.eps[(g0 + n) * xd + 0] -= mvx * m; a.eps[(g0 + n) * xd + 1] -= mvy * m; a.eps[(g0 + n) * xd + 2] -= mvz * m;
+    }
+    return;
+  }
+  const float* cf = a.coef + (size_t)step * 8;
+  const float ca = cf[1], cb = cf[2], cc = cf[3], qa = cf[5], qb = cf[6];
+  const int frame = __float_as_int(cf[4]);
+  const size_t slab = (size_t)gm.B * N * xd;
+  const float* nA = a.noise + (size_t)(1 + 2 * step) * slab;
+  const float* nB = nA + slab;
+  if (step < a.T) {
+    // pass 1: new latent before the centre-of-mass projection
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    for (int idx = tid; idx < N * xd; idx += 256) {
+      const int n = idx / xd, d = idx - n * xd;
+      const float m = a.nm[g0 + n], lm = a.linker_mask[g0 + n], fm = a.fragment_mask[g0 + n];
+      const size_t gi = (g0 + n) * xd + d;
+      float e = a.eps[gi];
+      if (d < 3) e -= (d == 0 ? mvx : d == 1 ? mvy : mvz) * m;
+      const float zt = a.z[gi];
+      const float zl = (zt / ca - cb * e) + cc * nA[gi];                         // edm.py:634-642
+      const float zf = (qa * zt + qb * (a.xh0[gi] * fm)) + cc * nB[gi];           // edm.py:655-668
+      const float zn = zl * lm + zf * fm;                                        // edm.py:589
+      a.z[gi] = zn;
+      if (d == 0) cx += zn; else if (d == 1) cy += zn; else if (d == 2) cz += zn;
+    }
+    cx = block_sum_256(cx, red); cy = block_sum_256(cy, red); cz = block_sum_256(cz, red);
+    if (tid == 0) { means[0] = cx / cnt; means[1] = cy / cnt; means[2] = cz / cnt; }
+    __syncthreads();
+    for (int idx = tid; idx < N * xd; idx += 256) {
+      const int n = idx / xd, d = idx - n * xd;
+      const size_t gi = (g0 + n) * xd + d;
+      float zn = a.z[gi];
+      if (d < 3) { zn -= means[d] * a.nm[g0 + n]; a.z[gi] = zn; }                // edm.py:592, utils.py:56-63
+      if (frame >= 0) a.chain[(size_t)frame * slab + gi] = d < 3 ? zn * a.norm0 : zn * a.norm1 + a.bias1;
+    }
+  } else {
+    // final step: thread per atom, both variants and their argmax (edm.py:689-721)
+    for (int n = tid; n < N; n += 256) {
+      const float m = a.nm[g0 + n], lm = a.linker_mask[g0 + n], fm = a.fragment_mask[g0 + n];
+      int bl = 0, bf = 0;
+      float vl = -INFINITY, vf = -INFINITY;
+      for (int d = 0; d < xd; ++d) {
+        const size_t gi = (g0 + n) * xd + d;
+        float e = a.eps[gi];
+        if (d < 3) e -= (d == 0 ? mvx : d == 1 ? mvy : mvz) * m;
+        const float zt = a.z[gi];
+        const float xl = ca * (zt - cb * e) + cc * nA[gi];                       // edm.py:701-702 (ca = 1/alpha_0, cb = sigma_0)
+        const float xf = ca * zt - qa * nB[gi];                                  // edm.py:716 (qa = sigma_0/alpha_0)
+        if (d < 3) {
+          a.chain[gi] = (xl * a.norm0) * lm + (xf * a.norm0) * fm;
+        } else {
+          const float hl = xl * a.norm1 + a.bias1, hf = xf * a.norm1 + a.bias1;
+          if (hl > vl) { vl = hl; bl = d; }
+          if (hf > vf) { vf = hf; bf = d; }
+        }
+      }
+      for (int d = 3; d < xd; ++d)
+        a.chain[(g0 + n) * xd + d] = ((d == bl ? 1.f : 0.f) * m) * lm + ((d == bf ? 1.f : 0.f) * m) * fm;
+    }
+  }
+  if (tid == 0 && b == 0) *a.step_prep = step + 1;
 }
 
 // z0 = xh*fragment_mask + (noise[0]*linker_mask)*linker_mask   (edm.py:136-137)

@@ -13,7 +13,7 @@ import torch.nn as nn
 
 from . import utils
 from .batching import create_templates_for_linker_generation
-from .edm import EDM
+from .edm import EDM, InpaintingEDM
 from .egnn import Dynamics, DynamicsWithPockets
 
 
@@ -22,8 +22,6 @@ def _build_edm(hp: dict, edge_impl='auto'):
     graph_type = hp.get('graph_type')
     if graph_type is None:
         graph_type = '4A' if pocket else 'FC'                              # lightning.py:75-76
-    if hp.get('inpainting'):
-        raise NotImplementedError("InpaintingEDM (src/edm.py:466-730) is a 'next' row, not implemented yet")
     activation = hp.get('activation', 'silu')
     if isinstance(activation, str):
         if activation != 'silu':
@@ -38,7 +36,8 @@ def _build_edm(hp: dict, edge_impl='auto'):
         normalization_factor=hp['normalization_factor'], aggregation_method=hp['aggregation_method'],
         model=hp['model'], normalization=hp.get('normalization'), centering=bool(hp.get('inpainting', False)),
         graph_type=graph_type, edge_impl=edge_impl)
-    return EDM(dynamics=dynamics, in_node_nf=hp['in_node_nf'], n_dims=hp['n_dims'],
+    edm_cls = InpaintingEDM if hp.get('inpainting') else EDM                 # lightning.py:102
+    return edm_cls(dynamics=dynamics, in_node_nf=hp['in_node_nf'], n_dims=hp['n_dims'],
                timesteps=hp['diffusion_steps'], noise_schedule=hp['diffusion_noise_schedule'],
                noise_precision=hp['diffusion_noise_precision'], loss_type=hp['diffusion_loss_type'],
                norm_values=hp['normalize_factors'])

@@ -175,3 +175,105 @@ class EDM(torch.nn.Module):
         if bad:
             raise FoundNaNException(flags=flags.cpu().tolist())
         return chain
+
+
+class InpaintingEDM(EDM):
+    """Full-molecule variant (reference: src/edm.py:466-730, sampling half): every atom is denoised by the network
+    (`linker_mask=None`, dynamics built with centering=True), fragment atoms are then re-noised from the known
+    fragments with q(z_s | z_t, x), and the centre of mass is projected out every step.
+    NB the reference's positional order differs from EDM.sample_chain (edge_mask comes third): call by keyword."""
+
+    @staticmethod
+    def _com_free(x, mask):
+        """utils.sample_center_gravity_zero_gaussian_with_mask (utils.py:158-168) applied to a raw draw."""
+        xm = x * mask
+        return xm - (xm.sum(dim=-2, keepdim=True) / mask.sum(dim=-2, keepdim=True)) * mask
+
+    def draw_noise_inpaint(self, n_samples, n_nodes, device, node_mask, fragment_mask, generator=None):
+        """(2T+3, B, N, 3+F): the reference's draws in call order, already masked and COM-projected:
+        init (all atoms); per step: p(z_s|z_t) on all atoms then q(z_s|z_t,x) on fragment atoms; final p and q draws."""
+        T, nd, nf = self.T, self.n_dims, self.in_node_nf
+        masks = [node_mask] + [node_mask, fragment_mask] * T + [node_mask, node_mask]
+        out = torch.empty((len(masks), n_samples, n_nodes, nd + nf), device=device, dtype=torch.float32)
+        for r, m in enumerate(masks):
+            m = m.to(device=device, dtype=torch.float32)
+            out[r, :, :, :nd] = self._com_free(torch.randn((n_samples, n_nodes, nd), device=device, generator=generator), m)
+            out[r, :, :, nd:] = torch.randn((n_samples, n_nodes, nf), device=device, generator=generator) * m
+        return out
+
+    def step_coefficients(self, keep_frames, n_samples=1):
+        rows = super().step_coefficients(keep_frames, n_samples)
+        if getattr(self, '_qcoef_key', None) == self._coef_cache[0]:
+            return rows
+        T = self.T
+        gamma = PredefinedNoiseSchedule.__new__(PredefinedNoiseSchedule)
+        torch.nn.Module.__init__(gamma)
+        gamma.timesteps = self.gamma.timesteps
+        gamma.gamma = torch.nn.Parameter(self.gamma.gamma.detach().cpu(), requires_grad=False)
+        for r in range(T):
+            s = T - 1 - r
+            s_arr = torch.full((n_samples, 1), fill_value=s)
+            t_arr = (s_arr + 1) / T
+            s_arr = s_arr / T
+            g_s, g_t = gamma(s_arr), gamma(t_arr)
+            sigma2_ts, _, alpha_ts = self.sigma_and_alpha_t_given_s(g_t, g_s)
+            sigma_s, sigma_t, alpha_s = self.sigma(g_s), self.sigma(g_t), self.alpha(g_s)
+            rows[r].qa = float((alpha_ts * (sigma_s ** 2) / (sigma_t ** 2))[0])      # edm.py:661-664
+            rows[r].qb = float((alpha_s * sigma2_ts / (sigma_t ** 2))[0])
+            # the chain frame is written after the COM projection by the per-molecule kernel: frame 0 is live too
+            frame = (s * keep_frames) // T
+            last_writer = (s == 0 or ((s - 1) * keep_frames) // T != frame) and frame > 0
+            rows[r].frame = frame if last_writer else -1
+        g0 = gamma(torch.zeros(size=(n_samples, 1)))
+        rows[T].qa = float((self.sigma(g0) / self.alpha(g0))[0])                      # edm.py:716
+        self._qcoef_key = self._coef_cache[0]
+        return rows
+
+    @torch.no_grad()
+    def sample_chain(self, x, h, node_mask, edge_mask, fragment_mask, linker_mask, context, keep_frames=None,
+                     noise=None):
+        lib = _native.load_library()
+        n_samples, n_nodes = x.size(0), x.size(1)
+        dev = x.device
+        T = self.T
+        if keep_frames is None:
+            keep_frames = T
+        else:
+            assert keep_frames <= T
+        d = self.n_dims + self.in_node_nf
+        xn, hn = self.normalize(x, h)
+        xh = torch.cat([xn, hn], dim=2).to(torch.float32).contiguous()
+        if noise is None:
+            noise = self.draw_noise_inpaint(n_samples, n_nodes, dev, node_mask, fragment_mask)
+        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+        assert noise.shape == (2 * T + 3, n_samples, n_nodes, d), noise.shape
+        eng = self.dynamics.engine(self.dynamics._device_index(x))
+        self.dynamics._check_graph_type()
+        prep = lambda v, dt: None if v is None else v.detach().to(device=dev, dtype=dt).contiguous()
+        nm = prep(node_mask.reshape(n_samples, n_nodes), torch.int8)
+        fm = prep(fragment_mask.reshape(n_samples, n_nodes), torch.float32)
+        lm = prep(linker_mask.reshape(n_samples, n_nodes), torch.float32)
+        em = None
+        if self.dynamics.graph_type == 'FC' and edge_mask is not None:
+            em = prep(edge_mask.reshape(-1), torch.int8)
+        ctx = None if context is None else prep(context.reshape(n_samples, n_nodes, -1), torch.float32)
+        coef = self.step_coefficients(keep_frames, n_samples)
+        norm = (C.c_float * 3)(float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]))
+        chain = torch.empty((keep_frames, n_samples, n_nodes, d), device=dev, dtype=torch.float32)
+        flags = torch.zeros(n_samples, dtype=torch.int32, device=dev)
+        ptr = lambda v: None if v is None else v.data_ptr()
+        args = (eng, _native.SAMPLER_INPAINT, n_samples, n_nodes, T, keep_frames, ptr(xh), ptr(nm), ptr(fm), ptr(lm),
+                ptr(em), ptr(ctx), ptr(noise), coef, norm, ptr(chain), ptr(flags))
+        if dev.type == 'cuda':
+            with torch.cuda.device(dev):
+                st = lib.dl_sample_chain(*args, torch.cuda.current_stream(dev).cuda_stream)
+                _native.check(st, "dl_sample_chain")
+                bad = bool(flags.any().item())
+        else:
+            st = lib.dl_sample_chain_host(*args)
+            _native.check(st, "dl_sample_chain_host")
+            bad = st == _native.DL_NAN_DETECTED
+        self.last_loop_ms = float(lib.dl_last_elapsed_ms(eng))
+        if bad:
+            raise FoundNaNException(flags=flags.cpu().tolist())
+        return chain

@@ -123,8 +123,15 @@ dl_status dl_dynamics_forward_host(dl_engine* e, int32_t B, int32_t N, const flo
  *   fragment_mask, linker_mask (B,N) fp32 DEVICE; node_mask (B,N) int8; edge_mask, context as above
  *   noise      (T+2,B,N,3+F) UNMASKED standard normal draws, DEVICE: slab 0 initialises the linker,
  *              slab 1+r feeds reverse step r, slab T+1 the final p(x|z0) draw -- i.e. the reference's
- *              torch.randn call order (edm.py:328-345).  For DL_SAMPLER_INPAINT: (2T+3,...) slabs in the
- *              order edm.py:565,577-592,605-610 consumes them.
+ *              torch.randn call order (edm.py:328-345).
+ *              DL_SAMPLER_INPAINT (edm.py:549-727): (2T+3,B,N,3+F) PREPARED draws in the order the reference consumes
+ *              them -- slab 0 initial z; slabs 1+2r / 2+2r the p(z_s|z_t) (all atoms) and q(z_s|z_t,x) (fragment atoms)
+ *              draws of reverse step r; slabs 2T+1 / 2T+2 the final p(x|z0) and q(x|z0,x) draws -- each already
+ *              multiplied by its mask with the coordinate part projected to zero centre of mass
+ *              (utils.sample_center_gravity_zero_gaussian_with_mask, utils.py:158-168).  The engine must have been
+ *              created with centering = 1 (lightning.py:99); all atoms move (the dynamics get linker_mask = NULL),
+ *              the latent is re-centred every step (edm.py:592-594) and chain[0] mixes the two final variants by
+ *              linker_mask / fragment_mask (edm.py:603-608).
  *   coef       (T+1) dl_step_coef, HOST
  *   norm       {norm_values[0], norm_values[1], norm_biases[1]} HOST (edm.py:347-355)
  *   chain      (keep_frames,B,N,3+F) DEVICE out; chain[0] holds final x and one-hot h (edm.py:174)

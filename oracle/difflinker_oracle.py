@@ -342,6 +342,80 @@ def edm_sample_chain(sd, cfg: OracleConfig, gamma: Tensor, T: int, x, h, node_ma
     return chain
 
 
+def remove_mean(x, node_mask):
+    """utils.remove_mean_with_mask (utils.py:56-63)."""
+    return x - (x.sum(dim=1, keepdim=True) / node_mask.sum(1, keepdim=True)) * node_mask
+
+
+def com_free_noise(noise_fn: NoiseFn, B: int, N: int, n_dims: int, F_: int, mask: Tensor) -> Tensor:
+    """InpaintingEDM.sample_combined_position_feature_noise (edm.py:715-727): the coordinate part is masked and
+    projected to zero centre of mass (utils.py:158-168), the feature part only masked."""
+    zx = remove_mean(noise_fn((B, N, n_dims)) * mask, mask)
+    zh = noise_fn((B, N, F_)) * mask
+    return torch.cat([zx, zh], dim=2)
+
+
+def inpainting_sample_chain(sd, cfg: OracleConfig, gamma: Tensor, T: int, x, h, node_mask, fragment_mask, linker_mask,
+                            edge_mask, context, keep_frames=None, norm_values=(1.0, 4.0, 10.0),
+                            norm_biases=(None, 0.0, 0.0), noise_fn: Optional[NoiseFn] = None,
+                            table_timesteps: Optional[int] = None):
+    """InpaintingEDM.sample_chain (edm.py:549-612) with sample_p_zs_given_zt (614-646), sample_q_zs_given_zt_and_x
+    (648-670), sample_p_xh_given_z0 (672-698) and sample_q_xh_given_z0_and_x (700-713) inlined.
+    `cfg.centering` must be True (lightning.py:99) and the dynamics are called with linker_mask=None."""
+    assert cfg.centering
+    if noise_fn is None:
+        noise_fn = lambda shape: torch.randn(shape)
+    if table_timesteps is None:
+        table_timesteps = gamma.numel() - 1
+    B, N = x.shape[0], x.shape[1]
+    nd, F_ = cfg.n_dims, cfg.in_node_nf
+    nmf = node_mask.to(x.dtype)
+    x = x / norm_values[0]
+    h = (h.float() - norm_biases[1]) / norm_values[1]
+    xh = torch.cat([x, h], dim=2)
+    z = com_free_noise(noise_fn, B, N, nd, F_, nmf)                        # edm.py:565
+    if keep_frames is None:
+        keep_frames = T
+    chain = torch.zeros((keep_frames,) + z.shape)
+
+    def unnorm(zz):
+        return torch.cat([zz[:, :, :nd] * norm_values[0], zz[:, :, nd:] * norm_values[1] + norm_biases[1]], dim=2)
+
+    for s in reversed(range(T)):
+        s_arr = torch.full((B, 1), fill_value=s)
+        t_arr = (s_arr + 1) / T
+        s_arr = s_arr / T
+        g_s = gamma_lookup(gamma, s_arr, table_timesteps)
+        g_t = gamma_lookup(gamma, t_arr, table_timesteps)
+        sig2_ts, sig_ts, a_ts = _sigma_alpha_t_given_s(g_t, g_s)
+        sig_s, sig_t, al_s = _sigma(g_s), _sigma(g_t), _alpha(g_s)
+        eps = dynamics_forward(sd, cfg, t_arr, z, node_mask, None, edge_mask, context)               # edm.py:626-633
+        mu = z / _bcast(a_ts) - (_bcast(sig2_ts) / _bcast(a_ts) / _bcast(sig_t)) * eps
+        sigma = _bcast(sig_ts) * _bcast(sig_s) / _bcast(sig_t)
+        z_lin = mu + sigma * com_free_noise(noise_fn, B, N, nd, F_, nmf)                             # edm.py:645
+        xf = xh * fragment_mask
+        mu_q = _bcast(a_ts) * (_bcast(sig_s) ** 2) / (_bcast(sig_t) ** 2) * z + _bcast(al_s) * _bcast(sig2_ts) / (_bcast(sig_t) ** 2) * xf
+        z_frag = mu_q + sigma * com_free_noise(noise_fn, B, N, nd, F_, fragment_mask)                # edm.py:669
+        z = z_lin * linker_mask + z_frag * fragment_mask                                              # edm.py:589
+        z = torch.cat([remove_mean(z[:, :, :nd], nmf), z[:, :, nd:]], dim=2)                          # edm.py:592-594
+        chain[(s * keep_frames) // T] = unnorm(z)
+
+    zeros = torch.zeros((B, 1))
+    g0 = gamma_lookup(gamma, zeros, table_timesteps)
+    sigma_x = torch.exp(-(-0.5 * g0)).unsqueeze(1)
+    eps = dynamics_forward(sd, cfg, zeros, z, node_mask, None, edge_mask, context)
+    mu_x = 1.0 / _bcast(_alpha(g0)) * (z - _bcast(_sigma(g0)) * eps)
+    out_l = mu_x + sigma_x * com_free_noise(noise_fn, B, N, nd, F_, nmf)                              # edm.py:689-690
+    xl = out_l[:, :, :nd] * norm_values[0]
+    hl = F.one_hot(torch.argmax(out_l[:, :, nd:] * norm_values[1] + norm_biases[1], dim=2), F_) * node_mask
+    e2 = com_free_noise(noise_fn, B, N, nd, F_, nmf)                                                  # edm.py:706
+    out_f = (1 / _bcast(_alpha(g0))) * z - (_bcast(_sigma(g0)) / _bcast(_alpha(g0))) * e2
+    xf2 = out_f[:, :, :nd] * norm_values[0]
+    hf2 = F.one_hot(torch.argmax(out_f[:, :, nd:] * norm_values[1] + norm_biases[1], dim=2), F_) * node_mask
+    chain[0] = torch.cat([xl, hl], dim=2) * linker_mask + torch.cat([xf2, hf2], dim=2) * fragment_mask   # edm.py:603-608
+    return chain
+
+
 # ------------------------------------------------------------------------------------------------
 # batching contract (datasets.py) -- restated for fixtures; int8 masks incl. the -1/-2 edge mask
 # ------------------------------------------------------------------------------------------------

@@ -194,6 +194,45 @@ def golden_chain(ns, name, spec, nb, seed, keep_frames, n_steps=None):
     save(name, meta, chain=chain, node_mask=node_mask, coef=coef)
 
 
+def golden_inpaint_chain(ns, name, spec, nb, seed, keep_frames):
+    """InpaintingEDM through the reference's DDPM.sample_chain (lightning.py:405-463 with inpainting=True)."""
+    hp = synthetic.model_hparams(spec)
+    hp['inpainting'] = True
+    torch.manual_seed(seed)
+    ddpm = ns.lightning.DDPM(**hp, data_path=None, batch_size=nb, lr=1e-4, torch_device='cpu', test_epochs=1,
+                             n_stability_samples=1)
+    synthetic.init_reference_like_weights(ddpm)
+    ddpm.eval()
+    T = ddpm.edm.T
+    data = ns.datasets.collate(synthetic.make_items(spec, batch=nb))
+    noise_seed = seed + 2000
+    draw = seeded_noise(noise_seed)
+    o1, o2 = ns.utils.sample_gaussian_with_mask, ns.utils.sample_center_gravity_zero_gaussian_with_mask
+    ns.utils.sample_gaussian_with_mask = lambda size, device, node_mask: draw(size) * node_mask
+    ns.utils.sample_center_gravity_zero_gaussian_with_mask = \
+        lambda size, device, node_mask: ns.utils.remove_mean_with_mask(draw(size) * node_mask, node_mask)
+    try:
+        with torch.no_grad():
+            chain, node_mask = ddpm.sample_chain(data, keep_frames=keep_frames)
+    finally:
+        ns.utils.sample_gaussian_with_mask, ns.utils.sample_center_gravity_zero_gaussian_with_mask = o1, o2
+    d2 = orc.collate_molecules(synthetic.make_items(spec, batch=nb))
+    x = orc.remove_partial_mean(d2['positions'], d2['atom_mask'], d2['atom_mask'])
+    sd_dyn = {k[len("edm.dynamics."):]: v for k, v in ddpm.state_dict().items() if k.startswith("edm.dynamics.")}
+    gam = orc.gamma_table(hp['diffusion_noise_schedule'], hp['diffusion_steps'], hp['diffusion_noise_precision'])
+    ocfg = oracle_cfg(hp)
+    ocfg.centering = True
+    with torch.no_grad():
+        oc = orc.inpainting_sample_chain(sd_dyn, ocfg, gam, T, x, d2['one_hot'], d2['atom_mask'], d2['fragment_mask'],
+                                         d2['linker_mask'], d2['edge_mask'], d2['fragment_mask'], keep_frames=keep_frames,
+                                         norm_values=tuple(hp['normalize_factors']), noise_fn=seeded_noise(noise_seed))
+    err = (oc - chain).abs().max().item()
+    assert err < 5e-5, f"{name}: oracle inpainting chain vs reference {err}"
+    meta = dict(kind="inpaint_chain", spec=spec.name, batch=nb, seed=seed, noise_seed=noise_seed, keep_frames=keep_frames,
+                T=T, sha=state_sha(ddpm.edm.dynamics.state_dict()), oracle_max_abs_err=err)
+    save(name, meta, chain=chain, node_mask=node_mask)
+
+
 def golden_schedules():
     ns = load_reference()
     arrs = {}
@@ -224,6 +263,7 @@ def main():
         golden_dynamics(ns, f"dyn_small_pocket_{gt}", pk, 2, seed=3, pocket=True)
     golden_chain(ns, "chain_cfg1", S["cfg1_plumbing"], 4, seed=0, keep_frames=5)
     golden_chain(ns, "chain_cfg1_nsteps20", S["cfg1_plumbing"], 4, seed=0, keep_frames=1, n_steps=20)
+    golden_inpaint_chain(ns, "inpaint_chain_cfg1", S["cfg1_plumbing"], 4, seed=0, keep_frames=3)
     print("all oracle / host-mirror checks against the reference passed")
 
 

@@ -48,7 +48,7 @@ def oracle_cfg(hp):
                             normalization_factor=hp['normalization_factor'], graph_type=hp['graph_type'])
 
 
-def build_dynamics(spec, seed, edge_impl='auto'):
+def build_dynamics(spec, seed, edge_impl='auto', **over):
     """Product-side Dynamics with the fixture's weights (same seed, same construction order as the reference)."""
     from difflinker_b200 import Dynamics, DynamicsWithPockets
     hp = synthetic.model_hparams(spec)
@@ -56,7 +56,7 @@ def build_dynamics(spec, seed, edge_impl='auto'):
     cls = DynamicsWithPockets if spec.pocket else Dynamics
     dyn = cls(in_node_nf=hp['in_node_nf'], n_dims=3, context_node_nf=hp['context_node_nf'], hidden_nf=128,
               n_layers=hp['n_layers'], norm_constant=hp['norm_constant'], inv_sublayers=hp['inv_sublayers'],
-              normalization_factor=hp['normalization_factor'], graph_type=hp['graph_type'], edge_impl=edge_impl)
+              normalization_factor=hp['normalization_factor'], graph_type=hp['graph_type'], edge_impl=edge_impl, **over)
     synthetic.init_reference_like_weights(dyn)
     return dyn, hp
 
@@ -84,6 +84,16 @@ def noise_tensor(seed, T, B, N, F):
         out[r, :, :, :3] = draw((B, N, 3))
         out[r, :, :, 3:] = draw((B, N, F))
     return out
+
+
+def inpaint_noise_tensor(seed, T, B, N, F, node_mask, fragment_mask):
+    """(2T+3,B,N,3+F): InpaintingEDM's draws in the reference's call order (edm.py:565,645,669,689,706), each already
+    masked and, for the coordinates, projected to zero centre of mass -- the form dl_sample_chain(INPAINT) consumes."""
+    from oracle import difflinker_oracle as orc
+    draw = seeded_noise(seed)
+    nm, fm = node_mask.float(), fragment_mask.float()
+    masks = [nm] + [nm, fm] * T + [nm, nm]
+    return torch.stack([orc.com_free_noise(draw, B, N, 3, F, m) for m in masks])
 
 
 def context_of(batch, spec):

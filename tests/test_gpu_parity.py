@@ -88,6 +88,53 @@ def test_sample_chain_matches_reference_golden(name, impl):
 
 
 @pytest.mark.parametrize("impl", IMPLS)
+def test_inpainting_sample_chain_matches_reference_golden(impl):
+    """InpaintingEDM (edm.py:549-727) through DDPM(inpainting=True): centring dynamics, all atoms move, fragments are
+    re-noised from the data every step."""
+    meta, a = helpers.load_golden("inpaint_chain_cfg1")
+    spec = helpers.spec_by_name(meta["spec"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"], edge_impl=impl, inpainting=True)
+    from difflinker_b200 import InpaintingEDM, utils
+    assert isinstance(ddpm.edm, InpaintingEDM)
+    d = dev()
+    data = collate(synthetic.make_items(spec, batch=meta["batch"]))
+    B, N = data['positions'].shape[:2]
+    noise = helpers.inpaint_noise_tensor(meta["noise_seed"], meta["T"], B, N, spec.F, data['atom_mask'], data['fragment_mask'])
+    x = utils.remove_partial_mean_with_mask(data['positions'], data['atom_mask'], data['atom_mask'])
+    mv = lambda v: v.to(d)
+    chain = ddpm.edm.sample_chain(x=mv(x), h=mv(data['one_hot']), node_mask=mv(data['atom_mask']),
+                                  fragment_mask=mv(data['fragment_mask']), linker_mask=mv(data['linker_mask']),
+                                  edge_mask=mv(data['edge_mask']), context=mv(data['fragment_mask']),
+                                  keep_frames=meta["keep_frames"], noise=mv(noise)).cpu()
+    want = a["chain"]
+    assert chain.shape == want.shape
+    assert torch.equal(chain[0][..., 3:], want[0][..., 3:]), "atom types differ"
+    for f in range(meta["keep_frames"]):
+        assert rel_err(chain[f], want[f]) <= REL_TOL, f
+    # the public entry point with its own noise: finite, one-hot atom types, zero centre of mass per molecule
+    ddpm = ddpm.to(d)
+    chain2, nm = ddpm.sample_chain(data, keep_frames=1)
+    assert torch.isfinite(chain2).all()
+    assert torch.equal(chain2[0][..., 3:].sum(-1).cpu(), data['atom_mask'].squeeze(-1).float())
+
+
+@pytest.mark.parametrize("impl", IMPLS)
+def test_centering_dynamics_forward_vs_oracle(impl):
+    """Dynamics(centering=True) (egnn.py:404-410): the velocity is re-centred over all atoms."""
+    spec = helpers.spec_by_name("cfg1_plumbing")
+    dyn, hp = helpers.build_dynamics(spec, 3, edge_impl=impl, centering=True)
+    batch = collate(synthetic.make_items(spec, batch=5))
+    z, t = helpers.random_latent(batch, 11)
+    ctx = helpers.context_of(batch, spec)
+    ocfg = helpers.oracle_cfg(hp)
+    ocfg.centering = True
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), ocfg, t, z, batch['atom_mask'], None, batch['edge_mask'], ctx)
+    got = run_dyn(dyn, t, z, batch['atom_mask'], None, batch['edge_mask'], ctx, dev())
+    assert rel_err(got, want) <= REL_TOL
+
+
+@pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("spec_name,nb", [("cfg2_zinc_ragged", 8), ("cfg3_geom_ragged", 4)])
 def test_forward_at_config_shapes_vs_oracle(spec_name, nb, impl):
     spec = synthetic.SPECS[spec_name]

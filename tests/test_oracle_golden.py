@@ -48,6 +48,27 @@ def test_oracle_chain_matches_reference_golden(name):
     assert torch.equal(chain[0][:, :, 3:], a["chain"][0][:, :, 3:])     # atom types identical
 
 
+def test_oracle_inpainting_chain_matches_reference_golden():
+    meta, a = helpers.load_golden("inpaint_chain_cfg1")
+    spec = helpers.spec_by_name(meta["spec"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"], inpainting=True)
+    assert helpers.state_sha(ddpm.edm.dynamics.state_dict()) == meta["sha"]
+    data = orc.collate_molecules(synthetic.make_items(spec, batch=meta["batch"]))
+    x = orc.remove_partial_mean(data['positions'], data['atom_mask'], data['atom_mask'])   # lightning.py:417-419,438
+    gam = orc.gamma_table(hp['diffusion_noise_schedule'], hp['diffusion_steps'], hp['diffusion_noise_precision'])
+    ocfg = helpers.oracle_cfg(hp)
+    ocfg.centering = True                                                                   # lightning.py:99
+    with torch.no_grad():
+        chain = orc.inpainting_sample_chain(ddpm.edm.dynamics.state_dict(), ocfg, gam, meta["T"], x, data['one_hot'],
+                                            data['atom_mask'], data['fragment_mask'], data['linker_mask'],
+                                            data['edge_mask'], data['fragment_mask'], keep_frames=meta["keep_frames"],
+                                            norm_values=tuple(hp['normalize_factors']),
+                                            noise_fn=helpers.seeded_noise(meta["noise_seed"]))
+    assert chain.shape == a["chain"].shape
+    assert (chain - a["chain"]).abs().max().item() <= 5e-5
+    assert torch.equal(chain[0][:, :, 3:], a["chain"][0][:, :, 3:])
+
+
 def test_gamma_tables_match_reference_golden():
     _, a = helpers.load_golden("gamma_tables")
     for key, ref in a.items():
