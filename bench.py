@@ -303,10 +303,14 @@ def main():
     hb = host_batches[args.warmup]
     n_b = hb['atom_mask'].reshape(spec.B, -1).sum(1).tolist()
     l_b = hb['linker_mask'].reshape(spec.B, -1).sum(1).tolist()
-    edge_flops = sum((2 * H * H + 10 * H) * n * n for n in n_b)          # GCL edge kernel: second Linear + first layer/mask/sum
+    if spec.pocket:
+        e_b = synthetic.cutoff_edge_counts(hb, spec.graph_type)         # true edges of the cut-off graph, not n^2
+    else:
+        e_b = [(n * n, l * n) for n, l in zip(n_b, l_b)]
+    edge_flops = sum((2 * H * H + 10 * H) * e for e, _ in e_b)           # GCL edge kernel: second Linear + first layer/mask/sum
     ms_gcl = float(lib.dl_time_edge_kernel(eng, 20))
     fwd_ms = (sum(loop_ms) / len(loop_ms)) / (T + 1)
-    flops_fwd = sum(synthetic.flops_alg(int(n), int(l), spec) for n, l in zip(n_b, l_b))
+    flops_fwd = sum(synthetic.flops_alg(int(n), int(l), spec, e, ex) for n, l, (e, ex) in zip(n_b, l_b, e_b))
     bytes_fwd = spec.B * synthetic.bytes_alg(spec.N, spec)
     roofline = None
     if ms_gcl and ms_gcl > 0:
@@ -333,8 +337,10 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec.name, "B": spec.B, "N": spec.N, "n_layers": spec.L, "T": T, "hidden_nf": 128,
-                       "edge_impl": args.edge_impl, "coord_gain": coord_gain, "l2": "working set per step (noise slab + activations) streams "
-                       "through; each step consumes a fresh 226 MB noise tensor > L2"},
+                       "edge_impl": args.edge_impl, "coord_gain": coord_gain,
+                       "edges_per_launch": int(sum(e for e, _ in e_b)),
+                       "l2": "inputs larger than L2: every timed step consumes a fresh %.0f MB noise tensor"
+                             % ((T + 2) * spec.B * spec.N * (3 + spec.F) * 4 / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "forward": forward,
             "cpu_baseline": cpu, "loop_ms_device": loop_ms,
         }

@@ -44,6 +44,7 @@ struct Workspace {
   float *nm = nullptr, *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *ABg = nullptr, *ABc = nullptr,
         *agg = nullptr, *z = nullptr, *ABgmax = nullptr, *ABcmax = nullptr, *eps = nullptr;
   int* cls = nullptr;
+  int *nbr = nullptr, *deg = nullptr;   // cut-off graphs on the tcgen05 path: per-row neighbour lists of the current call
   float4 *x04 = nullptr, *xa4 = nullptr, *xb4 = nullptr;
   int *rowidx = nullptr, *colidx = nullptr, *xrowidx = nullptr, *nr = nullptr, *nc = nullptr, *nxr = nullptr,
       *n_items = nullptr, *xmols = nullptr, *n_xmols = nullptr, *n_xitems = nullptr;
@@ -177,6 +178,7 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   WSA(agg, n * H); WSA(z, n * xd); WSA(eps, n * xd); WSA(cls, n); WSA(x04, n); WSA(xa4, n); WSA(xb4, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
   WSA(rowidx, n); WSA(colidx, n); WSA(xrowidx, n); WSA(nr, B); WSA(nc, B); WSA(nxr, B); WSA(n_items, 1);
   WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(xitems, n); WSA(n_xitems, 1); WSA(tile_ctr, 64);
+  if (e->use_tc && e->cfg.graph_type != 0) { WSA(nbr, n * N); WSA(deg, n); }
 #undef WSA
   ws.B = B; ws.N = N;
   return DL_OK;
@@ -217,7 +219,8 @@ dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const 
   LAUNCH_CHECK();
   const int tile_edges = e->use_tc ? tc::TN : ET;
   const int max_rows = e->use_tc ? tc::MAXR : MAXR;
-  k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols,
+  const int sparse_rows = e->use_tc && e->cfg.graph_type != 0 ? SPARSE_ITEM_ROWS : 0;
+  k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, sparse_rows, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols,
                                 ws.n_xmols, ws.xitems, ws.n_xitems);
   LAUNCH_CHECK();
   e->launches += 2;
@@ -275,6 +278,14 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   LAUNCH_CHECK();
   e->launches += 1;
 
+  if (ws.nbr != nullptr) {
+    // the cut-off graph of this call (a function of its input coordinates) as per-row neighbour lists
+    k_nbr<<<B, 512, (size_t)N * 24, st>>>(N, e->cfg.graph_type, ws.x04, ws.cls, ws.rowidx, ws.colidx, ws.nr, ws.nc, ws.nbr,
+                                         ws.deg);
+    LAUNCH_CHECK();
+    e->launches += 1;
+  }
+
   float* xin = ws.xa;
   float* xout = ws.xb;
   float4* xin4 = ws.xa4;
@@ -289,7 +300,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = nullptr;
       ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
       ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
-      ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr;
+      ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.deg = ws.deg;
       dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st);
       if (st2 != DL_OK) return st2;
 
@@ -342,7 +353,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = xout4;
     ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
     ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = w.w5;
-    ea.plan = plan; ea.agg = nullptr; ea.x_out = xout;
+    ea.plan = plan; ea.agg = nullptr; ea.x_out = xout; ea.nbr = ws.nbr; ea.deg = ws.deg;
     dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st);
     if (st2 != DL_OK) return st2;
     std::swap(xin, xout);
@@ -380,12 +391,18 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   return DL_OK;
 }
 
-int launches_per_forward(const dl_engine* e) { return 2 + e->cfg.n_layers * (2 * e->cfg.inv_sublayers + 2); }
+int launches_per_forward(const dl_engine* e) {
+  return 2 + e->cfg.n_layers * (2 * e->cfg.inv_sublayers + 2) + (e->use_tc && e->cfg.graph_type != 0 ? 1 : 0);
+}
 
 dl_status check_shapes(const dl_engine* e, int B, int N) {
   if (!e || !e->finalized) { set_err("engine not finalized (dl_finalize_weights)"); return DL_ERR_INVALID; }
   if (B <= 0 || N <= 0) { set_err("B and N must be positive (got %d, %d)", B, N); return DL_ERR_INVALID; }
   if ((int64_t)B * N * N > (int64_t)1 << 40) { set_err("B*N*N too large"); return DL_ERR_INVALID; }
+  if (e->use_tc && e->cfg.graph_type != 0 && N > 2000) {
+    set_err("cut-off graphs: N = %d exceeds the neighbour-list kernel's shared-memory staging (N <= 2000)", N);
+    return DL_ERR_INVALID;
+  }
   return DL_OK;
 }
 
@@ -784,7 +801,7 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
   ea.x = ws.xa; ea.x0 = ws.x0; ea.x4 = ws.xa4; ea.x04 = ws.x04; ea.x4_out = nullptr; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
   ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
-  ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr;
+  ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.deg = ws.deg;
   cudaStream_t st = e->loop_stream;
   if (e->use_tc && getenv("DL_PROFILE_EDGE")) tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
   if (e->use_tc && getenv("DL_PROFILE_NODE")) {

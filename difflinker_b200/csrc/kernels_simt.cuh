@@ -59,7 +59,11 @@ __global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edg
 
 // Single thread: flatten per-molecule row groups into the GCL work list. A work item is `rows_per_tile`
 // complete rows (so the segment sum over j never crosses CTAs and stays order-deterministic).
-__global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __restrict__ nr,
+constexpr int SPARSE_ITEM_ROWS = 8;   // rows per work item of the neighbour-list (cut-off graph) tcgen05 path
+
+// sparse_rows > 0 (cut-off graphs on the tcgen05 path): tiles are packed from per-row neighbour lists at run time, so an
+// item is simply `sparse_rows` consecutive row slots.
+__global__ void k_plan_items(int B, int tile_edges, int max_rows, int sparse_rows, const int* __restrict__ nr,
                              const int* __restrict__ nc, const int* __restrict__ nxr, int4* __restrict__ items,
                              int* __restrict__ n_items, int* __restrict__ xmols, int* __restrict__ n_xmols,
                              int4* __restrict__ xitems, int* __restrict__ n_xitems) {
@@ -70,12 +74,14 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __r
     if (r > 0 && c > 0) {
       int per = c >= tile_edges ? 1 : tile_edges / c;
       if (per > max_rows) per = max_rows;
+      if (sparse_rows > 0) per = sparse_rows;
       for (int r0 = 0; r0 < r; r0 += per) items[cnt++] = make_int4(b, r0, min(per, r - r0), c);
     }
     if (nxr[b] > 0 && c > 0) {
       xmols[xc++] = b;
       int per = c >= tile_edges ? 1 : tile_edges / c;
       if (per > max_rows) per = max_rows;
+      if (sparse_rows > 0) per = sparse_rows;
       for (int r0 = 0; r0 < nxr[b]; r0 += per) xitems[xi++] = make_int4(b, r0, min(per, nxr[b] - r0), c);
     }
   }
@@ -361,6 +367,57 @@ __device__ __forceinline__ float edge_weight(int graph_type, const int8_t* __res
   return dist <= cut ? 1.f : 0.f;
 }
 
+// Cut-off graphs on the tcgen05 path: per-row neighbour lists of this forward call (the graph is a function of the
+// call's input coordinates, egnn.py:554-596), so that edges the reference never creates cost nothing.
+// One CTA per molecule; coordinates / classes / live columns are staged in shared memory, then one warp per row slot
+// compacts the neighbours in ascending column order (ballot + popc: deterministic).
+//   nbr[(b*N + i)*N + k] = k-th neighbour of node i  (bit 31 set: padding edge of weight 0 -- a live row without any
+//                          neighbour still owns one tile column, so its aggregate is written as exactly 0)
+//   deg[b*N + i]         = number of entries (>= 1 for every live row)
+__global__ void __launch_bounds__(512) k_nbr(int N, int graph_type, const float4* __restrict__ x04,
+                                             const int* __restrict__ cls, const int* __restrict__ rowidx,
+                                             const int* __restrict__ colidx, const int* __restrict__ nr,
+                                             const int* __restrict__ nc, int* __restrict__ nbr, int* __restrict__ deg) {
+  extern __shared__ uint8_t sm_nbr[];
+  float4* xs = reinterpret_cast<float4*>(sm_nbr);             // [N]
+  int* cl = reinterpret_cast<int*>(xs + N);                   // [N]
+  int* col = cl + N;                                          // [N]
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+  const size_t gb = (size_t)b * N;
+  const int nrows = nr[b], ncols = nc[b];
+  for (int i = tid; i < N; i += blockDim.x) {
+    xs[i] = x04[gb + i]; cl[i] = cls[gb + i];
+    col[i] = i < ncols ? colidx[gb + i] : 0;
+  }
+  __syncthreads();
+  for (int slot = warp; slot < nrows; slot += nwarp) {
+    const int i = rowidx[gb + slot];
+    const float4 xi = xs[i];
+    const int ci = cl[i];
+    int* out = nbr + (gb + i) * N;
+    int count = 0;
+    for (int c0 = 0; c0 < ncols; c0 += 32) {
+      const int c = c0 + lane;
+      bool keep = false;
+      int j = 0;
+      if (c < ncols) {
+        j = col[c];
+        const float4 xj = xs[j];
+        const float ex = xi.x - xj.x, ey = xi.y - xj.y, ez = xi.z - xj.z;
+        const float d0 = ex * ex + ey * ey + ez * ez;
+        keep = edge_weight(graph_type, nullptr, N, i, j, ci, cl[j], d0) != 0.f;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, keep);
+      if (keep) out[count + __popc(m & ((1u << lane) - 1u))] = j;
+      count += __popc(m);
+    }
+    if (lane == 0) {
+      if (count == 0) { out[0] = i | (int)0x80000000; count = 1; }
+      deg[gb + i] = count;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Reference fp32 SIMT edge kernel: second Linear of the edge / coord MLP as a 128x128x128 tile GEMM.
 //   GCL   (egnn.py:45-66):   agg_i = sum_j silu(W2 silu(A_i+B_j+d_ij wd+d0_ij w0)+b2) * EM_ij / nf
@@ -388,6 +445,8 @@ struct EdgeArgs {
   Plan plan;
   float* agg;               // GCL out (B*N,128)
   float* x_out;             // COORD out (B*N,3)
+  const int* nbr;           // cut-off graphs, tcgen05 path: per-row neighbour lists (k_nbr) or null
+  const int* deg;
 };
 
 constexpr size_t EDGE_SIMT_SMEM =

@@ -71,13 +71,16 @@ constexpr int TBL_SC = TBL_D0 + TN * 4;                  // f32  [TN]  power-of-
 constexpr int TBL_EM = TBL_SC + TN * 4;                  // f32x2[TN]  (edge weight, accumulator descale)
 constexpr int TBL_CD = TBL_EM + TN * 8;                  // f32  [TN][3] normalised difference (COORD)
 constexpr int TBL_ROWNODE = TBL_CD + TN * 12;            // int  [MAXR] node index of each tile row
-constexpr int TBL_BYTES = TBL_ROWNODE + MAXR * 4;
+constexpr int TBL_ROWSTART = TBL_ROWNODE + MAXR * 4;     // int  [MAXR+1] first tile column of each row (neighbour-list tiles)
+constexpr int TBL_BYTES = TBL_ROWSTART + (MAXR + 4) * 4;
 constexpr int OFF_B2W5 = OFF_TBL + N_ACC * TBL_BYTES;    // float2 [128] (b2, w5)
 constexpr int OFF_TX = OFF_B2W5 + H * 8;                 // f32 [TN][3] per-edge translation (COORD epilogue)
 constexpr int OFF_BAR = OFF_TX + TN * 12;                // mbarriers + tmem ptr
 constexpr int BAR_W = 0, BAR_FULL = 8, BAR_EMPTY = BAR_FULL + 8 * N_STAGE, BAR_TBL = BAR_EMPTY + 8 * N_STAGE,
               BAR_TFULL = BAR_TBL + 8 * N_ACC, BAR_TEMPTY = BAR_TFULL + 8 * N_ACC, BAR_TMEMSLOT = BAR_TEMPTY + 8 * N_ACC;
 constexpr int SMEM_BYTES = OFF_BAR + BAR_TMEMSLOT + 16 + 1024;   // + alignment slack
+static_assert(SMEM_BYTES <= 232448, "k_edge_tc exceeds the 227 KB of shared memory a CTA can opt into");
+static_assert(TBL_BYTES % 16 == 0, "table slots must keep 16-byte alignment");
 
 // ---------------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -219,33 +222,95 @@ struct Tile {
   int b, nc, slot0, nrt, c0, ncc;
   bool first_chunk, last_chunk;
   const int* rows;
+  // neighbour-list (SPARSE) tiles only; per-lane values: lane l describes tile row l
+  int Et;        // edges in the tile (uniform)
+  int start;     // first tile column of row l (exclusive prefix of the row degrees)
+  int node;      // node index of row l
 };
 
 // Warp-synchronous (all 32 lanes of a table warp call it together): the CTA's contiguous slice of the work-item
 // list is read 32 items at a time with one coalesced load and served from registers by shuffles, so walking the
 // list costs no dependent global round trip per tile (items carry their molecule's live column count).
-template <bool COORD>
+template <bool COORD, bool SPARSE = false>
 struct TileIter {
   const int4* list;
   const int* rowlist;
-  int N, wi_end, wi, rt, c0, cache_base, lane;
+  const int* deg;
+  int N, wi_end, wi, rt, c0, cache_base, lane, first, stride;   // wi counts this CTA's items: global index first + wi*stride
   int4 cache;
-  __device__ TileIter(const Plan& p, int N_) : N(N_), rt(0), c0(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31) {
+  int d_wi, d_deg, d_node;     // SPARSE: lane l caches (degree, node) of row l of work item d_wi
+  __device__ TileIter(const Plan& p, int N_, const int* deg_ = nullptr)
+      : deg(deg_), N(N_), rt(0), c0(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31), d_wi(-1), d_deg(0), d_node(0) {
     // blocked distribution: CTA c owns the contiguous work items [lo, hi) -- consecutive tiles then mostly belong to
     // the same molecule, so the table warps' and producers' L2 lines are reused while they are hot.
     list = COORD ? p.xitems : p.items;
     rowlist = COORD ? p.xrowidx : p.rowidx;
     const int total = COORD ? *p.n_xitems : *p.n_items;
-    const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
-    wi = c * per + min(c, extra);
-    wi_end = wi + per + (c < extra ? 1 : 0);
+    const int G = (int)gridDim.x, per = total / G, extra = total % G, c = (int)blockIdx.x;
+    wi = 0;
+    if (SPARSE) {
+      // neighbour-list items differ a lot in edge count (ligand rows vs pocket rows): deal them round-robin
+      first = c; stride = G; wi_end = total > c ? (total - c + G - 1) / G : 0;
+    } else {
+      first = c * per + min(c, extra); stride = 1; wi_end = per + (c < extra ? 1 : 0);
+    }
     cache = make_int4(0, 0, 0, 0);
   }
+  // Neighbour-list tiles: whole rows of one work item (<= 32 rows) are packed while their degrees fit TN columns; a row
+  // with more than TN neighbours becomes a run of single-row chunk tiles (the epilogue carries its sum across them).
+  __device__ bool next_sparse(Tile& t) {
+    while (wi < wi_end) {
+      if (wi - cache_base >= 32) {
+        cache_base = wi;
+        cache = list[first + min(wi + lane, wi_end - 1) * stride];
+      }
+      const int src = wi - cache_base;
+      const int b = __shfl_sync(0xffffffffu, cache.x, src), r_begin = __shfl_sync(0xffffffffu, cache.y, src);
+      const int r_count = __shfl_sync(0xffffffffu, cache.z, src), nc = __shfl_sync(0xffffffffu, cache.w, src);
+      if (rt >= r_count || nc <= 0) { wi += 1; rt = 0; c0 = 0; continue; }
+      if (d_wi != wi) {                                    // (degree, node) of the item's rows: two dependent loads per item
+        d_wi = wi;
+        d_node = lane < r_count ? rowlist[(size_t)b * N + r_begin + lane] : 0;
+        d_deg = lane < r_count ? deg[(size_t)b * N + d_node] : (1 << 20);
+      }
+      // lane l looks at row rt + l of the item
+      const int sl = (rt + lane) & 31;
+      int dg = __shfl_sync(0xffffffffu, d_deg, sl);
+      const int nd = __shfl_sync(0xffffffffu, d_node, sl);
+      if (rt + lane >= 32) dg = 1 << 20;
+      const int d_first = __shfl_sync(0xffffffffu, dg, 0);
+      t.b = b; t.nc = nc; t.slot0 = r_begin + rt; t.rows = rowlist + (size_t)b * N; t.node = nd;
+      if (c0 > 0 || d_first > TN) {
+        t.nrt = 1; t.c0 = c0; t.ncc = min(TN, d_first - c0); t.Et = t.ncc;
+        t.first_chunk = c0 == 0; t.last_chunk = c0 + TN >= d_first;
+        t.start = lane == 0 ? 0 : t.ncc;
+        c0 += TN;
+        if (c0 >= d_first) { c0 = 0; rt += 1; }
+        return true;
+      }
+      int incl = dg;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+      }
+      const unsigned fit = __ballot_sync(0xffffffffu, incl <= TN);      // a prefix of the lanes (degrees are >= 1)
+      const int nrt = min(fit == 0xffffffffu ? 32 : __ffs(~fit) - 1, MAXR);
+      t.nrt = nrt; t.c0 = 0; t.first_chunk = true; t.last_chunk = true;
+      t.start = incl - dg;
+      t.Et = __shfl_sync(0xffffffffu, incl, nrt - 1);
+      t.ncc = t.Et;
+      rt += nrt;
+      return true;
+    }
+    return false;
+  }
   __device__ bool next(Tile& t) {
+    if (SPARSE) return next_sparse(t);
     while (wi < wi_end) {
       if (wi - cache_base >= 32) {                        // refill (warp-uniform)
         cache_base = wi;
-        cache = list[min(wi + lane, wi_end - 1)];
+        cache = list[first + min(wi + lane, wi_end - 1) * stride];
       }
       const int src = wi - cache_base;
       const int b = __shfl_sync(0xffffffffu, cache.x, src), r_begin = __shfl_sync(0xffffffffu, cache.y, src);
@@ -279,7 +344,9 @@ struct TileIter {
 // the tensor pipe overlap; the two SiLUs per edge-channel (MUFU) are the shared bottleneck by design.
 // ---------------------------------------------------------------------------------------------------------
 // PROF = true adds clock64() accounting per role (wait vs work cycles) into `prof` (16 x u64 per CTA); debug only.
-template <bool COORD, bool PROF = false>
+// SPARSE = true: cut-off (pocket) graphs -- tiles are packed from the per-row neighbour lists k_nbr built for this
+// forward call, so only edges the reference creates are processed (egnn.py:554-596); FC graphs use SPARSE = false.
+template <bool COORD, bool PROF = false, bool SPARSE = false>
 __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArgs a, const __half* __restrict__ w2tc,
                                                                 unsigned long long* __restrict__ prof = nullptr) {
   extern __shared__ uint8_t smem_raw[];
@@ -335,7 +402,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
     // Tile-parallel: table warp k builds the tables of tiles t = k, k+3, ... on its own (4 edges per lane), so the
     // three warps overlap their dependent L2 round trips (index -> coordinates / maxima / mask) across tiles.
     const int tw = warp - W_TBL;
-    TileIter<COORD> iter(a.plan, N);
+    TileIter<COORD, SPARSE> iter(a.plan, N, a.deg);
     Tile cur;
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1);
@@ -345,28 +412,48 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
       uint8_t* tb = sm + OFF_TBL + acc * TBL_BYTES;
       int* hdr = reinterpret_cast<int*>(tb + TBL_HDR);
       if (more) {
-        const int Et = cur.nrt * cur.ncc;
+        const int Et = SPARSE ? cur.Et : cur.nrt * cur.ncc;
         const size_t gb = (size_t)cur.b * N;
         if (lane == 0) {
           hdr[0] = Et; hdr[1] = cur.nrt; hdr[2] = cur.ncc;
           hdr[3] = (cur.first_chunk ? 1 : 0) | (cur.last_chunk ? 2 : 0);
           hdr[4] = cur.b;
         }
-        if (lane < cur.nrt) reinterpret_cast<int*>(tb + TBL_ROWNODE)[lane] = cur.rows[cur.slot0 + lane];
+        if (SPARSE) {
+          if (lane < cur.nrt) {
+            reinterpret_cast<int*>(tb + TBL_ROWNODE)[lane] = cur.node;
+            reinterpret_cast<int*>(tb + TBL_ROWSTART)[lane] = cur.start;
+          }
+          if (lane == 0) reinterpret_cast<int*>(tb + TBL_ROWSTART)[cur.nrt] = Et;
+        } else if (lane < cur.nrt) {
+          reinterpret_cast<int*>(tb + TBL_ROWNODE)[lane] = cur.rows[cur.slot0 + lane];
+        }
         bool any_rescale = false;
 #pragma unroll
         for (int e = lane; e < TN; e += 32) {
           const int ev = min(e, Et - 1);                   // slots past Et mirror the last edge: producers may prefetch them
-          const int rr = ev / cur.ncc, jj = ev - rr * cur.ncc;
-          const int i = cur.rows[cur.slot0 + rr];
-          const int j = a.plan.colidx[gb + cur.c0 + jj];
+          int i, j;
+          float ew_list = 1.f;
+          if (SPARSE) {
+            int rr = 0;                                    // tile row of this edge: rows start at ascending columns
+            for (int r = 1; r < cur.nrt; ++r) rr += ev >= __shfl_sync(0xffffffffu, cur.start, r) ? 1 : 0;
+            i = __shfl_sync(0xffffffffu, cur.node, rr);
+            const int first_col = __shfl_sync(0xffffffffu, cur.start, rr);
+            const int raw = a.nbr[(gb + i) * N + cur.c0 + (ev - first_col)];
+            j = raw & 0x7fffffff;
+            ew_list = raw < 0 ? 0.f : 1.f;                 // padding edge of an isolated row
+          } else {
+            const int rr = ev / cur.ncc, jj = ev - rr * cur.ncc;
+            i = cur.rows[cur.slot0 + rr];
+            j = a.plan.colidx[gb + cur.c0 + jj];
+          }
           const float4 xi = a.x4[gb + i], xj = a.x4[gb + j], yi = a.x04[gb + i], yj = a.x04[gb + j];   // 16-byte gathers
           const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
           const float d = dx * dx + dy * dy + dz * dz;                       // egnn.py:297-298
           const float ex = yi.x - yj.x, ey = yi.y - yj.y, ez = yi.z - yj.z;
           const float d0 = ex * ex + ey * ey + ez * ez;                      // egnn.py:220
           int ci = 0, cj = 0;
-          if (gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
+          if (!SPARSE && gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
           reinterpret_cast<int*>(tb + TBL_ROWOFF)[e] = (int)((gb + i) * 2 * H);
           reinterpret_cast<int*>(tb + TBL_COLOFF)[e] = (int)((gb + j) * 2 * H + H);
           reinterpret_cast<float*>(tb + TBL_D)[e] = d;
@@ -383,7 +470,8 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
           any_rescale |= (sc != 1.0f);
           // GCL epilogue works in the log2 domain: u = -log2(e) * (D*descale + b2) is one FMA, sigmoid = 1/(1+2^u), and
           // the -ln(2) that turns u*sigmoid back into silu rides on the edge weight (one rounding of a constant).
-          const float ew = edge_weight(gm.graph_type, a.edge_mask ? a.edge_mask + gb * N : nullptr, N, i, j, ci, cj, d0);
+          const float ew = SPARSE ? ew_list
+                                  : edge_weight(gm.graph_type, a.edge_mask ? a.edge_mask + gb * N : nullptr, N, i, j, ci, cj, d0);
           reinterpret_cast<float2*>(tb + TBL_EM)[e] =
               COORD ? make_float2(ew, a.w2_descale / sc)
                     : make_float2(ew * -0.6931471805599453f, (a.w2_descale / sc) * -1.4426950408889634f);
@@ -551,18 +639,20 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
       const int* hdr = reinterpret_cast<const int*>(tb + TBL_HDR);
       const int Et = hdr[0];
       if (Et <= 0) break;
-      const int nrt = hdr[1], ncc = hdr[2];
+      const int nrt = hdr[1], ncc_tile = hdr[2];
       const bool first_chunk = hdr[3] & 1, last_chunk = hdr[3] & 2;
       const size_t gb = (size_t)hdr[4] * N;
       const float2* emds = reinterpret_cast<const float2*>(tb + TBL_EM);
       const int* rownode = reinterpret_cast<const int*>(tb + TBL_ROWNODE);
+      const int* rowstart = reinterpret_cast<const int*>(tb + TBL_ROWSTART);
       if (!COORD) {
         const int c = q * 32 + lane;
         const float bias = b2w5[c].x * -1.4426950408889634f;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + acc * TN;
         for (int rr = (nrt == 1 ? hw : ((hw + t) & 1)); rr < nrt; rr += 2) {   // single-row (chunked) tiles: half 0 only
           float2 acc2 = make_float2((nrt == 1 && !first_chunk) ? run : 0.f, 0.f);   // (even, odd) column partial sums
-          const int col0 = rr * ncc;
+          const int col0 = SPARSE ? rowstart[rr] : rr * ncc_tile;
+          const int ncc = SPARSE ? rowstart[rr + 1] - col0 : ncc_tile;
           int jj = 0;
           for (; jj + 16 <= ncc; jj += 16) {
             uint32_t r[16];
@@ -647,7 +737,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         if (et < nrt * 3) {
           const int rr = et / 3, dim = et - rr * 3;
           float sacc = (nrt == 1 && !first_chunk) ? run : 0.f;
-          for (int jj = 0; jj < ncc; ++jj) sacc += txs[(rr * ncc + jj) * 3 + dim];
+          const int col0 = SPARSE ? rowstart[rr] : rr * ncc_tile;
+          const int ncc = SPARSE ? rowstart[rr + 1] - col0 : ncc_tile;
+          for (int jj = 0; jj < ncc; ++jj) sacc += txs[(col0 + jj) * 3 + dim];
           if (nrt == 1) run = sacc;
           if (last_chunk) {
             const int i = rownode[rr];
@@ -674,7 +766,9 @@ edge_tc_done:
 // Host side
 // ---------------------------------------------------------------------------------------------------------
 inline dl_status configure() {
-  if (cudaFuncSetAttribute(k_edge_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+  if (cudaFuncSetAttribute(k_edge_tc<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_edge_tc<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_edge_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(k_edge_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(k_edge_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
     return DL_ERR_CUDA;
@@ -709,7 +803,10 @@ inline size_t pack_w2(const std::vector<float>& W, std::vector<__half>& blob, fl
 inline dl_status launch_edge_tc(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc, int num_sms,
                                 cudaStream_t st) {
   const __half* w = reinterpret_cast<const __half*>(w2_tc);
-  if (coord) k_edge_tc<true, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+  if (ea.nbr != nullptr) {
+    if (coord) k_edge_tc<true, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+    else k_edge_tc<false, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+  } else if (coord) k_edge_tc<true, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
   else k_edge_tc<false, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
   return DL_OK;
 }

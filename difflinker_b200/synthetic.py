@@ -139,13 +139,41 @@ def init_reference_like_weights(module: torch.nn.Module, seed: int = 0, coord_ga
     return module
 
 
-def flops_alg(n: int, l: int, spec: WorkloadSpec) -> float:
+def flops_alg(n: int, l: int, spec: WorkloadSpec, edges: float = None, linker_edges: float = None) -> float:
     """Algorithmic FLOPs of one Dynamics.forward for one molecule with n valid atoms, l linker atoms
-    (SURVEY.md section 8(d))."""
+    (SURVEY.md section 8(d)). Cut-off graphs: `edges` / `linker_edges` = the molecule's true edge count and the edges
+    whose row is a linker atom replace n^2 and l*n."""
     H, D = 128, spec.F + spec.context_node_nf + 1
-    gcl = 2 * H * H * n * n + 10 * H * H * n + 10 * H * n * n
-    coord = 2 * H * H * l * n + 4 * H * H * n + 8 * H * l * n
+    e = n * n if edges is None else edges
+    ex = l * n if linker_edges is None else linker_edges
+    gcl = 2 * H * H * e + 10 * H * H * n + 10 * H * e
+    coord = 2 * H * H * ex + 4 * H * H * n + 8 * H * ex
     return 2 * D * H * n + spec.L * (spec.S * gcl + coord) + 2 * H * spec.F * l
+
+
+def cutoff_edge_counts(batch, graph_type: str):
+    """Per-molecule (edges, edges on linker rows) of the cut-off graph at the batch's input coordinates
+    (egnn.py:554-596); the graph is re-derived from the current coordinates every step, so this is the count the
+    roofline uses for the whole chain (only the <= 12 linker atoms move)."""
+    x = batch['positions'].float()
+    nm = batch['atom_mask'].reshape(x.shape[0], -1) != 0
+    pk = batch['pocket_mask'].reshape(x.shape[0], -1) > 0
+    lig = nm & ~pk
+    lm = batch['linker_mask'].reshape(x.shape[0], -1) > 0
+    out = []
+    for b in range(x.shape[0]):
+        d = torch.cdist(x[b], x[b])
+        ll = lig[b][:, None] & lig[b][None, :]
+        pp = pk[b][:, None] & pk[b][None, :]
+        lp = (lig[b][:, None] & pk[b][None, :]) | (pk[b][:, None] & lig[b][None, :])
+        if graph_type == '4A':
+            adj = (nm[b][:, None] & nm[b][None, :]) & (d <= 4)
+        else:
+            cut = 4.0 if graph_type == 'FC-4A' else 10.0
+            adj = ll | (pp & (d <= 4)) | (lp & (d <= cut))
+        adj = adj & ~torch.eye(adj.shape[0], dtype=torch.bool)
+        out.append((float(adj.sum()), float(adj[lm[b]].sum())))
+    return out
 
 
 def bytes_alg(N: int, spec: WorkloadSpec) -> float:

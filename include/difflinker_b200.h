@@ -16,6 +16,7 @@
  *     sample_p_zs_given_zt_only_linker  edm.py:178-208
  *     sample_p_xh_given_z0_only_linker  edm.py:210-235
  *   InpaintingEDM.sample_chain   src/edm.py:549-612      dl_sample_chain with DL_SAMPLER_INPAINT
+ *   frame restore + .xyz text    generate.py:163-171, src/visualizer.py:14-31   dl_restore_frame, dl_format_xyz
  *   utils.FoundNaNException      src/utils.py:274-289    DL_NAN_DETECTED + per-molecule nan_flags
  *
  * Memory: all `const` device pointers are caller-owned and only read; outputs are caller-owned.
@@ -164,6 +165,30 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps);
 /* Self-test of the tcgen05 edge-MLP tile against the SIMT path on random data. Blocking.
  * Returns DL_OK and writes the max abs/rel error. */
 dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err);
+
+/*
+ * Output stage (the step right after sample_chain in every generation script).
+ *
+ * dl_restore_frame -- generate.py:163-171, generate_with_pocket.py:272-280, sample.py:164-171: put the molecules back
+ * to the input frame, x += (sum_n positions*com_mask / sum_n com_mask) * node_mask, in place on the first three columns
+ * of `xh` (row stride `row_stride` floats: 3 for a packed x, 3+F for chain[0]).  DEVICE buffers, enqueued on `stream`.
+ *   positions (B,N,3) fp32; com_mask (B,N) fp32 (fragment_mask or anchors); node_mask (B,N) int8
+ */
+dl_status dl_restore_frame(int32_t B, int32_t N, int32_t row_stride, float* xh, const float* positions,
+                           const float* com_mask, const int8_t* node_mask, void* stream);
+
+/*
+ * dl_format_xyz -- visualizer.save_xyz_file (src/visualizer.py:14-31) for a whole batch: the text of the B .xyz files
+ * ("%d\n\n" then one "%s %.9f %.9f %.9f\n" line per valid atom, symbol = symbols[argmax one_hot]) written
+ * back to back into `out`; molecule b occupies out[offsets[b] .. offsets[b+1]).  HOST buffers.
+ *   positions (B,N,>=3) fp32 with row stride pos_row_stride; one_hot (B,N,>=F) fp32 with row stride oh_row_stride
+ *   symbols: n_symbols >= F NUL-terminated element symbols (const.IDX2ATOM / GEOM_IDX2ATOM, src/const.py:15,31)
+ * Returns the number of bytes the full text needs (write again with a larger buffer if > out_cap; out may be NULL
+ * for a sizing call), or a negative dl_status.
+ */
+int64_t dl_format_xyz(int32_t B, int32_t N, int32_t F, const float* positions, int32_t pos_row_stride,
+                      const float* one_hot, int32_t oh_row_stride, const int8_t* node_mask,
+                      const char* const* symbols, int32_t n_symbols, char* out, int64_t out_cap, int64_t* offsets);
 
 #ifdef __cplusplus
 }

@@ -417,6 +417,31 @@ def inpainting_sample_chain(sd, cfg: OracleConfig, gamma: Tensor, T: int, x, h, 
 
 
 # ------------------------------------------------------------------------------------------------
+# output stage (generate.py:163-171, visualizer.py:14-31)
+# ------------------------------------------------------------------------------------------------
+def restore_frame(x, positions, com_mask, node_mask):
+    """generate.py:165-171."""
+    pos_masked = positions * com_mask
+    n = com_mask.sum(1, keepdims=True)
+    mean = torch.sum(pos_masked, dim=1, keepdim=True) / n
+    return x + mean * node_mask
+
+
+def xyz_text(one_hot, positions, node_mask, idx2atom):
+    """visualizer.save_xyz_file (visualizer.py:14-31) returning the file contents instead of writing them."""
+    out = []
+    for b in range(one_hot.size(0)):
+        mask = node_mask[b].squeeze()
+        lines = ["%d\n\n" % mask.sum()]
+        atoms = torch.argmax(one_hot[b], dim=1)
+        for i in torch.where(mask)[0]:
+            lines.append("%s %.9f %.9f %.9f\n" % (idx2atom[atoms[i].item()], positions[b, i, 0], positions[b, i, 1],
+                                                positions[b, i, 2]))
+        out.append("".join(lines))
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # batching contract (datasets.py) -- restated for fixtures; int8 masks incl. the -1/-2 edge mask
 # ------------------------------------------------------------------------------------------------
 PAD_KEYS = ("positions", "one_hot", "charges", "anchors", "fragment_mask", "linker_mask", "pocket_mask",

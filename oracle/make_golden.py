@@ -233,6 +233,39 @@ def golden_inpaint_chain(ns, name, spec, nb, seed, keep_frames):
     save(name, meta, chain=chain, node_mask=node_mask)
 
 
+def golden_xyz(ns):
+    """visualizer.save_xyz_file (visualizer.py:14-31) run for real into a temp dir; its files pin oracle.xyz_text."""
+    import importlib
+    import tempfile
+    vis = importlib.import_module("src.visualizer")
+    g = torch.Generator().manual_seed(77)
+    for name, is_geom, F in (("xyz_zinc", False, 8), ("xyz_geom", True, 9)):
+        B, N = 5, 13
+        pos = torch.randn((B, N, 3), generator=g) * torch.tensor([1.0, 30.0, 1e-4])
+        pos[0, 0] = torch.tensor([0.0, -0.0, 1.0])
+        pos[0, 1] = torch.tensor([0.5e-9, 1.5e-9, 2.5e-9])             # rounding at the last printed digit
+        pos[0, 2] = torch.tensor([123456.789, -98765.4321, 3.4e38])
+        pos[0, 3] = torch.tensor([1e-10, -1e-10, 0.9999999995])
+        pos[1, 0] = torch.tensor([float('nan'), float('inf'), float('-inf')])
+        types = torch.randint(0, F, (B, N), generator=g)
+        one_hot = torch.nn.functional.one_hot(types, F).float()
+        n_valid = torch.tensor([13, 7, 1, 9, 4])
+        node_mask = (torch.arange(N)[None, :] < n_valid[:, None]).to(torch.int8).unsqueeze(-1)
+        node_mask[3, 2] = 0                                            # holes in the mask, not just padding
+        names = [f"m{b}" for b in range(B)]
+        with tempfile.TemporaryDirectory() as d:
+            vis.save_xyz_file(d, one_hot, pos, node_mask, names=names, is_geom=is_geom, suffix='s')
+            texts = [open(f"{d}/{n}_s.xyz").read() for n in names]
+        idx2atom = ns.const.GEOM_IDX2ATOM if is_geom else ns.const.IDX2ATOM
+        assert texts == orc.xyz_text(one_hot, pos, node_mask, idx2atom), name
+        blob = "".join(texts).encode()
+        offs = [0]
+        for t in texts:
+            offs.append(offs[-1] + len(t.encode()))
+        save(name, dict(kind="xyz", is_geom=is_geom), positions=pos, one_hot=one_hot, node_mask=node_mask,
+             text=torch.tensor(list(blob), dtype=torch.uint8), offsets=torch.tensor(offs))
+
+
 def golden_schedules():
     ns = load_reference()
     arrs = {}
@@ -264,6 +297,7 @@ def main():
     golden_chain(ns, "chain_cfg1", S["cfg1_plumbing"], 4, seed=0, keep_frames=5)
     golden_chain(ns, "chain_cfg1_nsteps20", S["cfg1_plumbing"], 4, seed=0, keep_frames=1, n_steps=20)
     golden_inpaint_chain(ns, "inpaint_chain_cfg1", S["cfg1_plumbing"], 4, seed=0, keep_frames=3)
+    golden_xyz(ns)
     print("all oracle / host-mirror checks against the reference passed")
 
 

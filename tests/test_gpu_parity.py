@@ -329,6 +329,33 @@ def test_pockets_full_size_slice_vs_oracle():
     assert rel_err(got[..., 3:], want[..., 3:]) <= REL_TOL
 
 
+@pytest.mark.parametrize("graph_type", ["4A", "FC-4A", "FC-10A-4A"])
+def test_cutoff_graph_neighbour_lists_isolated_rows_and_chunked_rows(graph_type):
+    """The tcgen05 path walks per-row neighbour lists (k_nbr): rows without any neighbour (pocket atoms moved far away),
+    rows with more than one tile of neighbours (ligand rows, > 128 entries under FC-10A-4A) and everything between,
+    against the oracle's adjacency construction (egnn.py:538-596) and against the dense SIMT path."""
+    base = synthetic.SPECS["cfg4_pockets"]
+    spec = synthetic.WorkloadSpec(base.name, B=3, N=base.N, n_min=base.n_min, l_min=base.l_min, l_max=base.l_max,
+                                  F=base.F, L=2, T=10, seed=7, pocket=base.pocket, graph_type=graph_type)
+    dyn, hp = helpers.build_dynamics(spec, 1)
+    batch = collate(synthetic.make_items(spec, batch=3))
+    z, t = helpers.random_latent(batch, 17, pad_garbage=False)
+    # isolate a few pocket atoms of molecule 1: 200 A away and 50 A apart from each other
+    pk = torch.nonzero(batch['pocket_mask'][1, :, 0] > 0).view(-1)[:5]
+    for k, idx in enumerate(pk.tolist()):
+        z[1, idx, :3] = torch.tensor([200.0 + 50.0 * k, -150.0, 90.0])
+    ctx = helpers.context_of(batch, spec)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'],
+                                    batch['linker_mask'], batch['edge_mask'], ctx)
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], ctx, dev())
+    assert rel_err(got[..., :3], want[..., :3]) <= REL_TOL
+    assert rel_err(got[..., 3:], want[..., 3:]) <= REL_TOL
+    dyn_simt, _ = helpers.build_dynamics(spec, 1, edge_impl='simt')
+    got_simt = run_dyn(dyn_simt, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], ctx, dev())
+    assert rel_err(got, got_simt) <= REL_TOL
+
+
 @pytest.mark.parametrize("N", [128, 512])
 def test_sweep_sizes_vs_oracle(N):
     """BASELINE configs[4] padded-N sweep end points (rows spanning 1 and 4 column chunks of the edge tile)."""
@@ -371,3 +398,22 @@ def test_chain_T500_cfg1_vs_oracle():
     assert torch.equal(chain[0][..., 3:], want[0][..., 3:]), "atom types differ"
     lm = tpl['linker_mask']
     assert rel_err(chain[0][..., :3] * lm, want[0][..., :3] * lm) <= REL_TOL
+
+
+def test_restore_frame_vs_oracle():
+    """generate.py:163-171 on the device, in place on chain[0] (row stride 3+F) and on a packed (B,N,3) tensor."""
+    from difflinker_b200 import output
+    spec = synthetic.SPECS["cfg2_zinc_ragged"]
+    data = collate(synthetic.make_items(spec, batch=16))
+    g = torch.Generator().manual_seed(5)
+    chain0 = torch.randn(data['positions'].shape[:2] + (3 + spec.F,), generator=g)
+    positions = data['positions'] + torch.tensor([11.0, -7.0, 3.5])
+    for com_mask in (data['fragment_mask'], data['anchors']):
+        if float(com_mask.sum(1).min()) == 0:
+            continue
+        want = orc.restore_frame(chain0[..., :3], positions, com_mask, data['atom_mask'])
+        got = output.restore_frame(chain0.clone().to(dev()), positions, com_mask, data['atom_mask']).cpu()
+        assert rel_err(got[..., :3], want) <= 1e-6
+        assert torch.equal(got[..., 3:], chain0[..., 3:])
+        got3 = output.restore_frame(chain0[..., :3].contiguous().to(dev()), positions, com_mask, data['atom_mask']).cpu()
+        assert torch.equal(got3, got[..., :3])

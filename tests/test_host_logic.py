@@ -13,6 +13,7 @@ from difflinker_b200 import _native, synthetic
 from difflinker_b200.distributed import batch_ids_for_rank, shard_range
 from difflinker_b200.utils import FoundNaNException
 import dl_helpers as helpers
+from oracle import difflinker_oracle as orc
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -139,3 +140,42 @@ def test_accelerate_swaps_reference_edm():
     after = ref.edm.state_dict()
     assert list(after.keys()) == list(before.keys())
     assert all(torch.equal(after[k], before[k]) for k in before)
+
+
+# ------------------------------------------------------------------------------------------------
+# output stage (generate.py:163-180, visualizer.py:14-31)
+# ------------------------------------------------------------------------------------------------
+def _xyz_golden(name):
+    meta, a = helpers.load_golden(name)
+    blob, offs = bytes(a["text"].tolist()), a["offsets"].tolist()
+    return meta, a, [blob[offs[i]:offs[i + 1]].decode() for i in range(len(offs) - 1)]
+
+
+@pytest.mark.parametrize("name", ["xyz_zinc", "xyz_geom"])
+def test_xyz_text_oracle_and_native_formatter_match_reference_files(name, tmp_path):
+    """The reference's own save_xyz_file output (written by oracle/make_golden.py) pins both the oracle restatement and
+    the batched native formatter, byte for byte -- incl. -0.0, nan/inf, 1e38 and last-digit rounding cases."""
+    from difflinker_b200 import output
+    meta, a, want = _xyz_golden(name)
+    idx2atom = output.GEOM_IDX2ATOM if meta["is_geom"] else output.IDX2ATOM
+    assert orc.xyz_text(a["one_hot"], a["positions"], a["node_mask"], idx2atom) == want
+    assert output.format_xyz(a["one_hot"], a["positions"], a["node_mask"], meta["is_geom"]) == want
+    names = [f"output_{i}_mol" for i in range(len(want))]
+    output.save_xyz_file(str(tmp_path), a["one_hot"], a["positions"], a["node_mask"], names, meta["is_geom"], suffix='')
+    for n, w in zip(names, want):
+        assert (tmp_path / f"{n}_.xyz").read_text() == w           # generate.py:176 reads `<name>_.xyz`
+
+
+def test_xyz_formatter_edge_cases():
+    from difflinker_b200 import output
+    # empty molecule: header only; chain[0]-style strided input (3+F columns) is accepted as positions
+    oh = torch.zeros((2, 3, 8)); oh[:, :, 2] = 1
+    xh = torch.cat([torch.arange(18.).view(2, 3, 3), oh], dim=2)
+    nm = torch.tensor([[0, 0, 0], [1, 0, 1]], dtype=torch.int8).unsqueeze(-1)
+    got = output.format_xyz(oh, xh, nm, False)
+    assert got[0] == "0\n\n"
+    assert got[1] == "2\n\nN 9.000000000 10.000000000 11.000000000\nN 15.000000000 16.000000000 17.000000000\n"
+    with pytest.raises(KeyError):
+        output.format_xyz(torch.zeros((1, 2, 10)), torch.zeros((1, 2, 3)), torch.ones((1, 2, 1)), True)
+    with pytest.raises(RuntimeError):
+        output.restore_frame(torch.zeros((1, 2, 3)), torch.zeros((1, 2, 3)), torch.ones((1, 2, 1)), torch.ones((1, 2, 1)))
