@@ -227,14 +227,10 @@ def main():
         return {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in data.items()}
 
     def resident_inputs(data):
-        """What DDPM.sample_chain hands to EDM.sample_chain (lightning.py:405-452), precomputed on the device."""
-        from difflinker_b200 import utils
-        from difflinker_b200.batching import create_templates_for_linker_generation
-        d = to_device(data)
-        tpl = create_templates_for_linker_generation(d, d['linker_mask'].sum(1).view(-1).int())
-        x = utils.remove_partial_mean_with_mask(tpl['positions'], tpl['atom_mask'], tpl['fragment_mask'])
-        return dict(x=x, h=tpl['one_hot'], node_mask=tpl['atom_mask'], fragment_mask=tpl['fragment_mask'],
-                    linker_mask=tpl['linker_mask'], edge_mask=tpl['edge_mask'], context=tpl['fragment_mask'])
+        """What DDPM.sample_chain hands to EDM.sample_chain (lightning.py:405-452), precomputed on the device by the
+        same code the public entry point runs (template batch, context columns, centred coordinates)."""
+        from difflinker_b200.ddpm import sampler_inputs
+        return sampler_inputs(ddpm, to_device(data))
 
     def barrier():
         if world > 1:
@@ -309,6 +305,14 @@ def main():
         e_b = [(n * n, l * n) for n, l in zip(n_b, l_b)]
     edge_flops = sum((2 * H * H + 10 * H) * e for e, _ in e_b)           # GCL edge kernel: second Linear + first layer/mask/sum
     ms_gcl = float(lib.dl_time_edge_kernel(eng, 20))
+    cut_stats = None
+    if spec.pocket:
+        import ctypes
+        st4 = (ctypes.c_int64 * 4)()
+        lib.dl_cut_graph_stats(eng, st4)
+        cut_stats = {"records": st4[0], "tiles": st4[1], "edges": st4[2], "coord_records": st4[3]}
+        if st4[2] > 0:                                                  # the graph the timed kernel actually walked
+            edge_flops = (2 * H * H + 10 * H) * float(st4[2])
     fwd_ms = (sum(loop_ms) / len(loop_ms)) / (T + 1)
     flops_fwd = sum(synthetic.flops_alg(int(n), int(l), spec, e, ex) for n, l, (e, ex) in zip(n_b, l_b, e_b))
     bytes_fwd = spec.B * synthetic.bytes_alg(spec.N, spec)
@@ -338,7 +342,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec.name, "B": spec.B, "N": spec.N, "n_layers": spec.L, "T": T, "hidden_nf": 128,
                        "edge_impl": args.edge_impl, "coord_gain": coord_gain,
-                       "edges_per_launch": int(sum(e for e, _ in e_b)),
+                       "edges_per_launch": int(sum(e for e, _ in e_b)), "cut_graph_device_stats": cut_stats,
                        "l2": "inputs larger than L2: every timed step consumes a fresh %.0f MB noise tensor"
                              % ((T + 2) * spec.B * spec.N * (3 + spec.F) * 4 / 1e6)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "forward": forward,

@@ -42,6 +42,7 @@ SYMBOLS = {
     "dl_last_elapsed_ms": (_F, [_P]),
     "dl_time_edge_kernel": (_F, [_P, _I32]),
     "dl_selftest_tc": (_I32, [_P, C.POINTER(_F), C.POINTER(_F)]),
+    "dl_cut_graph_stats": (_I32, [_P, C.POINTER(_I64)]),
     "dl_restore_frame": (_I32, [_I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "dl_format_xyz": (_I64, [_I32, _I32, _I32, _P, _I32, _P, _I32, _P, C.POINTER(C.c_char_p), _I32, _P, _I64, _P]),
 }

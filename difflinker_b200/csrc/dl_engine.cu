@@ -44,7 +44,8 @@ struct Workspace {
   float *nm = nullptr, *x0 = nullptr, *xa = nullptr, *xb = nullptr, *h = nullptr, *ABg = nullptr, *ABc = nullptr,
         *agg = nullptr, *z = nullptr, *ABgmax = nullptr, *ABcmax = nullptr, *eps = nullptr;
   int* cls = nullptr;
-  int *nbr = nullptr, *deg = nullptr;   // cut-off graphs on the tcgen05 path: per-row neighbour lists of the current call
+  // cut-off graphs on the tcgen05 path: per-row neighbour lists and packed tile records of the current call (k_nbr)
+  int *nbr = nullptr, *recs = nullptr, *xrecs = nullptr, *n_recs = nullptr;
   float4 *x04 = nullptr, *xa4 = nullptr, *xb4 = nullptr;
   int *rowidx = nullptr, *colidx = nullptr, *xrowidx = nullptr, *nr = nullptr, *nc = nullptr, *nxr = nullptr,
       *n_items = nullptr, *xmols = nullptr, *n_xmols = nullptr, *n_xitems = nullptr;
@@ -178,7 +179,7 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   WSA(agg, n * H); WSA(z, n * xd); WSA(eps, n * xd); WSA(cls, n); WSA(x04, n); WSA(xa4, n); WSA(xb4, n); WSA(ABgmax, n * 2); WSA(ABcmax, n * 2);
   WSA(rowidx, n); WSA(colidx, n); WSA(xrowidx, n); WSA(nr, B); WSA(nc, B); WSA(nxr, B); WSA(n_items, 1);
   WSA(xmols, B); WSA(n_xmols, 1); WSA(items, n); WSA(xitems, n); WSA(n_xitems, 1); WSA(tile_ctr, 64);
-  if (e->use_tc && e->cfg.graph_type != 0) { WSA(nbr, n * N); WSA(deg, n); }
+  if (e->use_tc && e->cfg.graph_type != 0) { WSA(nbr, n * N); WSA(recs, n * CUT_REC); WSA(xrecs, n * CUT_REC); WSA(n_recs, 2); }
 #undef WSA
   ws.B = B; ws.N = N;
   return DL_OK;
@@ -219,8 +220,7 @@ dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const 
   LAUNCH_CHECK();
   const int tile_edges = e->use_tc ? tc::TN : ET;
   const int max_rows = e->use_tc ? tc::MAXR : MAXR;
-  const int sparse_rows = e->use_tc && e->cfg.graph_type != 0 ? SPARSE_ITEM_ROWS : 0;
-  k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, sparse_rows, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols,
+  k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols,
                                 ws.n_xmols, ws.xitems, ws.n_xitems);
   LAUNCH_CHECK();
   e->launches += 2;
@@ -279,9 +279,11 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   e->launches += 1;
 
   if (ws.nbr != nullptr) {
-    // the cut-off graph of this call (a function of its input coordinates) as per-row neighbour lists
-    k_nbr<<<B, 512, (size_t)N * 24, st>>>(N, e->cfg.graph_type, ws.x04, ws.cls, ws.rowidx, ws.colidx, ws.nr, ws.nc, ws.nbr,
-                                         ws.deg);
+    // the cut-off graph of this call (a function of its input coordinates): neighbour lists + packed tiles
+    CK(cudaMemsetAsync(ws.n_recs, 0, 2 * sizeof(int), st));
+    k_nbr<<<B, 512, (size_t)N * CUT_SMEM_PER_NODE, st>>>(N, e->cfg.graph_type, ws.x04, ws.cls, ws.rowidx, ws.colidx,
+                                                        ws.xrowidx, ws.nr, ws.nc, ws.nxr, ws.nbr, ws.recs, ws.xrecs,
+                                                        ws.n_recs);
     LAUNCH_CHECK();
     e->launches += 1;
   }
@@ -300,7 +302,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = nullptr;
       ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
       ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
-      ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.deg = ws.deg;
+      ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
       dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st);
       if (st2 != DL_OK) return st2;
 
@@ -353,7 +355,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = xout4;
     ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
     ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = w.w5;
-    ea.plan = plan; ea.agg = nullptr; ea.x_out = xout; ea.nbr = ws.nbr; ea.deg = ws.deg;
+    ea.plan = plan; ea.agg = nullptr; ea.x_out = xout; ea.nbr = ws.nbr; ea.recs = ws.xrecs; ea.n_recs = ws.n_recs ? ws.n_recs + 1 : nullptr;
     dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st);
     if (st2 != DL_OK) return st2;
     std::swap(xin, xout);
@@ -399,8 +401,8 @@ dl_status check_shapes(const dl_engine* e, int B, int N) {
   if (!e || !e->finalized) { set_err("engine not finalized (dl_finalize_weights)"); return DL_ERR_INVALID; }
   if (B <= 0 || N <= 0) { set_err("B and N must be positive (got %d, %d)", B, N); return DL_ERR_INVALID; }
   if ((int64_t)B * N * N > (int64_t)1 << 40) { set_err("B*N*N too large"); return DL_ERR_INVALID; }
-  if (e->use_tc && e->cfg.graph_type != 0 && N > 2000) {
-    set_err("cut-off graphs: N = %d exceeds the neighbour-list kernel's shared-memory staging (N <= 2000)", N);
+  if (e->use_tc && e->cfg.graph_type != 0 && N > 4000) {
+    set_err("cut-off graphs: N = %d exceeds the neighbour-list kernel's shared-memory staging (N <= 4000)", N);
     return DL_ERR_INVALID;
   }
   return DL_OK;
@@ -462,6 +464,7 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * NODE_TM * LDX * sizeof(float)));
   CK(cudaFuncSetAttribute(k_edge_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_edge_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
+  CK(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * CUT_SMEM_PER_NODE));
   dl_status s = tc::configure();
   if (s == DL_OK) s = tcn::configure_node();
   if (s != DL_OK) { set_err("cudaFuncSetAttribute failed for the tcgen05 kernels"); delete e; return s; }
@@ -791,6 +794,33 @@ float dl_last_elapsed_ms(dl_engine* e) {
   return ms;
 }
 
+dl_status dl_cut_graph_stats(dl_engine* e, int64_t* out) {
+  if (!e || !out) return DL_ERR_INVALID;
+  Workspace& ws = e->ws;
+  out[0] = out[1] = out[2] = out[3] = 0;
+  if (ws.recs == nullptr) return DL_OK;
+  if (cudaSetDevice(e->cfg.device) != cudaSuccess) return DL_ERR_CUDA;
+  CK(cudaDeviceSynchronize());
+  int n[2] = {0, 0};
+  CK(cudaMemcpy(n, ws.n_recs, sizeof(n), cudaMemcpyDeviceToHost));
+  std::vector<int> recs((size_t)n[0] * CUT_REC);
+  CK(cudaMemcpy(recs.data(), ws.recs, recs.size() * sizeof(int), cudaMemcpyDeviceToHost));
+  out[0] = n[0]; out[3] = n[1];
+  long long n_heavy = 0, e_heavy = 0, max_heavy = 0, rows_light = 0;
+  for (int k = 0; k < n[0]; ++k) {
+    const int* r = recs.data() + (size_t)k * CUT_REC;
+    const bool heavy = (r[1] >> 8) & 1;
+    out[1] += heavy ? (r[2] + tc::TN - 1) / tc::TN : 1;
+    out[2] += r[2];
+    if (heavy) { ++n_heavy; e_heavy += r[2]; max_heavy = std::max<long long>(max_heavy, r[2]); }
+    else rows_light += r[1] & 0xff;
+  }
+  if (getenv("DL_DEBUG_CUT"))
+    fprintf(stderr, "[dl cut] records %d (heavy %lld, deg sum %lld, max %lld; light rows %lld) tiles %lld edges %lld | coord records %d\n",
+            n[0], n_heavy, e_heavy, max_heavy, rows_light, (long long)out[1], (long long)out[2], n[1]);
+  return DL_OK;
+}
+
 float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   if (!e || !e->finalized || e->last_B == 0 || reps < 1) { set_err("dl_time_edge_kernel: no previous forward"); return -1.f; }
   if (cudaSetDevice(e->cfg.device) != cudaSuccess) return -1.f;
@@ -801,7 +831,7 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
   ea.x = ws.xa; ea.x0 = ws.x0; ea.x4 = ws.xa4; ea.x04 = ws.x04; ea.x4_out = nullptr; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
   ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
-  ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.deg = ws.deg;
+  ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
   cudaStream_t st = e->loop_stream;
   if (e->use_tc && getenv("DL_PROFILE_EDGE")) tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
   if (e->use_tc && getenv("DL_PROFILE_NODE")) {

@@ -59,11 +59,7 @@ __global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edg
 
 // Single thread: flatten per-molecule row groups into the GCL work list. A work item is `rows_per_tile`
 // complete rows (so the segment sum over j never crosses CTAs and stays order-deterministic).
-constexpr int SPARSE_ITEM_ROWS = 8;   // rows per work item of the neighbour-list (cut-off graph) tcgen05 path
-
-// sparse_rows > 0 (cut-off graphs on the tcgen05 path): tiles are packed from per-row neighbour lists at run time, so an
-// item is simply `sparse_rows` consecutive row slots.
-__global__ void k_plan_items(int B, int tile_edges, int max_rows, int sparse_rows, const int* __restrict__ nr,
+__global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __restrict__ nr,
                              const int* __restrict__ nc, const int* __restrict__ nxr, int4* __restrict__ items,
                              int* __restrict__ n_items, int* __restrict__ xmols, int* __restrict__ n_xmols,
                              int4* __restrict__ xitems, int* __restrict__ n_xitems) {
@@ -74,14 +70,12 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, int sparse_row
     if (r > 0 && c > 0) {
       int per = c >= tile_edges ? 1 : tile_edges / c;
       if (per > max_rows) per = max_rows;
-      if (sparse_rows > 0) per = sparse_rows;
       for (int r0 = 0; r0 < r; r0 += per) items[cnt++] = make_int4(b, r0, min(per, r - r0), c);
     }
     if (nxr[b] > 0 && c > 0) {
       xmols[xc++] = b;
       int per = c >= tile_edges ? 1 : tile_edges / c;
       if (per > max_rows) per = max_rows;
-      if (sparse_rows > 0) per = sparse_rows;
       for (int r0 = 0; r0 < nxr[b]; r0 += per) xitems[xi++] = make_int4(b, r0, min(per, nxr[b] - r0), c);
     }
   }
@@ -368,26 +362,119 @@ __device__ __forceinline__ float edge_weight(int graph_type, const int8_t* __res
 }
 
 // Cut-off graphs on the tcgen05 path: per-row neighbour lists of this forward call (the graph is a function of the
-// call's input coordinates, egnn.py:554-596), so that edges the reference never creates cost nothing.
-// One CTA per molecule; coordinates / classes / live columns are staged in shared memory, then one warp per row slot
-// compacts the neighbours in ascending column order (ballot + popc: deterministic).
-//   nbr[(b*N + i)*N + k] = k-th neighbour of node i  (bit 31 set: padding edge of weight 0 -- a live row without any
-//                          neighbour still owns one tile column, so its aggregate is written as exactly 0)
-//   deg[b*N + i]         = number of entries (>= 1 for every live row)
+// call's input coordinates, egnn.py:554-596) and the 128-edge tiles packed from them, so that edges the reference
+// never creates cost nothing and tiles are full.
+// One CTA per molecule; coordinates / classes / live columns are staged in shared memory.
+//   1. one warp per row slot compacts the row's neighbours in ascending column order (ballot + popc: deterministic)
+//        nbr[(b*N + i)*N + k] = k-th neighbour of node i  (bit 31 set: padding edge of weight 0 -- a live row without
+//                               any neighbour still owns one tile column, so its aggregate is written as exactly 0)
+//   2. rows with <= 128 neighbours are bin-packed into tiles, first-fit over the rows in decreasing degree (ties by
+//      row slot: the packing, hence the summation order of every row, is a pure function of the graph);
+//      a row with more neighbours becomes one record that the edge kernel expands into 128-column chunk tiles
+//   3. tile records (32 ints) are appended to the launch-wide list (one atomicAdd per molecule; the order of the
+//      molecules' ranges does not influence any result):
+//        [0] molecule  [1] rows | heavy << 8  [2] edges (heavy: the row's degree)  [3] 0
+//        [4 + r] node | first tile column << 16   for row r of the tile (<= CUT_MAXR rows)
+// Done twice: for all live rows (GCL tiles) and for the coordinate-update rows (linker rows; COORD tiles).
+constexpr int CUT_TN = 128;       // = tc::TN
+constexpr int CUT_MAXR = 28;      // rows per packed tile (record = 4 + 28 ints = 128 bytes)
+constexpr int CUT_REC = 32;
+
+__device__ __forceinline__ void cut_pack_rows(int b, int N, int nrows, const int* __restrict__ rowlist /*global, slot order*/,
+                                              const int* degn, int* srt, int* row_bin, int* row_pos, int* row_start,
+                                              int* bin_rem, int* bin_cnt, int* misc, int* __restrict__ recs,
+                                              int* __restrict__ n_recs) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // rank of every light row among the light rows: degree descending, slot ascending
+  if (tid == 0) { misc[0] = 0; misc[1] = 0; }
+  __syncthreads();
+  for (int s = tid; s < nrows; s += blockDim.x) {
+    const int node = rowlist[s], d = degn[node];
+    if (d <= CUT_TN) {
+      int rank = 0;
+      for (int s2 = 0; s2 < nrows; ++s2) {
+        const int d2 = degn[rowlist[s2]];
+        rank += (d2 <= CUT_TN && (d2 > d || (d2 == d && s2 < s))) ? 1 : 0;
+      }
+      srt[rank] = node;
+      atomicAdd(&misc[0], 1);                              // number of light rows
+    } else {
+      row_pos[node] = atomicAdd(&misc[1], 1);              // heavy rows: any distinct record slot will do
+    }
+  }
+  __syncthreads();
+  const int n_light = misc[0], n_heavy = misc[1];
+  if (warp == 0) {
+    int nb = 0, first_open = 0;
+    const int d_min = n_light > 0 ? degn[srt[n_light - 1]] : 0;
+    for (int idx = 0; idx < n_light; ++idx) {
+      const int node = srt[idx], d = degn[node];
+      int found = -1;
+      for (int base = first_open; base < nb && found < 0; base += 32) {
+        const int bb = base + lane;
+        const bool ok = bb < nb && bin_rem[bb] >= d && bin_cnt[bb] < CUT_MAXR;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (m) found = base + __ffs(m) - 1;
+      }
+      if (lane == 0) {
+        if (found < 0) { bin_rem[nb] = CUT_TN; bin_cnt[nb] = 0; }
+      }
+      if (found < 0) { found = nb; ++nb; }
+      __syncwarp();
+      if (lane == 0) {
+        row_bin[node] = found; row_pos[node] = bin_cnt[found]; row_start[node] = CUT_TN - bin_rem[found];
+        bin_rem[found] -= d; bin_cnt[found] += 1;
+      }
+      __syncwarp();
+      while (first_open < nb && (bin_rem[first_open] < d_min || bin_cnt[first_open] >= CUT_MAXR)) ++first_open;
+    }
+    if (lane == 0) {
+      misc[2] = nb;
+      misc[3] = atomicAdd(n_recs, nb + n_heavy);           // this molecule's range in the launch-wide list
+    }
+  }
+  __syncthreads();
+  const int nb = misc[2];
+  int* out = recs + (size_t)misc[3] * CUT_REC;
+  for (int bb = tid; bb < nb; bb += blockDim.x) {
+    int* r = out + (size_t)bb * CUT_REC;
+    r[0] = b; r[1] = bin_cnt[bb]; r[2] = CUT_TN - bin_rem[bb]; r[3] = 0;
+  }
+  for (int s = tid; s < nrows; s += blockDim.x) {
+    const int node = rowlist[s], d = degn[node];
+    if (d <= CUT_TN) {
+      out[(size_t)row_bin[node] * CUT_REC + 4 + row_pos[node]] = node | (row_start[node] << 16);
+    } else {
+      int* r = out + (size_t)(nb + row_pos[node]) * CUT_REC;
+      r[0] = b; r[1] = 1 | (1 << 8); r[2] = d; r[3] = 0; r[4] = node;
+    }
+  }
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(512) k_nbr(int N, int graph_type, const float4* __restrict__ x04,
                                              const int* __restrict__ cls, const int* __restrict__ rowidx,
-                                             const int* __restrict__ colidx, const int* __restrict__ nr,
-                                             const int* __restrict__ nc, int* __restrict__ nbr, int* __restrict__ deg) {
+                                             const int* __restrict__ colidx, const int* __restrict__ xrowidx,
+                                             const int* __restrict__ nr, const int* __restrict__ nc,
+                                             const int* __restrict__ nxr, int* __restrict__ nbr,
+                                             int* __restrict__ recs, int* __restrict__ xrecs,
+                                             int* __restrict__ n_recs /*[2]: GCL, COORD*/) {
   extern __shared__ uint8_t sm_nbr[];
   float4* xs = reinterpret_cast<float4*>(sm_nbr);             // [N]
   int* cl = reinterpret_cast<int*>(xs + N);                   // [N]
   int* col = cl + N;                                          // [N]
+  int* degn = col + N;                                        // [N] degree by node
+  int* srt = degn + N;                                        // [N] light rows, degree descending
+  int* row_bin = srt + N; int* row_pos = row_bin + N; int* row_start = row_pos + N;
+  int* bin_rem = row_start + N; int* bin_cnt = bin_rem + N;   // [N] each
+  __shared__ int misc[4];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   const size_t gb = (size_t)b * N;
   const int nrows = nr[b], ncols = nc[b];
   for (int i = tid; i < N; i += blockDim.x) {
     xs[i] = x04[gb + i]; cl[i] = cls[gb + i];
     col[i] = i < ncols ? colidx[gb + i] : 0;
+    degn[i] = 0;
   }
   __syncthreads();
   for (int slot = warp; slot < nrows; slot += nwarp) {
@@ -413,10 +500,14 @@ __global__ void __launch_bounds__(512) k_nbr(int N, int graph_type, const float4
     }
     if (lane == 0) {
       if (count == 0) { out[0] = i | (int)0x80000000; count = 1; }
-      deg[gb + i] = count;
+      degn[i] = count;
     }
   }
+  __syncthreads();
+  cut_pack_rows(b, N, nrows, rowidx + gb, degn, srt, row_bin, row_pos, row_start, bin_rem, bin_cnt, misc, recs, n_recs);
+  cut_pack_rows(b, N, nxr[b], xrowidx + gb, degn, srt, row_bin, row_pos, row_start, bin_rem, bin_cnt, misc, xrecs, n_recs + 1);
 }
+constexpr int CUT_SMEM_PER_NODE = 16 + 9 * 4;
 
 // ------------------------------------------------------------------------------------------------
 // Reference fp32 SIMT edge kernel: second Linear of the edge / coord MLP as a 128x128x128 tile GEMM.
@@ -446,7 +537,8 @@ struct EdgeArgs {
   float* agg;               // GCL out (B*N,128)
   float* x_out;             // COORD out (B*N,3)
   const int* nbr;           // cut-off graphs, tcgen05 path: per-row neighbour lists (k_nbr) or null
-  const int* deg;
+  const int* recs;          // ... and this launch's packed tile records (GCL or COORD list), CUT_REC ints each
+  const int* n_recs;        // [1]
 };
 
 constexpr size_t EDGE_SIMT_SMEM =

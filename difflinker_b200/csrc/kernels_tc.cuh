@@ -22,6 +22,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <type_traits>
 #include <vector>
 
 #include "../../include/difflinker_b200.h"
@@ -231,86 +232,28 @@ struct Tile {
 // Warp-synchronous (all 32 lanes of a table warp call it together): the CTA's contiguous slice of the work-item
 // list is read 32 items at a time with one coalesced load and served from registers by shuffles, so walking the
 // list costs no dependent global round trip per tile (items carry their molecule's live column count).
-template <bool COORD, bool SPARSE = false>
+template <bool COORD>
 struct TileIter {
   const int4* list;
   const int* rowlist;
-  const int* deg;
-  int N, wi_end, wi, rt, c0, cache_base, lane, first, stride;   // wi counts this CTA's items: global index first + wi*stride
+  int N, wi_end, wi, rt, c0, cache_base, lane;
   int4 cache;
-  int d_wi, d_deg, d_node;     // SPARSE: lane l caches (degree, node) of row l of work item d_wi
-  __device__ TileIter(const Plan& p, int N_, const int* deg_ = nullptr)
-      : deg(deg_), N(N_), rt(0), c0(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31), d_wi(-1), d_deg(0), d_node(0) {
+  __device__ TileIter(const Plan& p, int N_) : N(N_), rt(0), c0(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31) {
     // blocked distribution: CTA c owns the contiguous work items [lo, hi) -- consecutive tiles then mostly belong to
     // the same molecule, so the table warps' and producers' L2 lines are reused while they are hot.
     list = COORD ? p.xitems : p.items;
     rowlist = COORD ? p.xrowidx : p.rowidx;
     const int total = COORD ? *p.n_xitems : *p.n_items;
-    const int G = (int)gridDim.x, per = total / G, extra = total % G, c = (int)blockIdx.x;
-    wi = 0;
-    if (SPARSE) {
-      // neighbour-list items differ a lot in edge count (ligand rows vs pocket rows): deal them round-robin
-      first = c; stride = G; wi_end = total > c ? (total - c + G - 1) / G : 0;
-    } else {
-      first = c * per + min(c, extra); stride = 1; wi_end = per + (c < extra ? 1 : 0);
-    }
+    const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
+    wi = c * per + min(c, extra);
+    wi_end = wi + per + (c < extra ? 1 : 0);
     cache = make_int4(0, 0, 0, 0);
   }
-  // Neighbour-list tiles: whole rows of one work item (<= 32 rows) are packed while their degrees fit TN columns; a row
-  // with more than TN neighbours becomes a run of single-row chunk tiles (the epilogue carries its sum across them).
-  __device__ bool next_sparse(Tile& t) {
-    while (wi < wi_end) {
-      if (wi - cache_base >= 32) {
-        cache_base = wi;
-        cache = list[first + min(wi + lane, wi_end - 1) * stride];
-      }
-      const int src = wi - cache_base;
-      const int b = __shfl_sync(0xffffffffu, cache.x, src), r_begin = __shfl_sync(0xffffffffu, cache.y, src);
-      const int r_count = __shfl_sync(0xffffffffu, cache.z, src), nc = __shfl_sync(0xffffffffu, cache.w, src);
-      if (rt >= r_count || nc <= 0) { wi += 1; rt = 0; c0 = 0; continue; }
-      if (d_wi != wi) {                                    // (degree, node) of the item's rows: two dependent loads per item
-        d_wi = wi;
-        d_node = lane < r_count ? rowlist[(size_t)b * N + r_begin + lane] : 0;
-        d_deg = lane < r_count ? deg[(size_t)b * N + d_node] : (1 << 20);
-      }
-      // lane l looks at row rt + l of the item
-      const int sl = (rt + lane) & 31;
-      int dg = __shfl_sync(0xffffffffu, d_deg, sl);
-      const int nd = __shfl_sync(0xffffffffu, d_node, sl);
-      if (rt + lane >= 32) dg = 1 << 20;
-      const int d_first = __shfl_sync(0xffffffffu, dg, 0);
-      t.b = b; t.nc = nc; t.slot0 = r_begin + rt; t.rows = rowlist + (size_t)b * N; t.node = nd;
-      if (c0 > 0 || d_first > TN) {
-        t.nrt = 1; t.c0 = c0; t.ncc = min(TN, d_first - c0); t.Et = t.ncc;
-        t.first_chunk = c0 == 0; t.last_chunk = c0 + TN >= d_first;
-        t.start = lane == 0 ? 0 : t.ncc;
-        c0 += TN;
-        if (c0 >= d_first) { c0 = 0; rt += 1; }
-        return true;
-      }
-      int incl = dg;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += v;
-      }
-      const unsigned fit = __ballot_sync(0xffffffffu, incl <= TN);      // a prefix of the lanes (degrees are >= 1)
-      const int nrt = min(fit == 0xffffffffu ? 32 : __ffs(~fit) - 1, MAXR);
-      t.nrt = nrt; t.c0 = 0; t.first_chunk = true; t.last_chunk = true;
-      t.start = incl - dg;
-      t.Et = __shfl_sync(0xffffffffu, incl, nrt - 1);
-      t.ncc = t.Et;
-      rt += nrt;
-      return true;
-    }
-    return false;
-  }
   __device__ bool next(Tile& t) {
-    if (SPARSE) return next_sparse(t);
     while (wi < wi_end) {
       if (wi - cache_base >= 32) {                        // refill (warp-uniform)
         cache_base = wi;
-        cache = list[first + min(wi + lane, wi_end - 1) * stride];
+        cache = list[min(wi + lane, wi_end - 1)];
       }
       const int src = wi - cache_base;
       const int b = __shfl_sync(0xffffffffu, cache.x, src), r_begin = __shfl_sync(0xffffffffu, cache.y, src);
@@ -329,6 +272,51 @@ struct TileIter {
     return false;
   }
 };
+
+// Cut-off graphs: the CTA walks the tile records k_nbr packed for this call (round-robin over CTAs: records cost one
+// tile, or ceil(degree / 128) chunk tiles for a row with more than 128 neighbours -- its sum is carried in the epilogue's
+// registers, so the chunks stay on one CTA). Warp-synchronous; lane l holds int l of the 128-byte record and the
+// next record is prefetched while the current one is served.
+struct RecIter {
+  const int* recs;
+  int n, k, G, lane, cur, nxt, chunk;
+  __device__ RecIter(const int* recs_, const int* n_recs) : recs(recs_), lane(threadIdx.x & 31), cur(0), chunk(0) {
+    n = *n_recs; G = (int)gridDim.x; k = (int)blockIdx.x;
+    nxt = k < n ? recs[(size_t)k * CUT_REC + lane] : 0;
+  }
+  __device__ bool next(Tile& t) {
+    if (chunk == 0) {
+      if (k >= n) return false;
+      cur = nxt;
+      const int kn = k + G;
+      nxt = kn < n ? recs[(size_t)kn * CUT_REC + lane] : 0;
+    }
+    const int w1 = __shfl_sync(0xffffffffu, cur, 1), v2 = __shfl_sync(0xffffffffu, cur, 2);
+    const int info = __shfl_sync(0xffffffffu, cur, (4 + lane) & 31);
+    t.b = __shfl_sync(0xffffffffu, cur, 0);
+    t.nc = 0; t.slot0 = 0; t.rows = nullptr;
+    if (((w1 >> 8) & 1) == 0) {
+      t.nrt = w1 & 0xff; t.Et = v2; t.ncc = v2; t.c0 = 0; t.first_chunk = true; t.last_chunk = true;
+      t.node = info & 0xffff; t.start = info >> 16;
+      k += G;
+    } else {
+      const int deg = v2, c0 = chunk * TN;
+      t.nrt = 1; t.Et = min(TN, deg - c0); t.ncc = t.Et; t.c0 = c0;
+      t.first_chunk = chunk == 0; t.last_chunk = c0 + TN >= deg;
+      t.node = __shfl_sync(0xffffffffu, cur, 4) & 0xffff;
+      t.start = lane == 0 ? 0 : t.Et;
+      ++chunk;
+      if (t.last_chunk) { chunk = 0; k += G; }
+    }
+    return true;
+  }
+};
+
+template <bool COORD, bool SPARSE>
+__device__ __forceinline__ typename std::conditional<SPARSE, RecIter, TileIter<COORD>>::type make_iter(const EdgeArgs& a, int N) {
+  if constexpr (SPARSE) return RecIter(a.recs, a.n_recs);
+  else return TileIter<COORD>(a.plan, N);
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // The kernel: persistent, 1 CTA / SM, 17 warps in four roles connected by mbarrier rings.
@@ -402,7 +390,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
     // Tile-parallel: table warp k builds the tables of tiles t = k, k+3, ... on its own (4 edges per lane), so the
     // three warps overlap their dependent L2 round trips (index -> coordinates / maxima / mask) across tiles.
     const int tw = warp - W_TBL;
-    TileIter<COORD, SPARSE> iter(a.plan, N, a.deg);
+    typename std::conditional<SPARSE, RecIter, TileIter<COORD>>::type iter = make_iter<COORD, SPARSE>(a, N);
     Tile cur;
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1);
@@ -630,6 +618,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
     if (COORD && hw != 0) goto edge_tc_done;               // coord variant: lanes are edges, 4 warps cover the tile
     float* txs = reinterpret_cast<float*>(sm + OFF_TX);
     float run = 0.f;   // GCL: row sum carried across column chunks (thread = channel); COORD: (row,dim) running sum
+    int xbuf = 0;      // GCL: parity of the half-to-half exchange buffer (reuses the COORD-only txs region)
     for (int t = 0;; ++t) {
       const int acc = t & (N_ACC - 1);
       wait_on(bars + BAR_TBL + 8 * acc, (t / N_ACC) & 1, 0);
@@ -649,10 +638,18 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         const int c = q * 32 + lane;
         const float bias = b2w5[c].x * -1.4426950408889634f;
         const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + acc * TN;
-        for (int rr = (nrt == 1 ? hw : ((hw + t) & 1)); rr < nrt; rr += 2) {   // single-row (chunked) tiles: half 0 only
-          float2 acc2 = make_float2((nrt == 1 && !first_chunk) ? run : 0.f, 0.f);   // (even, odd) column partial sums
-          const int col0 = SPARSE ? rowstart[rr] : rr * ncc_tile;
-          const int ncc = SPARSE ? rowstart[rr + 1] - col0 : ncc_tile;
+        // Multi-row tiles: the two warp halves take alternate rows. Single-row tiles (a row with more live columns than
+        // half a tile, or one 128-column chunk of a longer row): the halves split the row's columns, each carries its own
+        // partial sum across the chunks, and they meet once per row through shared memory (fixed order: deterministic).
+        const bool single = nrt == 1;
+        for (int rr = single ? 0 : ((hw + t) & 1); rr < nrt; rr += 2) {
+          float2 acc2 = make_float2((single && !first_chunk) ? run : 0.f, 0.f);   // (even, odd) column partial sums
+          int col0 = SPARSE ? rowstart[rr] : rr * ncc_tile;
+          int ncc = SPARSE ? rowstart[rr + 1] - col0 : ncc_tile;
+          if (single) {
+            const int split = min(ncc, (((ncc + 1) >> 1) + 15) & ~15);
+            if (hw) { col0 += split; ncc -= split; } else ncc = split;
+          }
           int jj = 0;
           for (; jj + 16 <= ncc; jj += 16) {
             uint32_t r[16];
@@ -699,8 +696,18 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             acc2.x = fmaf(usig_f(fmaf(__uint_as_float(r), ed.y, bias)), ed.x, acc2.x);
           }
           const float accv = acc2.x + acc2.y;
-          if (nrt == 1) run = accv;
-          if (last_chunk) a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
+          if (single) {
+            run = accv;
+            if (last_chunk) {
+              float* xch = txs + (xbuf & 1) * H;             // double-buffered: a half may run one row ahead of the other
+              ++xbuf;
+              if (hw) xch[c] = accv;
+              named_sync(4 + q, 64);                         // warps q and q + 4: same TMEM lane quarter, same channels
+              if (!hw) a.agg[(gb + rownode[rr]) * H + c] = (accv + xch[c]) / gm.normalization_factor;
+            }
+          } else {
+            a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
+          }
         }
         tc_fence_before();
         __syncwarp();
@@ -770,7 +777,8 @@ inline dl_status configure() {
       cudaFuncSetAttribute(k_edge_tc<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(k_edge_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
       cudaFuncSetAttribute(k_edge_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_edge_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
+      cudaFuncSetAttribute(k_edge_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
+      cudaFuncSetAttribute(k_edge_tc<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
     return DL_ERR_CUDA;
   return DL_OK;
 }
@@ -803,7 +811,7 @@ inline size_t pack_w2(const std::vector<float>& W, std::vector<__half>& blob, fl
 inline dl_status launch_edge_tc(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc, int num_sms,
                                 cudaStream_t st) {
   const __half* w = reinterpret_cast<const __half*>(w2_tc);
-  if (ea.nbr != nullptr) {
+  if (ea.recs != nullptr) {
     if (coord) k_edge_tc<true, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
     else k_edge_tc<false, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
   } else if (coord) k_edge_tc<true, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
@@ -816,14 +824,23 @@ inline dl_status profile_edge_tc(const Geom& gm, const EdgeArgs& ea, const void*
   unsigned long long* d = nullptr;
   if (cudaMalloc(&d, (size_t)num_sms * 16 * 8) != cudaSuccess) return DL_ERR_CUDA;
   cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
-  k_edge_tc<false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
+  if (ea.recs != nullptr)
+    k_edge_tc<false, true, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
+  else
+    k_edge_tc<false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
   if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
   std::vector<unsigned long long> h((size_t)num_sms * 16);
   cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
   cudaFree(d);
   double avg[16] = {0};
   for (int b = 0; b < num_sms; ++b) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)b * 16 + i] / num_sms;
-  fprintf(stderr, "[dl prof] cycles per CTA (avg over %d): tiles %.1f\n", num_sms, avg[10]);
+  unsigned long long tmin = ~0ull, tmax = 0, cmin = ~0ull, cmax = 0;
+  for (int b = 0; b < num_sms; ++b) {
+    tmin = std::min(tmin, h[(size_t)b * 16 + 10]); tmax = std::max(tmax, h[(size_t)b * 16 + 10]);
+    cmin = std::min(cmin, h[(size_t)b * 16 + 15]); cmax = std::max(cmax, h[(size_t)b * 16 + 15]);
+  }
+  fprintf(stderr, "[dl prof] cycles per CTA (avg over %d): tiles %.1f (min %llu max %llu), epilogue total min %llu max %llu\n",
+          num_sms, avg[10], tmin, tmax, cmin, cmax);
   fprintf(stderr, "[dl prof]  table   : wait tempty %.0f | total %.0f\n", avg[0], avg[3]);
   fprintf(stderr, "[dl prof]  producer: wait tbl %.0f, wait empty %.0f | total %.0f\n", avg[4], avg[5], avg[7]);
   fprintf(stderr, "[dl prof]  mma     : wait full %.0f, wait tempty %.0f | total %.0f\n", avg[8], avg[9], avg[11]);

@@ -43,9 +43,10 @@ def _build_edm(hp: dict, edge_impl='auto'):
                norm_values=hp['normalize_factors'])
 
 
-def sample_chain(model, data, sample_fn=None, keep_frames=None):
-    """Body of DDPM.sample_chain (lightning.py:405-463), shared by `DDPM` below and by accelerated reference
-    modules; `model` needs .edm, .inpainting, .anchors_context, .train_data_prefix, .center_of_mass, .val_dataset."""
+def sampler_inputs(model, data, sample_fn=None):
+    """What DDPM.sample_chain hands to EDM.sample_chain (lightning.py:405-452): the template batch, the context
+    columns and the centred coordinates, as the keyword arguments of `edm.sample_chain`.
+    `model` needs .inpainting, .anchors_context, .train_data_prefix, .center_of_mass, .val_dataset."""
     if sample_fn is None:
         linker_sizes = data['linker_mask'].sum(1).view(-1).int()
     else:
@@ -73,9 +74,16 @@ def sample_chain(model, data, sample_fn=None, keep_frames=None):
     else:
         raise NotImplementedError(model.center_of_mass)
     x = utils.remove_partial_mean_with_mask(x, node_mask, com_mask)
-    chain = model.edm.sample_chain(x=x, h=h, node_mask=node_mask, edge_mask=edge_mask, fragment_mask=fragment_mask,
-                                   linker_mask=linker_mask, context=context, keep_frames=keep_frames)
-    return chain, node_mask
+    return dict(x=x, h=h, node_mask=node_mask, edge_mask=edge_mask, fragment_mask=fragment_mask,
+                linker_mask=linker_mask, context=context)
+
+
+def sample_chain(model, data, sample_fn=None, keep_frames=None):
+    """Body of DDPM.sample_chain (lightning.py:405-463), shared by `DDPM` below and by accelerated reference
+    modules (`model` additionally needs .edm)."""
+    kw = sampler_inputs(model, data, sample_fn)
+    chain = model.edm.sample_chain(**kw, keep_frames=keep_frames)
+    return chain, kw['node_mask']
 
 
 class DDPM(nn.Module):

@@ -151,7 +151,8 @@ class EDM(torch.nn.Module):
         if self.dynamics.graph_type == 'FC' and edge_mask is not None:
             em = prep(edge_mask.reshape(-1), torch.int8)
             assert em.numel() == n_samples * n_nodes * n_nodes
-        ctx = None if context is None else prep(context.reshape(n_samples, n_nodes, -1), torch.float32)
+        ctx = None if context is None else prep(
+            context.reshape(n_samples, n_nodes, self.dynamics.context_node_nf), torch.float32)   # wrong width -> raises
         coef = self.step_coefficients(keep_frames, n_samples)
         norm = (C.c_float * 3)(float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]))
         chain = torch.empty((keep_frames, n_samples, n_nodes, d), device=dev, dtype=torch.float32)
@@ -256,7 +257,8 @@ class InpaintingEDM(EDM):
         em = None
         if self.dynamics.graph_type == 'FC' and edge_mask is not None:
             em = prep(edge_mask.reshape(-1), torch.int8)
-        ctx = None if context is None else prep(context.reshape(n_samples, n_nodes, -1), torch.float32)
+        ctx = None if context is None else prep(
+            context.reshape(n_samples, n_nodes, self.dynamics.context_node_nf), torch.float32)   # wrong width -> raises
         coef = self.step_coefficients(keep_frames, n_samples)
         norm = (C.c_float * 3)(float(self.norm_values[0]), float(self.norm_values[1]), float(self.norm_biases[1]))
         chain = torch.empty((keep_frames, n_samples, n_nodes, d), device=dev, dtype=torch.float32)

@@ -162,6 +162,10 @@ float dl_last_elapsed_ms(dl_engine* e);
  * edge kernel -- relaunched `reps` times on the engine's current workspace (state of the last call; the
  * caller's mask tensors of that call must still be alive). Blocking. Negative on error. For bench.py's roofline. */
 float dl_time_edge_kernel(dl_engine* e, int32_t reps);
+/* Cut-off (pocket) graphs, tcgen05 path: what the neighbour-list kernel packed for the most recent forward call --
+ * out[0] GCL tile records, out[1] GCL tiles (a row with more than 128 neighbours expands to several), out[2] GCL edges,
+ * out[3] coordinate-update records.  All zero for FC graphs.  Blocking (device synchronise). For bench.py / tests. */
+dl_status dl_cut_graph_stats(dl_engine* e, int64_t* out);
 /* Self-test of the tcgen05 edge-MLP tile against the SIMT path on random data. Blocking.
  * Returns DL_OK and writes the max abs/rel error. */
 dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err);

@@ -354,6 +354,23 @@ def test_cutoff_graph_neighbour_lists_isolated_rows_and_chunked_rows(graph_type)
     dyn_simt, _ = helpers.build_dynamics(spec, 1, edge_impl='simt')
     got_simt = run_dyn(dyn_simt, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], ctx, dev())
     assert rel_err(got, got_simt) <= REL_TOL
+    # what the neighbour-list kernel packed: exactly the reference's edges (+ one padding column per isolated live row),
+    # in well-filled 128-edge tiles (first-fit decreasing over the rows of a molecule)
+    import ctypes
+    from difflinker_b200 import _native
+    stats = (ctypes.c_int64 * 4)()
+    _native.check(_native.load_library().dl_cut_graph_stats(dyn.engine(0), stats), "dl_cut_graph_stats")
+    B, N = z.shape[:2]
+    nmf = batch['atom_mask'].reshape(B * N, 1).float()
+    flat = z.reshape(B * N, -1) * nmf
+    cflat = ctx.reshape(B * N, -1)
+    row, col = orc.pocket_edge_index(flat[:, :3], nmf, batch['edge_mask'].reshape(-1), batch['linker_mask'].reshape(B * N, 1),
+                                     cflat[:, -2], cflat[:, -1], graph_type)
+    deg = torch.bincount(row, minlength=B * N)
+    isolated = int(((deg == 0) & (nmf.view(-1) > 0)).sum())
+    assert isolated >= 5
+    assert stats[2] == row.numel() + isolated
+    assert stats[1] <= math.ceil(1.35 * stats[2] / 128) + B, (stats[1], stats[2])
 
 
 @pytest.mark.parametrize("N", [128, 512])
