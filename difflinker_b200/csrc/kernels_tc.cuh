@@ -334,7 +334,10 @@ __device__ __forceinline__ typename std::conditional<SPARSE, RecIter, TileIter<C
 // PROF = true adds clock64() accounting per role (wait vs work cycles) into `prof` (16 x u64 per CTA); debug only.
 // SPARSE = true: cut-off (pocket) graphs -- tiles are packed from the per-row neighbour lists k_nbr built for this
 // forward call, so only edges the reference creates are processed (egnn.py:554-596); FC graphs use SPARSE = false.
-template <bool COORD, bool PROF = false, bool SPARSE = false>
+// SPLIT = true: single-row tiles (chunks of rows longer than a tile: N > 64 on FC graphs, long rows of cut-off graphs)
+// are split column-wise between the two epilogue warp halves; the SPLIT = false instantiation keeps the leaner epilogue for
+// workloads whose tiles are (almost) all multi-row (N <= 64: the headline config).
+template <bool COORD, bool PROF = false, bool SPARSE = false, bool SPLIT = SPARSE>
 __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArgs a, const __half* __restrict__ w2tc,
                                                                 unsigned long long* __restrict__ prof = nullptr) {
   extern __shared__ uint8_t smem_raw[];
@@ -641,9 +644,9 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
         // Multi-row tiles: the two warp halves take alternate rows. Single-row tiles (a row with more live columns than
         // half a tile, or one 128-column chunk of a longer row): the halves split the row's columns, each carries its own
         // partial sum across the chunks, and they meet once per row through shared memory (fixed order: deterministic).
-        const bool single = nrt == 1;
-        for (int rr = single ? 0 : ((hw + t) & 1); rr < nrt; rr += 2) {
-          float2 acc2 = make_float2((single && !first_chunk) ? run : 0.f, 0.f);   // (even, odd) column partial sums
+        const bool single = SPLIT && nrt == 1;
+        for (int rr = single ? 0 : (nrt == 1 ? hw : ((hw + t) & 1)); rr < nrt; rr += 2) {   // !SPLIT: single-row tiles on half 0
+          float2 acc2 = make_float2((nrt == 1 && !first_chunk) ? run : 0.f, 0.f);   // (even, odd) column partial sums
           int col0 = SPARSE ? rowstart[rr] : rr * ncc_tile;
           int ncc = SPARSE ? rowstart[rr + 1] - col0 : ncc_tile;
           if (single) {
@@ -706,7 +709,8 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
               if (!hw) a.agg[(gb + rownode[rr]) * H + c] = (accv + xch[c]) / gm.normalization_factor;
             }
           } else {
-            a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
+            if (nrt == 1) run = accv;
+            if (last_chunk) a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
           }
         }
         tc_fence_before();
@@ -772,15 +776,16 @@ edge_tc_done:
 // ---------------------------------------------------------------------------------------------------------
 // Host side
 // ---------------------------------------------------------------------------------------------------------
+template <typename K>
+inline bool opt_in_smem(K kern) {
+  return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) == cudaSuccess;
+}
 inline dl_status configure() {
-  if (cudaFuncSetAttribute(k_edge_tc<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_edge_tc<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_edge_tc<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_edge_tc<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_edge_tc<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_edge_tc<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess)
-    return DL_ERR_CUDA;
-  return DL_OK;
+  const bool ok = opt_in_smem(k_edge_tc<true, false, false>) && opt_in_smem(k_edge_tc<true, false, true>) &&
+                  opt_in_smem(k_edge_tc<false, false, false, false>) && opt_in_smem(k_edge_tc<false, false, false, true>) &&
+                  opt_in_smem(k_edge_tc<false, false, true>) && opt_in_smem(k_edge_tc<false, true, false, false>) &&
+                  opt_in_smem(k_edge_tc<false, true, false, true>) && opt_in_smem(k_edge_tc<false, true, true>);
+  return ok ? DL_OK : DL_ERR_CUDA;
 }
 
 // edge_mlp.2 / coord_mlp.2 weight (out=128, in=128, row-major) -> [hi|lo][kc][out][8] fp16, scaled by the power of
@@ -808,14 +813,18 @@ inline size_t pack_w2(const std::vector<float>& W, std::vector<__half>& blob, fl
   return off;
 }
 
+// FC graphs: rows longer than half a tile (N > 64) make single-row tiles the norm -> column-split epilogue.
+inline bool split_epilogue(const Geom& gm) { return gm.N > 64; }
+
 inline dl_status launch_edge_tc(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc, int num_sms,
                                 cudaStream_t st) {
   const __half* w = reinterpret_cast<const __half*>(w2_tc);
   if (ea.recs != nullptr) {
     if (coord) k_edge_tc<true, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
     else k_edge_tc<false, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
-  } else if (coord) k_edge_tc<true, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
-  else k_edge_tc<false, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+  } else if (coord) k_edge_tc<true, false, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+  else if (split_epilogue(gm)) k_edge_tc<false, false, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
+  else k_edge_tc<false, false, false, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, w, nullptr);
   return DL_OK;
 }
 
@@ -826,8 +835,10 @@ inline dl_status profile_edge_tc(const Geom& gm, const EdgeArgs& ea, const void*
   cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
   if (ea.recs != nullptr)
     k_edge_tc<false, true, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
+  else if (split_epilogue(gm))
+    k_edge_tc<false, true, false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
   else
-    k_edge_tc<false, true><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
+    k_edge_tc<false, true, false, false><<<num_sms, EDGE_TC_THREADS, SMEM_BYTES, st>>>(gm, ea, reinterpret_cast<const __half*>(w2_tc), d);
   if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
   std::vector<unsigned long long> h((size_t)num_sms * 16);
   cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
