@@ -19,6 +19,11 @@ class DLConfig(C.Structure):
                 ("normalization_factor", C.c_float)]
 
 
+class DLSizeGNNConfig(C.Structure):
+    _fields_ = [("in_node_nf", C.c_int32), ("hidden_nf", C.c_int32), ("out_node_nf", C.c_int32),
+                ("n_layers", C.c_int32), ("device", C.c_int32)]
+
+
 class DLStepCoef(C.Structure):
     _fields_ = [("t", C.c_float), ("a", C.c_float), ("b", C.c_float), ("c", C.c_float), ("frame", C.c_int32),
                 ("qa", C.c_float), ("qb", C.c_float), ("pad", C.c_float)]
@@ -43,6 +48,11 @@ SYMBOLS = {
     "dl_time_edge_kernel": (_F, [_P, _I32]),
     "dl_selftest_tc": (_I32, [_P, C.POINTER(_F), C.POINTER(_F)]),
     "dl_cut_graph_stats": (_I32, [_P, C.POINTER(_I64)]),
+    "dl_sizegnn_create": (_I32, [C.POINTER(DLSizeGNNConfig), C.POINTER(_P)]),
+    "dl_sizegnn_destroy": (_I32, [_P]),
+    "dl_sizegnn_set_weight": (_I32, [_P, C.c_char_p, _P, _I64]),
+    "dl_sizegnn_finalize_weights": (_I32, [_P]),
+    "dl_sizegnn_forward": (_I32, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
     "dl_restore_frame": (_I32, [_I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "dl_format_xyz": (_I64, [_I32, _I32, _I32, _P, _I32, _P, _I32, _P, C.POINTER(C.c_char_p), _I32, _P, _I64, _P]),
 }

@@ -341,7 +341,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
           if (l + 1 < L) { na.proj2 = proj_of(e->gcl[(l + 1) * S]); na.AB2 = ws.ABg; na.ABmax2 = ws.ABgmax; }
           else na.AB2 = nullptr;
         }
-        k_node<<<node_blocks, 256, node_smem, st>>>(n, na);
+        k_node<ACT_SILU><<<node_blocks, 256, node_smem, st>>>(n, na);
       }
       LAUNCH_CHECK();
       e->launches += 1;
@@ -461,7 +461,7 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaEventCreate(&e->ev_t0));
   CK(cudaEventCreate(&e->ev_t1));
   CK(cudaMalloc((void**)&e->step_ctr, 2 * sizeof(int)));
-  CK(cudaFuncSetAttribute(k_node, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * NODE_TM * LDX * sizeof(float)));
+  CK(cudaFuncSetAttribute(k_node<ACT_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * NODE_TM * LDX * sizeof(float)));
   CK(cudaFuncSetAttribute(k_edge_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_edge_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * CUT_SMEM_PER_NODE));
@@ -866,3 +866,5 @@ dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err) {
 }
 
 }  // extern "C"
+
+#include "size_gnn.cuh"

@@ -24,7 +24,7 @@ __global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edg
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
   for (int i = tid; i < N; i += blockDim.x) { rowlive[i] = 0; collive[i] = 0; }
   __syncthreads();
-  if (graph_type == 0 && edge_mask != nullptr) {
+  if ((graph_type == 0 || graph_type == 4) && edge_mask != nullptr) {
     const int8_t* em = edge_mask + (size_t)b * N * N;
     for (int i = warp; i < N; i += nwarp) {
       int any = 0;
@@ -35,7 +35,7 @@ __global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edg
       any = __any_sync(0xffffffffu, any);
       if (lane == 0 && any) rowlive[i] = 1;
     }
-  } else if (graph_type == 0) {
+  } else if (graph_type == 0 || graph_type == 4) {
     for (int i = tid; i < N; i += blockDim.x) { rowlive[i] = 1; collive[i] = 1; }
   } else {
     for (int i = tid; i < N; i += blockDim.x) {
@@ -83,6 +83,11 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __r
   *n_xmols = xc;
   *n_xitems = xi;
 }
+
+// Activation of the fp32 SIMT kernels: SiLU for the denoiser (egnn.py:325), ReLU for SizeGNN (linker_size.py:60).
+constexpr int ACT_SILU = 0, ACT_RELU = 1;
+template <int ACT>
+__device__ __forceinline__ float act_f(float x) { return ACT == ACT_RELU ? fmaxf(x, 0.f) : silu_f(x); }
 
 // ------------------------------------------------------------------------------------------------
 // Node-level SIMT tile GEMM: 32 nodes x 128 channels per CTA (256 threads).
@@ -234,7 +239,7 @@ __global__ void __launch_bounds__(256) k_prep(Geom gm, PrepArgs a) {
           reinterpret_cast<float*>(a.x4 + g)[d] = v;
         }
       }
-      if (gm.graph_type != 0) {
+      if (gm.graph_type >= 1 && gm.graph_type <= 3) {
         // egnn.py:566-570: ligand = (linker | fragment_only) & valid ; pocket = pocket_only & valid
         int valid = m != 0.f;
         int pk = a.context[(size_t)g * gm.C + gm.C - 1] != 0.f;
@@ -289,6 +294,7 @@ struct NodeArgs {
   ProjW proj2; float* AB2; float* ABmax2;  // AB2 == nullptr -> skip
 };
 
+template <int ACT = ACT_SILU>
 __global__ void __launch_bounds__(256) k_node(int n_total, NodeArgs a) {
   extern __shared__ __align__(16) float sm_node[];
   float* hs = sm_node;                    // [32][LDX]
@@ -318,8 +324,8 @@ __global__ void __launch_bounds__(256) k_node(int n_total, NodeArgs a) {
 #pragma unroll
     for (int r = 0; r < 4; ++r)
       *reinterpret_cast<float4*>(hid + (warp * 4 + r) * LDX + lane * 4) =
-          make_float4(silu_f(acc[r][0] + bb.x), silu_f(acc[r][1] + bb.y), silu_f(acc[r][2] + bb.z),
-                      silu_f(acc[r][3] + bb.w));
+          make_float4(act_f<ACT>(acc[r][0] + bb.x), act_f<ACT>(acc[r][1] + bb.y), act_f<ACT>(acc[r][2] + bb.z),
+                      act_f<ACT>(acc[r][3] + bb.w));
   }
   __syncwarp();
   zero_acc(acc);
@@ -339,7 +345,7 @@ __global__ void __launch_bounds__(256) k_node(int n_total, NodeArgs a) {
     }
   }
   __syncwarp();
-  project_ab(hs + warp * 4 * LDX, a.proj1, a.AB1, a.ABmax1, g0, n_total, warp, lane);
+  if (a.AB1 != nullptr) project_ab(hs + warp * 4 * LDX, a.proj1, a.AB1, a.ABmax1, g0, n_total, warp, lane);
   if (a.AB2 != nullptr) project_ab(hs + warp * 4 * LDX, a.proj2, a.AB2, a.ABmax2, g0, n_total, warp, lane);
 }
 
@@ -351,6 +357,8 @@ __global__ void __launch_bounds__(256) k_node(int n_total, NodeArgs a) {
 __device__ __forceinline__ float edge_weight(int graph_type, const int8_t* __restrict__ em_mol, int N, int i, int j,
                                              int ci, int cj, float d0) {
   if (graph_type == 0) return em_mol != nullptr ? (float)em_mol[(size_t)i * N + j] : 1.0f;
+  if (graph_type == 4)  // SizeGNN: (edge_mask.bool() & (radial < 6)).long() -- on the SQUARED distance (linker_size_lightning.py:107-108)
+    return ((em_mol == nullptr || em_mol[(size_t)i * N + j] != 0) && d0 < 6.0f) ? 1.f : 0.f;
   if (i == j || ci == 0 || cj == 0) return 0.f;
   float dist = sqrtf(d0);
   if (graph_type == 1) return dist <= 4.0f ? 1.f : 0.f;
@@ -545,7 +553,7 @@ constexpr size_t EDGE_SIMT_SMEM =
     sizeof(float) * ((size_t)H * H /*W2s*/ + (size_t)H * ET /*S1*/ + (size_t)ET * LDB /*Bs*/ + (size_t)MAXR * H /*As*/ +
                      4 * H /*b2,wd,w0,w5*/ + ET /*ems*/ + ET * 3 /*cds*/ + ET /*phis*/);
 
-template <bool COORD>
+template <bool COORD, int ACT = ACT_SILU>
 __global__ void __launch_bounds__(256, 1) k_edge_simt(Geom gm, EdgeArgs a) {
   extern __shared__ __align__(16) float sm_edge[];
   float* W2s = sm_edge;
@@ -619,7 +627,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_simt(Geom gm, EdgeArgs a) {
             d0 = ex * ex + ey * ey + ez * ez;
             if (kh == 0) {
               int ci = 0, cj = 0;
-              if (gm.graph_type != 0) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
+              if (gm.graph_type >= 1 && gm.graph_type <= 3) { ci = a.cls[gb + i]; cj = a.cls[gb + j]; }
               ems[e] = edge_weight(gm.graph_type, em_mol, N, i, j, ci, cj, d0);
               if (COORD) {
                 float inv = 1.0f / (sqrtf(d + 1e-8f) + gm.norm_constant);   // egnn.py:299-300
@@ -636,7 +644,7 @@ __global__ void __launch_bounds__(256, 1) k_edge_simt(Geom gm, EdgeArgs a) {
           for (int kk = 0; kk < H / 2; ++kk) {
             int k = kh * (H / 2) + kk;
             float pre = Ar[k] + Br[k] + d * wds[k] + d0 * w0s[k];
-            S1[k * ET + e] = valid ? silu_f(pre) : 0.f;
+            S1[k * ET + e] = valid ? act_f<ACT>(pre) : 0.f;
           }
         }
         __syncthreads();
@@ -670,10 +678,10 @@ __global__ void __launch_bounds__(256, 1) k_edge_simt(Geom gm, EdgeArgs a) {
           for (int qh = 0; qh < 2; ++qh) {
             int c = qh * 64 + tx * 4;
             float4 o;
-            o.x = silu_f(acc[p][qh * 4 + 0] + b2s[c + 0]) * w;
-            o.y = silu_f(acc[p][qh * 4 + 1] + b2s[c + 1]) * w;
-            o.z = silu_f(acc[p][qh * 4 + 2] + b2s[c + 2]) * w;
-            o.w = silu_f(acc[p][qh * 4 + 3] + b2s[c + 3]) * w;
+            o.x = act_f<ACT>(acc[p][qh * 4 + 0] + b2s[c + 0]) * w;
+            o.y = act_f<ACT>(acc[p][qh * 4 + 1] + b2s[c + 1]) * w;
+            o.z = act_f<ACT>(acc[p][qh * 4 + 2] + b2s[c + 2]) * w;
+            o.w = act_f<ACT>(acc[p][qh * 4 + 3] + b2s[c + 3]) * w;
             *reinterpret_cast<float4*>(Outs + e * H + c) = o;
           }
         }
@@ -972,5 +980,34 @@ __global__ void k_init_z(int n_total, int xd, const float* __restrict__ xh, cons
   float l = lm[g];
   z[idx] = xh[idx] * fm[g] + (noise[idx] * l) * l;
 }
+
+// SizeGNN head (linker_size.py:88-91 + linker_size_lightning.py:110): out[b] = mean over ALL N padded rows of
+// embedding_out(h[b, n]) -- masked rows hold h = 0 and contribute the bias, exactly as in the reference.
+// One CTA per molecule, warp per node (strided), lanes over channels; per-warp partial sums are combined in warp order.
+constexpr int SZ_MAX_OUT = 64;
+__global__ void __launch_bounds__(256) k_sz_out(int N, int out_nf, const float* __restrict__ h, const float* __restrict__ Wo,
+                                               const float* __restrict__ bo, float* __restrict__ out) {
+  __shared__ float part[8][SZ_MAX_OUT];
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int o = lane; o < out_nf; o += 32) part[warp][o] = 0.f;
+  __syncwarp();
+  for (int n = warp; n < N; n += 8) {
+    const float4 hv = *reinterpret_cast<const float4*>(h + ((size_t)b * N + n) * H + lane * 4);
+    for (int o = 0; o < out_nf; ++o) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(Wo + (size_t)o * H + lane * 4));
+      float s = hv.x * w.x + hv.y * w.y + hv.z * w.z + hv.w * w.w;
+#pragma unroll
+      for (int k = 16; k > 0; k >>= 1) s += __shfl_xor_sync(0xffffffffu, s, k);
+      if (lane == 0) part[warp][o] += s + bo[o];
+    }
+  }
+  __syncthreads();
+  if (tid < out_nf) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += part[w][tid];
+    out[(size_t)b * out_nf + tid] = s / (float)N;
+  }
+}
+
 
 }  // namespace dl

@@ -178,3 +178,22 @@ def cutoff_edge_counts(batch, graph_type: str):
 
 def bytes_alg(N: int, spec: WorkloadSpec) -> float:
     return spec.L * (2 * spec.S + 1) * N * 128 * 4 + 64 * N
+
+
+def init_size_gnn_like_trained(module, seed: int):
+    """Default torch init leaves the size classifier's logits almost constant; scale the weights a little and give the
+    BatchNorm layers non-trivial running statistics so that every term of the forward pass matters in parity tests."""
+    g = torch.Generator().manual_seed(4242 + seed)
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if p.dim() == 2:
+                p.mul_(1.5)
+        for name, b in module.named_buffers():
+            if name.endswith("running_mean"):
+                b.copy_(0.1 * torch.randn(b.shape, generator=g))
+            elif name.endswith("running_var"):
+                b.copy_(0.5 + torch.rand(b.shape, generator=g))
+        for name, p in module.named_parameters():
+            if ".node_mlp.1." in name or ".node_mlp.4." in name:            # BatchNorm affine
+                p.copy_(1.0 + 0.2 * torch.randn(p.shape, generator=g) if name.endswith("weight")
+                        else 0.1 * torch.randn(p.shape, generator=g))

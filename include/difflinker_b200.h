@@ -16,6 +16,7 @@
  *     sample_p_zs_given_zt_only_linker  edm.py:178-208
  *     sample_p_xh_given_z0_only_linker  edm.py:210-235
  *   InpaintingEDM.sample_chain   src/edm.py:549-612      dl_sample_chain with DL_SAMPLER_INPAINT
+ *   SizeClassifier.forward       src/linker_size_lightning.py:83-110  dl_sizegnn_create/.../dl_sizegnn_forward
  *   frame restore + .xyz text    generate.py:163-171, src/visualizer.py:14-31   dl_restore_frame, dl_format_xyz
  *   utils.FoundNaNException      src/utils.py:274-289    DL_NAN_DETECTED + per-molecule nan_flags
  *
@@ -193,6 +194,36 @@ dl_status dl_restore_frame(int32_t B, int32_t N, int32_t row_stride, float* xh, 
 int64_t dl_format_xyz(int32_t B, int32_t N, int32_t F, const float* positions, int32_t pos_row_stride,
                       const float* one_hot, int32_t oh_row_stride, const int8_t* node_mask,
                       const char* const* symbols, int32_t n_symbols, char* out, int64_t out_cap, int64_t* offsets);
+
+/*
+ * SizeGNN (src/linker_size.py:45-91) as called by SizeClassifier.forward (src/linker_size_lightning.py:83-110): the
+ * linker-size classifier that generate.py:88-99 runs once per batch before the sampler.
+ *   out[b] = mean_n embedding_out( GCL_L(...GCL_1(embedding_in(one_hot*frag))) )     (B, out_node_nf) logits
+ * with ReLU GCLs on the fragment atoms, edges = fragment pairs (self loops included) whose SQUARED distance is < 6
+ * (linker_size_lightning.py:107-108), sum aggregation, normalization_factor 1.
+ * Weight names: "embedding_in.{weight,bias}", "layer<l>.edge_mlp.{0,2}.{weight,bias}", "layer<l>.node_mlp.{0,2}.{weight,
+ * bias}" (l = 0 is SizeGNN.gcl1, l >= 1 is gcl_layers[l-1]; with normalization='batch_norm' the caller folds the eval-mode
+ * BatchNorm1d affine maps into node_mlp.0 / node_mlp.2), "embedding_out.{weight,bias}"; (out,in) row-major fp32, HOST.
+ */
+typedef struct dl_sizegnn dl_sizegnn; /* opaque */
+typedef struct dl_sizegnn_config {
+  int32_t in_node_nf;   /* one-hot width the network was trained with */
+  int32_t hidden_nf;    /* 128 */
+  int32_t out_node_nf;  /* number of linker-size classes */
+  int32_t n_layers;     /* GCLs (train_size_gnn.py:20: 3) */
+  int32_t device;
+} dl_sizegnn_config;
+dl_status dl_sizegnn_create(const dl_sizegnn_config* cfg, dl_sizegnn** out);
+dl_status dl_sizegnn_destroy(dl_sizegnn* e);
+dl_status dl_sizegnn_set_weight(dl_sizegnn* e, const char* name, const float* host_data, int64_t numel);
+dl_status dl_sizegnn_finalize_weights(dl_sizegnn* e);
+/* DEVICE buffers, enqueued on `stream`:
+ *   xh            (B,N,3+in_node_nf) fp32: [positions | one_hot] (the kernel applies fragment_mask to both)
+ *   fragment_mask (B,N) int8 0/1       (data['fragment_mask'], or 'fragment_only_mask' with pockets)
+ *   edge_mask     (B,N,N) int8, non-zero = live pair (datasets.collate_with_fragment_edges, datasets.py:396-402), or NULL
+ *   out           (B,out_node_nf) fp32 logits */
+dl_status dl_sizegnn_forward(dl_sizegnn* e, int32_t B, int32_t N, const float* xh, const int8_t* fragment_mask,
+                             const int8_t* edge_mask, float* out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -417,6 +417,57 @@ def inpainting_sample_chain(sd, cfg: OracleConfig, gamma: Tensor, T: int, x, h, 
 
 
 # ------------------------------------------------------------------------------------------------
+# linker-size classifier (linker_size.py:45-91, linker_size_lightning.py:83-110)
+# ------------------------------------------------------------------------------------------------
+def _bn_eval(sd, prefix, v, eps=1e-5):
+    """nn.BatchNorm1d in eval mode (running statistics)."""
+    return (v - sd[prefix + ".running_mean"]) / torch.sqrt(sd[prefix + ".running_var"] + eps) * sd[prefix + ".weight"] \
+        + sd[prefix + ".bias"]
+
+
+def size_gcl_forward(sd, prefix, h, row, col, edge_attr, node_mask, edge_mask, normalization):
+    """egnn.GCL with activation=ReLU, edges_in_d=1, normalization_factor=1, 'sum' (egnn.py:10-80 as built by
+    linker_size.py:53-83)."""
+    e_in = torch.cat([h.index_select(0, row), h.index_select(0, col), edge_attr], dim=1)
+    m = F.relu(_lin(sd, prefix + ".edge_mlp.0", e_in))
+    m = F.relu(_lin(sd, prefix + ".edge_mlp.2", m))
+    m = m * edge_mask
+    agg = segment_reduce(m, row, h.shape[0], 1, "sum")
+    n_in = torch.cat([h, agg], dim=1)
+    if normalization is None:
+        upd = _lin(sd, prefix + ".node_mlp.2", F.relu(_lin(sd, prefix + ".node_mlp.0", n_in)))
+    else:
+        upd = _bn_eval(sd, prefix + ".node_mlp.1", _lin(sd, prefix + ".node_mlp.0", n_in))
+        upd = _bn_eval(sd, prefix + ".node_mlp.4", _lin(sd, prefix + ".node_mlp.3", F.relu(upd)))
+    return (h + upd) * node_mask
+
+
+def size_classifier_forward(sd, data, in_node_nf, n_layers, normalization=None, with_pocket=False, adjust_shape=False,
+                            prefix="gnn"):
+    """SizeClassifier.forward(return_loss=False) (linker_size_lightning.py:83-110) with SizeGNN.forward inlined
+    (linker_size.py:85-91). `data` as produced by collate_with_fragment_edges. Returns the (B, classes) logits."""
+    h, x = data['one_hot'].float(), data['positions'].float()
+    fragment_mask = (data['fragment_only_mask'] if with_pocket else data['fragment_mask']).float()
+    x = x * fragment_mask
+    h = h * fragment_mask
+    if h.shape[-1] != in_node_nf and adjust_shape:
+        h = h[..., :-1]
+    B, N = x.shape[0], x.shape[1]
+    fm = fragment_mask.reshape(B * N, 1)
+    x = x.reshape(B * N, -1)
+    h = h.reshape(B * N, -1)
+    row, col = fc_edge_index(N, B)                                        # datasets.py:405-412
+    radial, _ = pair_geometry(x, row, col)                                # coord2diff: SQUARED distance
+    em = (data['edge_mask'].reshape(-1, 1).bool() & (radial < 6)).long()  # linker_size_lightning.py:107-108
+    h = _lin(sd, prefix + ".embedding_in", h)
+    h = size_gcl_forward(sd, prefix + ".gcl1", h, row, col, radial, fm, em, normalization)
+    for l in range(n_layers - 1):
+        h = size_gcl_forward(sd, f"{prefix}.gcl_layers.{l}", h, row, col, radial, fm, em, normalization)
+    out = _lin(sd, prefix + ".embedding_out", h)
+    return out.view(B, N, -1).mean(1)
+
+
+# ------------------------------------------------------------------------------------------------
 # output stage (generate.py:163-171, visualizer.py:14-31)
 # ------------------------------------------------------------------------------------------------
 def restore_frame(x, positions, com_mask, node_mask):

@@ -233,6 +233,40 @@ def golden_inpaint_chain(ns, name, spec, nb, seed, keep_frames):
     save(name, meta, chain=chain, node_mask=node_mask)
 
 
+def golden_size_classifier(ns):
+    """SizeClassifier.forward(return_loss=False) of the live reference (linker_size_lightning.py:83-110) on batches built by
+    the reference's collate_with_fragment_edges; pins oracle.size_classifier_forward and the host mirror's parameter
+    layout / collate."""
+    import importlib
+    from difflinker_b200 import linker_size as mine
+    lsl = importlib.import_module("src.linker_size_lightning")
+    for name, spec, nb, normalization, seed in (("size_gnn_zinc", synthetic.SPECS["cfg1_plumbing"], 4, None, 5),
+                                                ("size_gnn_zinc_bn", synthetic.SPECS["cfg2_zinc_ragged"], 6, "batch_norm", 6)):
+        out_nf = len(ns.const.ZINC_TRAIN_LINKER_ID2SIZE)
+        torch.manual_seed(seed)
+        ref = lsl.SizeClassifier(None, None, None, in_node_nf=spec.F, hidden_nf=128, out_node_nf=out_nf, n_layers=3,
+                                 batch_size=nb, lr=1e-3, torch_device='cpu', normalization=normalization)
+        torch.manual_seed(seed)
+        host = mine.SizeClassifier(in_node_nf=spec.F, hidden_nf=128, out_node_nf=out_nf, n_layers=3, normalization=normalization)
+        assert list(ref.state_dict().keys()) == list(host.state_dict().keys()), name
+        for k, v in ref.state_dict().items():
+            assert torch.equal(v, host.state_dict()[k]), (name, k)
+        synthetic.init_size_gnn_like_trained(ref, seed)
+        ref.eval()
+        items = synthetic.make_items(spec, batch=nb)
+        data = ns.datasets.collate_with_fragment_edges(items)
+        mydata = mine.collate_with_fragment_edges(items)
+        assert torch.equal(data['edge_mask'], mydata['edge_mask']) and torch.equal(data['edges'][0], mydata['edges'][0]) \
+            and torch.equal(data['edges'][1], mydata['edges'][1]), name
+        with torch.no_grad():
+            out, loss = ref.forward(data, return_loss=False)
+            ora = orc.size_classifier_forward(ref.state_dict(), data, spec.F, 3, normalization)
+        err = (out - ora).abs().max().item()
+        assert err <= 1e-6 * max(1.0, out.abs().max().item()), f"{name}: oracle vs reference {err}"
+        save(name, dict(kind="size_gnn", spec=spec.name, batch=nb, seed=seed, normalization=normalization, out_nf=out_nf,
+                        sha=state_sha(ref.state_dict()), oracle_max_abs_err=err), logits=out)
+
+
 def golden_xyz(ns):
     """visualizer.save_xyz_file (visualizer.py:14-31) run for real into a temp dir; its files pin oracle.xyz_text."""
     import importlib
@@ -298,6 +332,7 @@ def main():
     golden_chain(ns, "chain_cfg1_nsteps20", S["cfg1_plumbing"], 4, seed=0, keep_frames=1, n_steps=20)
     golden_inpaint_chain(ns, "inpaint_chain_cfg1", S["cfg1_plumbing"], 4, seed=0, keep_frames=3)
     golden_xyz(ns)
+    golden_size_classifier(ns)
     print("all oracle / host-mirror checks against the reference passed")
 
 

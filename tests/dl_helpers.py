@@ -71,6 +71,20 @@ def build_ddpm(spec, seed, edge_impl='auto', **over):
     return m, hp
 
 
+def build_size_classifier(meta):
+    """Host-side SizeClassifier with the fixture's weights (same seed and construction order as the reference) and the
+    fixture's batch (collate_with_fragment_edges layout)."""
+    from difflinker_b200 import linker_size
+    spec = spec_by_name(meta["spec"])
+    torch.manual_seed(meta["seed"])
+    model = linker_size.SizeClassifier(in_node_nf=spec.F, hidden_nf=128, out_node_nf=meta["out_nf"], n_layers=3,
+                                       normalization=meta["normalization"])
+    synthetic.init_size_gnn_like_trained(model, meta["seed"])
+    model.eval()
+    data = linker_size.collate_with_fragment_edges(synthetic.make_items(spec, batch=meta["batch"]))
+    return model, data
+
+
 def seeded_noise(seed):
     g = torch.Generator().manual_seed(seed)
     return lambda shape: torch.randn(tuple(shape), generator=g)

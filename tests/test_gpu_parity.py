@@ -434,3 +434,43 @@ def test_restore_frame_vs_oracle():
         assert torch.equal(got[..., 3:], chain0[..., 3:])
         got3 = output.restore_frame(chain0[..., :3].contiguous().to(dev()), positions, com_mask, data['atom_mask']).cpu()
         assert torch.equal(got3, got[..., :3])
+
+
+@pytest.mark.parametrize("name", ["size_gnn_zinc", "size_gnn_zinc_bn"])
+def test_size_classifier_matches_reference_golden(name):
+    """SizeClassifier.forward(return_loss=False) (linker_size_lightning.py:83-110): native logits vs the live reference's
+    (eval-mode batch norm folded on the host in the _bn case); then the sample_fn of generate.py:90-99."""
+    meta, a = helpers.load_golden(name)
+    model, data = helpers.build_size_classifier(meta)
+    d = dev()
+    dd = {k: (v.to(d) if torch.is_tensor(v) else v) for k, v in data.items()}
+    out, loss = model.forward(dd, return_loss=False)
+    assert loss is None and out.shape == a["logits"].shape
+    assert rel_err(out.cpu(), a["logits"]) <= 1e-5
+    out2, loss2 = model.forward(dd, return_loss=True)
+    assert torch.equal(out2, out) and torch.isfinite(loss2)
+    sizes = model.sample_sizes(dd, generator=torch.Generator(device=d).manual_seed(0))
+    assert sizes.dtype == torch.int8 and sizes.shape == (meta["batch"],)
+    assert set(sizes.tolist()) <= set(model.linker_id2size)
+
+
+def test_size_classifier_vs_oracle_ragged_geom_with_pocket_mask():
+    """9 atom types, with_pocket=True (fragment_only_mask selects the atoms), padded rows and isolated fragment atoms."""
+    from difflinker_b200 import linker_size
+    spec = synthetic.SPECS["cfg4_pockets"]
+    small = synthetic.WorkloadSpec(spec.name, B=3, N=70, n_min=70, l_min=5, l_max=5, F=9, L=2, T=10, seed=21, pocket=50,
+                                   graph_type=spec.graph_type)
+    torch.manual_seed(3)
+    model = linker_size.SizeClassifier(in_node_nf=9, out_node_nf=33, n_layers=2, normalization=None,
+                                       linker_size2id=linker_size.GEOM_TRAIN_LINKER_SIZE2ID,
+                                       linker_id2size=linker_size.GEOM_TRAIN_LINKER_ID2SIZE)
+    synthetic.init_size_gnn_like_trained(model, 3)
+    model.eval()
+    data = linker_size.collate_with_fragment_edges(synthetic.make_items(small, batch=3))
+    data['positions'][1, 3] += 40.0                                       # an isolated fragment atom (only its self loop)
+    with torch.no_grad():
+        want = orc.size_classifier_forward(model.state_dict(), data, 9, 2, None, with_pocket=True)
+    d = dev()
+    got, _ = model.forward({k: (v.to(d) if torch.is_tensor(v) else v) for k, v in data.items()}, return_loss=False,
+                           with_pocket=True)
+    assert rel_err(got.cpu(), want) <= 1e-5

@@ -179,3 +179,26 @@ def test_xyz_formatter_edge_cases():
         output.format_xyz(torch.zeros((1, 2, 10)), torch.zeros((1, 2, 3)), torch.ones((1, 2, 1)), True)
     with pytest.raises(RuntimeError):
         output.restore_frame(torch.zeros((1, 2, 3)), torch.zeros((1, 2, 3)), torch.ones((1, 2, 1)), torch.ones((1, 2, 1)))
+
+
+# ------------------------------------------------------------------------------------------------
+# linker-size classifier host mirror (linker_size.py, linker_size_lightning.py)
+# ------------------------------------------------------------------------------------------------
+def test_size_classifier_host_mirror_layout_and_errors():
+    from difflinker_b200 import SizeClassifier, linker_size
+    m = SizeClassifier(in_node_nf=8, out_node_nf=10, n_layers=3, normalization='batch_norm')
+    keys = list(m.state_dict())
+    assert keys[0] == 'gnn.embedding_in.weight' and keys[-1] == 'gnn.embedding_out.bias'
+    assert 'gnn.gcl_layers.1.node_mlp.4.running_var' in keys and 'gnn.gcl1.edge_mlp.2.bias' in keys
+    assert m.state_dict()['gnn.gcl1.edge_mlp.0.weight'].shape == (128, 257)       # [h_i | h_j | radial], linker_size.py:59
+    data = linker_size.collate_with_fragment_edges(synthetic.make_items(synthetic.SPECS["cfg1_plumbing"], batch=3))
+    B, N = data['positions'].shape[:2]
+    em = data['edge_mask'].view(B, N, N)
+    fm = data['fragment_mask'].squeeze(-1)
+    assert set(em.unique().tolist()) <= {0.0, -1.0, -2.0}                           # datasets.py:396-399
+    assert torch.equal(em != 0, (fm[:, :, None] * fm[:, None, :]) != 0)            # fragment pairs, self loops live
+    assert torch.equal(data['edges'][0][:N * N], torch.arange(N).repeat_interleave(N))
+    with pytest.raises(RuntimeError):                                              # no CPU fallback
+        m.eval().forward(data, return_loss=False)
+    assert m.get_true_labels(data['linker_mask']).tolist() == [m.linker_size2id.get(int(v), m.linker_size2id[12])
+                                                               for v in data['linker_mask'].sum((1, 2)).tolist()]
