@@ -4,6 +4,7 @@
 //                      Python loop with one .item() per atom; produces the exact text ("%d\n\n", "%s %.9f %.9f %.9f\n")
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -103,4 +104,55 @@ extern "C" int64_t dl_format_xyz(int32_t B, int32_t N, int32_t F, const float* p
   }
   offsets[B] = pos;
   return pos;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Bond inference: molecule_builder.build_xae_molecule / get_bond_order (src/molecule_builder.py:44-102) for a whole
+// padded batch. E[b][i][j] (i > j, both atoms valid) = bond order 0..3 decided by the pair's distance in pm against the
+// tabulated single / double / triple bond lengths (+ margins) of the type pair ordered by type index
+// (`sorted([atom_types[i], atom_types[j]])`); the upper triangle and masked rows are 0 ("the graph is DIRECTED").
+// thr1/thr2/thr3: (T x T) fp32 thresholds indexed [min type][max type]; a negative entry = pair absent from that table.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_bond_orders(int N, int T, const float* __restrict__ x, int x_stride,
+                                                     const int32_t* __restrict__ types, const int8_t* __restrict__ node_mask,
+                                                     const float* __restrict__ thr1, const float* __restrict__ thr2,
+                                                     const float* __restrict__ thr3, int8_t* __restrict__ E) {
+  const int b = blockIdx.y;
+  const size_t g0 = (size_t)b * N;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < N * N; idx += gridDim.x * blockDim.x) {
+    const int i = idx / N, j = idx - i * N;
+    int8_t order = 0;
+    if (j < i && node_mask[g0 + i] && node_mask[g0 + j]) {
+      const float* xi = x + (g0 + i) * x_stride;
+      const float* xj = x + (g0 + j) * x_stride;
+      const float dx = xi[0] - xj[0], dy = xi[1] - xj[1], dz = xi[2] - xj[2];
+      const float dist = 100.0f * sqrtf(dx * dx + dy * dy + dz * dz);       // "we change the metric" (pm)
+      const int ti = types[g0 + i], tj = types[g0 + j];
+      const int a = min(ti, tj), c = max(ti, tj);
+      if (a >= 0 && c < T) {
+        const float t1 = thr1[a * T + c], t2 = thr2[a * T + c], t3 = thr3[a * T + c];
+        if (t1 >= 0.f && dist < t1) {
+          order = 1;
+          if (t2 >= 0.f && dist < t2) {
+            order = 2;
+            if (t3 >= 0.f && dist < t3) order = 3;
+          }
+        }
+      }
+    }
+    E[g0 * N + idx] = order;
+  }
+}
+}  // namespace
+
+extern "C" dl_status dl_bond_orders(int32_t B, int32_t N, int32_t n_types, const float* x, int32_t x_row_stride,
+                                    const int32_t* atom_types, const int8_t* node_mask, const float* thr1,
+                                    const float* thr2, const float* thr3, int8_t* E, void* stream) {
+  if (B <= 0 || N <= 0 || n_types <= 0 || x_row_stride < 3 || !x || !atom_types || !node_mask || !thr1 || !thr2 || !thr3 || !E)
+    return DL_ERR_INVALID;
+  const dim3 grid((unsigned)std::min(64, (N * N + 255) / 256), (unsigned)B);
+  k_bond_orders<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(N, n_types, x, x_row_stride, atom_types, node_mask,
+                                                                           thr1, thr2, thr3, E);
+  return cudaGetLastError() == cudaSuccess ? DL_OK : DL_ERR_CUDA;
 }

@@ -17,6 +17,7 @@
  *     sample_p_xh_given_z0_only_linker  edm.py:210-235
  *   InpaintingEDM.sample_chain   src/edm.py:549-612      dl_sample_chain with DL_SAMPLER_INPAINT
  *   SizeClassifier.forward       src/linker_size_lightning.py:83-110  dl_sizegnn_create/.../dl_sizegnn_forward
+ *   build_xae_molecule           src/molecule_builder.py:44-102       dl_bond_orders
  *   frame restore + .xyz text    generate.py:163-171, src/visualizer.py:14-31   dl_restore_frame, dl_format_xyz
  *   utils.FoundNaNException      src/utils.py:274-289    DL_NAN_DETECTED + per-molecule nan_flags
  *
@@ -194,6 +195,19 @@ dl_status dl_restore_frame(int32_t B, int32_t N, int32_t row_stride, float* xh, 
 int64_t dl_format_xyz(int32_t B, int32_t N, int32_t F, const float* positions, int32_t pos_row_stride,
                       const float* one_hot, int32_t oh_row_stride, const int8_t* node_mask,
                       const char* const* symbols, int32_t n_symbols, char* out, int64_t out_cap, int64_t* offsets);
+
+/*
+ * dl_bond_orders -- molecule_builder.build_xae_molecule / get_bond_order (src/molecule_builder.py:44-102) for a padded
+ * batch: E[b][i][j] (i > j, both atoms valid) = 0..3 from the pair distance in pm against single / double / triple bond
+ * length thresholds (table value + margin, src/const.py:66-146,180) of the type pair ordered by type index; the upper
+ * triangle and masked rows are 0.  DEVICE buffers, enqueued on `stream`.
+ *   x (B,N,>=3) fp32 with row stride x_row_stride; atom_types (B,N) int32; node_mask (B,N) int8
+ *   thr1/thr2/thr3 (n_types,n_types) fp32 indexed [min type][max type]; negative = pair absent from that table
+ *   E (B,N,N) int8 out
+ */
+dl_status dl_bond_orders(int32_t B, int32_t N, int32_t n_types, const float* x, int32_t x_row_stride,
+                         const int32_t* atom_types, const int8_t* node_mask, const float* thr1, const float* thr2,
+                         const float* thr3, int8_t* E, void* stream);
 
 /*
  * SizeGNN (src/linker_size.py:45-91) as called by SizeClassifier.forward (src/linker_size_lightning.py:83-110): the

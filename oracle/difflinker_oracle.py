@@ -493,6 +493,35 @@ def xyz_text(one_hot, positions, node_mask, idx2atom):
 
 
 # ------------------------------------------------------------------------------------------------
+# bond inference (molecule_builder.py:44-102)
+# ------------------------------------------------------------------------------------------------
+def bond_order(sym1, sym2, distance, single, double, triple, margins):
+    """get_bond_order (molecule_builder.py:77-102); tables keyed by the (sym1, sym2) pair in type-index order."""
+    distance = 100 * distance
+    if (sym1, sym2) not in single:
+        return 0
+    if distance < single[(sym1, sym2)] + margins[0]:
+        if (sym1, sym2) in double and distance < double[(sym1, sym2)] + margins[1]:
+            if (sym1, sym2) in triple and distance < triple[(sym1, sym2)] + margins[2]:
+                return 3
+            return 2
+        return 1
+    return 0
+
+
+def xae_molecule(positions, atom_types, idx2atom, single, double, triple, margins=(10, 5, 2)):
+    """build_xae_molecule (molecule_builder.py:44-74): python pair loop over the lower triangle."""
+    n = positions.shape[0]
+    E = torch.zeros((n, n), dtype=torch.int)
+    dists = torch.cdist(positions.unsqueeze(0), positions.unsqueeze(0), p=2).squeeze(0)
+    for i in range(n):
+        for j in range(i):
+            a, c = sorted([int(atom_types[i]), int(atom_types[j])])
+            E[i, j] = bond_order(idx2atom[a], idx2atom[c], dists[i, j], single, double, triple, margins)
+    return atom_types, E.bool(), E
+
+
+# ------------------------------------------------------------------------------------------------
 # batching contract (datasets.py) -- restated for fixtures; int8 masks incl. the -1/-2 edge mask
 # ------------------------------------------------------------------------------------------------
 PAD_KEYS = ("positions", "one_hot", "charges", "anchors", "fragment_mask", "linker_mask", "pocket_mask",

@@ -267,6 +267,37 @@ def golden_size_classifier(ns):
                         sha=state_sha(ref.state_dict()), oracle_max_abs_err=err), logits=out)
 
 
+def golden_bonds(ns):
+    """molecule_builder.build_xae_molecule of the live reference on chain-like random molecules (bonded distances around
+    1.1-1.6 A so that all of single / double / triple / none occur); pins oracle.xae_molecule and the host tables."""
+    import importlib
+    from difflinker_b200 import molecule_builder as mb
+    ref = importlib.import_module("src.molecule_builder")
+    g = torch.Generator().manual_seed(99)
+    for name, is_geom, T in (("bonds_zinc", False, 8), ("bonds_geom", True, 9)):
+        idx2atom = ns.const.GEOM_IDX2ATOM if is_geom else ns.const.IDX2ATOM
+        mols = []
+        for n in (5, 17, 30, 41):                    # > 25 atoms: torch.cdist switches to the matmul formulation
+            step = torch.randn((n, 3), generator=g)
+            step = step / step.norm(dim=1, keepdim=True) * (1.05 + 0.6 * torch.rand((n, 1), generator=g))
+            pos = torch.cumsum(step, dim=0)
+            types = torch.randint(0, T, (n,), generator=g)
+            types[torch.rand((n,), generator=g) < 0.5] = 0                   # mostly carbon
+            X, A, E = ref.build_xae_molecule(pos, types, is_geom=is_geom)
+            oX, oA, oE = orc.xae_molecule(pos, types, idx2atom, mb.SINGLE, mb.DOUBLE, mb.TRIPLE, mb.MARGINS_EDM)
+            assert torch.equal(E, oE) and torch.equal(A, oA), name
+            mols.append((pos, types, E))
+        N = max(m[0].shape[0] for m in mols)
+        P = torch.zeros((len(mols), N, 3)); Ty = torch.zeros((len(mols), N), dtype=torch.long)
+        M = torch.zeros((len(mols), N), dtype=torch.int8); Eb = torch.zeros((len(mols), N, N), dtype=torch.int8)
+        for b, (pos, types, E) in enumerate(mols):
+            n = pos.shape[0]
+            P[b, :n] = pos; Ty[b, :n] = types; M[b, :n] = 1; Eb[b, :n, :n] = E.to(torch.int8)
+        counts = [int((Eb == k).sum()) for k in range(4)]
+        assert min(counts[1:]) > 0, counts
+        save(name, dict(kind="bonds", is_geom=is_geom, counts=counts), positions=P, types=Ty, node_mask=M, E=Eb)
+
+
 def golden_xyz(ns):
     """visualizer.save_xyz_file (visualizer.py:14-31) run for real into a temp dir; its files pin oracle.xyz_text."""
     import importlib
@@ -332,6 +363,7 @@ def main():
     golden_chain(ns, "chain_cfg1_nsteps20", S["cfg1_plumbing"], 4, seed=0, keep_frames=1, n_steps=20)
     golden_inpaint_chain(ns, "inpaint_chain_cfg1", S["cfg1_plumbing"], 4, seed=0, keep_frames=3)
     golden_xyz(ns)
+    golden_bonds(ns)
     golden_size_classifier(ns)
     print("all oracle / host-mirror checks against the reference passed")
 

@@ -474,3 +474,22 @@ def test_size_classifier_vs_oracle_ragged_geom_with_pocket_mask():
     got, _ = model.forward({k: (v.to(d) if torch.is_tensor(v) else v) for k, v in data.items()}, return_loss=False,
                            with_pocket=True)
     assert rel_err(got.cpu(), want) <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["bonds_zinc", "bonds_geom"])
+def test_bond_orders_match_reference_golden(name):
+    """build_xae_molecule (molecule_builder.py:44-74) batched: integer output, bit-exact against the live reference's E for
+    every molecule of the fixture (incl. n > 25 where torch.cdist uses its matmul formulation), padding rows all zero."""
+    from difflinker_b200 import molecule_builder as mb
+    meta, a = helpers.load_golden(name)
+    d = dev()
+    T = 9 if meta["is_geom"] else 8
+    one_hot = torch.nn.functional.one_hot(a["types"], T).float()
+    E = mb.bond_orders(one_hot.to(d), a["positions"].to(d), a["node_mask"].to(d), meta["is_geom"]).cpu()
+    assert E.dtype == torch.int8 and torch.equal(E, a["E"])
+    # chain[0]-style strided input and the single-molecule reference signature
+    xh = torch.cat([a["positions"], one_hot], dim=2)
+    assert torch.equal(mb.bond_orders(one_hot.to(d), xh.to(d), a["node_mask"].to(d), meta["is_geom"]).cpu(), a["E"])
+    n = int(a["node_mask"][1].sum())
+    X, A, E1 = mb.build_xae_molecule(a["positions"][1, :n].to(d), a["types"][1, :n].to(d), meta["is_geom"])
+    assert torch.equal(E1.cpu().to(torch.int8), a["E"][1, :n, :n]) and torch.equal(A.cpu(), a["E"][1, :n, :n] != 0)

@@ -80,6 +80,24 @@ def test_oracle_size_classifier_matches_reference_golden(name):
     assert (out - a["logits"]).abs().max().item() <= 2e-6 * max(1.0, a["logits"].abs().max().item())
 
 
+@pytest.mark.parametrize("name", ["bonds_zinc", "bonds_geom"])
+def test_oracle_bond_orders_match_reference_golden(name):
+    from difflinker_b200 import molecule_builder as mb, output
+    meta, a = helpers.load_golden(name)
+    idx2atom = output.GEOM_IDX2ATOM if meta["is_geom"] else output.IDX2ATOM
+    for b in range(a["positions"].shape[0]):
+        n = int(a["node_mask"][b].sum())
+        _, A, E = orc.xae_molecule(a["positions"][b, :n], a["types"][b, :n], idx2atom, mb.SINGLE, mb.DOUBLE, mb.TRIPLE,
+                                   mb.MARGINS_EDM)
+        assert torch.equal(E.to(torch.int8), a["E"][b, :n, :n]) and torch.equal(A, E.bool())
+    # host threshold tables: [min type][max type], -1 where the reference's dictionaries have no entry
+    t1, t2, t3 = mb.threshold_tables(meta["is_geom"])
+    assert t1[0, 0] == 164 and t2[0, 0] == 139 and t3[0, 0] == 122          # C-C: 154+10, 134+5, 120+2
+    assert t1[5, 7] == -1 and t1[6, 7] == -1                                 # Cl-I, Br-I: no typical bond length
+    lower = torch.tril(torch.ones_like(t1), -1).bool()
+    assert (t1[lower] == -1).all()                                           # only the index-ordered direction is ever read
+
+
 def test_gamma_tables_match_reference_golden():
     _, a = helpers.load_golden("gamma_tables")
     for key, ref in a.items():
