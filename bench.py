@@ -319,8 +319,14 @@ def main():
     roofline = None
     if ms_gcl and ms_gcl > 0:
         ach = edge_flops / (ms_gcl * 1e-3) / 1e12
+        traffic = None                                                  # DRAM bytes per launch from the committed ncu capture
+        try:
+            with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")) as f:
+                traffic = json.load(f).get(spec.name, {}).get("edge_gcl")
+        except OSError:
+            pass
         roofline = {"bound": "tensor", "kernel": "edge_gcl", "achieved": ach, "peak": peaks["bf16_tflops"],
-                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"], "traffic": traffic,
                     "peak_source": peaks["source"], "kernel_ms": ms_gcl,
                     "kernel_share_of_step": ms_gcl * spec.L * spec.S / fwd_ms}
     forward = {"ms": fwd_ms, "flops_alg": flops_fwd, "bytes_alg": bytes_fwd,

@@ -19,4 +19,5 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k
 # one full capture of the GCL edge kernel (and the node kernel next to it)
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"k_edge_tc|k_node_tc" -s 40 -c 3 \
   -o $O/edge_node_full python bench.py --steps 1 --warmup 1 --T 4 --no-e2e --no-cpu-baseline > $O/ncu_full.log 2>&1
+timeout 400 python bench.py --impl reference --steps 1 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err
 ls -la $O
