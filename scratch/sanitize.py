@@ -8,25 +8,26 @@ from difflinker_b200 import synthetic, linker_size, molecule_builder, output
 from difflinker_b200.batching import collate
 
 d = torch.device('cuda:0')
+IMPL = os.environ.get('DL_SAN_IMPL', 'auto')      # racecheck run: 'simt' keeps the mbarrier/TMA kernels out of the tool's way
 mv = lambda t: t.to(d) if torch.is_tensor(t) else t
 
 # FC forward + short linker chain (tcgen05 path), ragged masks
 spec = synthetic.WorkloadSpec("san_fc", B=3, N=23, n_min=11, l_min=2, l_max=6, F=8, L=2, T=4, seed=31)
-ddpm, hp = helpers.build_ddpm(spec, 0)
+ddpm, hp = helpers.build_ddpm(spec, 0, edge_impl=IMPL)
 ddpm = ddpm.to(d)
 data = {k: mv(v) for k, v in collate(synthetic.make_items(spec)).items()}
 chain, nm = ddpm.sample_chain(data, keep_frames=2)
 print("fc chain", tuple(chain.shape), bool(torch.isfinite(chain).all()))
 
 # inpainting chain
-ddpm_i, _ = helpers.build_ddpm(spec, 0, inpainting=True)
+ddpm_i, _ = helpers.build_ddpm(spec, 0, edge_impl=IMPL, inpainting=True)
 ddpm_i = ddpm_i.to(d)
 chain, nm = ddpm_i.sample_chain(data, keep_frames=1)
 print("inpaint chain", tuple(chain.shape), bool(torch.isfinite(chain).all()))
 
 # N > 64: column-split epilogue, chunked rows
 spec2 = synthetic.WorkloadSpec("san_big", B=2, N=150, n_min=150, l_min=8, l_max=8, F=8, L=1, T=2, seed=32)
-dyn, _ = helpers.build_dynamics(spec2, 0)
+dyn, _ = helpers.build_dynamics(spec2, 0, edge_impl=IMPL)
 b2 = collate(synthetic.make_items(spec2))
 z, t = helpers.random_latent(b2, 3)
 out = dyn(mv(t), mv(z), mv(b2['atom_mask']), mv(b2['linker_mask']), mv(b2['edge_mask']), mv(b2['fragment_mask']))
