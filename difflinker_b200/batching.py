@@ -28,12 +28,12 @@ def _stack_and_pad(batch):
     return out
 
 
-def collate(batch):
-    out = _stack_and_pad(batch)
+def _add_masks(out, pocket):
+    """atom_mask, edge_mask and the trailing singleton dims (datasets.py:353-375)."""
     atom_mask = (out["fragment_mask"].bool() | out["linker_mask"].bool()).to(TORCH_INT)
     out["atom_mask"] = atom_mask[:, :, None]
     bs, n = atom_mask.shape
-    if "pocket_mask" in batch[0]:
+    if pocket:
         # pocket models: `edge_mask` carries the molecule index of every node (int8!) instead of a mask
         out["edge_mask"] = torch.arange(bs, dtype=torch.int64, device=atom_mask.device).repeat_interleave(n).to(TORCH_INT)
     else:
@@ -46,9 +46,47 @@ def collate(batch):
     return out
 
 
+def collate(batch):
+    return _add_masks(_stack_and_pad(batch), "pocket_mask" in batch[0])
+
+
 def create_templates_for_linker_generation(data, linker_sizes):
-    """Keep the fragment rows of every padded attribute and append `linker_size` template rows
-    (ones for linker_mask, zeros elsewhere), then re-collate."""
+    """Keep the fragment rows of every padded attribute and append `linker_size` template rows (ones for linker_mask,
+    zeros elsewhere), then re-collate (datasets.py:483-512). Batched: the reference decouples the batch into one dict per
+    molecule and collates again (a few thousand tiny ops per call on the GPU); the same tensors come out of a handful of
+    masked selects on the padded batch -- one host sync for the new padded length."""
+    fm = data["fragment_mask"]
+    dev = fm.device
+    bs, n_old = fm.shape[0], fm.shape[1]
+    n_frag = fm.reshape(bs, n_old).sum(1).long()                       # fragment atoms come first (datasets.py:493-494)
+    sizes = torch.as_tensor(linker_sizes, device=dev).reshape(-1).long()
+    n_tot = n_frag + sizes
+    n_new = int(n_tot.max())
+    idx = torch.arange(n_new, device=dev)[None, :]
+    is_frag = (idx < n_frag[:, None])[:, :, None]
+    is_link = ((idx >= n_frag[:, None]) & (idx < n_tot[:, None]))[:, :, None]
+    out = {}
+    for key, value in data.items():
+        if key == "num_atoms":
+            out[key] = n_tot.tolist()
+        elif key in DATA_LIST_ATTRS:
+            out[key] = list(value)
+        elif key in DATA_ATTRS_TO_PAD:
+            v = value if value.dim() == 3 else value[:, :, None]
+            if n_new <= n_old:
+                v = v[:, :n_new]
+            else:
+                v = torch.cat([v, torch.zeros((bs, n_new - n_old, v.shape[2]), dtype=v.dtype, device=dev)], dim=1)
+            v = torch.where(is_frag, v, torch.zeros((), dtype=v.dtype, device=dev))
+            if key == "linker_mask":
+                v = torch.where(is_link, torch.ones((), dtype=v.dtype, device=dev), v)
+            out[key] = v.squeeze(-1) if key in DATA_ATTRS_TO_ADD_LAST_DIM else v
+    return _add_masks(out, "pocket_mask" in data)
+
+
+def _create_templates_per_molecule(data, linker_sizes):
+    """The reference's own formulation (decouple -> per-molecule template -> collate); kept as the cross-check of the batched
+    version above (tests/test_host_logic.py)."""
     singles = []
     for i, linker_size in enumerate(linker_sizes):
         linker_size = int(linker_size)

@@ -393,10 +393,6 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   return DL_OK;
 }
 
-int launches_per_forward(const dl_engine* e) {
-  return 2 + e->cfg.n_layers * (2 * e->cfg.inv_sublayers + 2) + (e->use_tc && e->cfg.graph_type != 0 ? 1 : 0);
-}
-
 dl_status check_shapes(const dl_engine* e, int B, int N) {
   if (!e || !e->finalized) { set_err("engine not finalized (dl_finalize_weights)"); return DL_ERR_INVALID; }
   if (B <= 0 || N <= 0) { set_err("B and N must be positive (got %d, %d)", B, N); return DL_ERR_INVALID; }

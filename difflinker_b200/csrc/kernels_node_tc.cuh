@@ -95,7 +95,6 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   uint8_t* xa_hi = sm + N_OFF_XA; uint8_t* xa_lo = xa_hi + X_BYTES;
   uint8_t* xb_hi = sm + N_OFF_XB; uint8_t* xb_lo = xb_hi + X_BYTES;
   float* nms = reinterpret_cast<float*>(sm + N_OFF_MISC);
-  int* nodemax = reinterpret_cast<int*>(sm + N_OFF_MISC + 512);      // [2][128] per-node |.| maxima as int bits
   int* tilemax = reinterpret_cast<int*>(sm + N_OFF_MISC + 512 * 3);
 
   if (tid == 0) {

@@ -202,3 +202,25 @@ def test_size_classifier_host_mirror_layout_and_errors():
         m.eval().forward(data, return_loss=False)
     assert m.get_true_labels(data['linker_mask']).tolist() == [m.linker_size2id.get(int(v), m.linker_size2id[12])
                                                                for v in data['linker_mask'].sum((1, 2)).tolist()]
+
+
+@pytest.mark.parametrize("spec_name,nb", [("cfg1_plumbing", 4), ("cfg2_zinc_ragged", 9), ("cfg4_pockets", 2)])
+def test_batched_template_creation_equals_per_molecule_formulation(spec_name, nb):
+    """datasets.create_templates_for_linker_generation (483-512): the batched masked-select version must reproduce the
+    decouple-and-recollate formulation key by key (order, dtype, shape, values) for shrinking, growing and zero linkers."""
+    from difflinker_b200 import batching
+    spec = synthetic.SPECS[spec_name]
+    data = batching.collate(synthetic.make_items(spec, batch=nb))
+    g = torch.Generator().manual_seed(nb)
+    for trial in range(3):
+        sizes = torch.randint(0, 15, (nb,), generator=g).to(torch.int8)
+        if trial == 2:
+            sizes = data['linker_mask'].sum(1).view(-1).int()               # what DDPM.sample_chain passes by default
+        a = batching.create_templates_for_linker_generation(data, sizes)
+        b = batching._create_templates_per_molecule(data, sizes)
+        assert list(a.keys()) == list(b.keys())
+        for k in a:
+            if torch.is_tensor(a[k]):
+                assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
+            else:
+                assert a[k] == b[k], k
