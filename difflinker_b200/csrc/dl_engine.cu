@@ -270,13 +270,27 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   pa.node_mask = io.node_mask; pa.linker_mask = io.linker_mask;
   pa.t = io.t; pa.t_numel = io.t_numel; pa.context = io.context;
   pa.We_t = e->We_t; pa.be = e->be; pa.proj = proj_of(e->gcl[0]);
-  pa.nm = ws.nm; pa.x0 = ws.x0; pa.x = ws.xa; pa.x04 = e->use_tc ? ws.x04 : nullptr; pa.x4 = e->use_tc ? ws.xa4 : nullptr; pa.cls = ws.cls; pa.h = ws.h; pa.AB = ws.ABg; pa.ABmax = ws.ABgmax;
+  pa.nm = ws.nm; pa.x0 = ws.x0; pa.x = ws.xa; pa.x04 = e->use_tc ? ws.x04 : nullptr; pa.x4 = e->use_tc ? ws.xa4 : nullptr; pa.cls = ws.cls; pa.h = ws.h;
+  pa.AB = e->use_tc ? nullptr : ws.ABg; pa.ABmax = ws.ABgmax;
   pa.coef = io.sampler ? e->coef_dev : nullptr;
   pa.step_prep = io.sampler ? e->step_ctr : nullptr;
   pa.step_fin = io.sampler ? e->step_ctr + 1 : nullptr;
   k_prep<<<node_blocks, 256, 0, st>>>(gm, pa);
   LAUNCH_CHECK();
   e->launches += 1;
+  if (e->use_tc) {
+    // A | B projections of block 0 / gcl 0 from the embedded h, on the tensor cores
+    const GclW& w0 = e->gcl[0];
+    tcn::NodeTcArgs ta{};
+    ta.h = ws.h; ta.agg = ws.h; ta.nm = ws.nm; ta.proj_only = 1;
+    ta.w3 = reinterpret_cast<const __half*>(w0.W3_tc); ta.w4 = reinterpret_cast<const __half*>(w0.W4_tc);
+    ta.b3 = w0.b3; ta.b4 = w0.b4; ta.w3_descale = 1.f; ta.w4_descale = 1.f;
+    ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(w0.W1_tc); ta.pb1[0] = w0.b1;
+    ta.p_descale[0] = w0.w1_descale; ta.AB[0] = ws.ABg; ta.ABmax[0] = ws.ABgmax;
+    tcn::k_node_tc<<<(n + tcn::TM - 1) / tcn::TM, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
+    LAUNCH_CHECK();
+    e->launches += 1;
+  }
 
   if (ws.nbr != nullptr) {
     // the cut-off graph of this call (a function of its input coordinates): neighbour lists + packed tiles

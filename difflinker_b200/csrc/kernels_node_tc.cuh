@@ -51,6 +51,7 @@ struct NodeTcArgs {
   const __half* w4;      // 1 packed block
   const float *b3, *b4;
   float w3_descale, w4_descale;
+  int proj_only;         // 1: skip the node MLP -- h is only projected (first layer of a forward: replaces the SIMT projection of k_prep)
   int n_proj;            // 1 or 2
   const __half* pw[2];   // 2 packed blocks each (W1a, W1b), common scale
   const float* pb1[2];
@@ -110,7 +111,8 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  const int n_blocks = 3 + 2 * a.n_proj;          // 128x128 weight blocks consumed by this tile, in order
+  const int blk0 = a.proj_only ? 3 : 0;           // proj_only: the W3 / W4 blocks are not streamed
+  const int n_blocks = 3 + 2 * a.n_proj - blk0;   // 128x128 weight blocks consumed by this tile, in order
   const int n_half = 2 * n_blocks;
 
   // ---- weight loader: a dedicated warp streams the half-blocks through the ring; it never joins the workers'
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   if (warp == NW) {
     if (lane == 0) {
       for (int i = 0; i < n_half; ++i) {
-        const int s = i % N_RING, blk = i >> 1, hf = i & 1;
+        const int s = i % N_RING, blk = (i >> 1) + blk0, hf = i & 1;
         if (i >= N_RING) mbar_wait(bar_empty + 8 * s, ((i - N_RING) / N_RING) & 1);
         const __half* base = blk < 2 ? a.w3 + (size_t)blk * (BLOCK_BYTES / 2)
                              : blk == 2 ? a.w4
@@ -150,7 +152,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
         hv[j] = make_float4(0, 0, 0, 0); av[j] = hv[j];
         if (r < n_live) {
           hv[j] = *reinterpret_cast<const float4*>(a.h + (size_t)(g0 + r) * H + lane * 4);
-          av[j] = __ldg(reinterpret_cast<const float4*>(a.agg + (size_t)(g0 + r) * H + lane * 4));
+          if (!a.proj_only) av[j] = __ldg(reinterpret_cast<const float4*>(a.agg + (size_t)(g0 + r) * H + lane * 4));
         }
       }
 #pragma unroll
@@ -211,100 +213,103 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     umma_commit(bar_acc + 8 * acc_bar);
   };
 
-  // ---- G1: W3 [h, agg]^T -> accumulator 0 ---------------------------------------------------------------------------
-  if (tid == 0) {
-    const uint8_t* xs[4] = {xa_hi, xa_hi, xb_hi, xb_hi};
-    issue(0, 4, xs, 0, 0);
-  }
-  mbar_wait(bar_acc, 0);
-  tc_fence_after();
-  mark(1);   // G1 accumulator ready
-  float s2;
-  {
-    const float ds = a.w3_descale / s1;
-    const float bias = __ldg(a.b3 + c);
-    auto epi1 = [&](float scale) -> float {           // hid = silu(D*ds + b3) -> XB (agg operand is dead: G1 is complete)
+  float s3 = s1;
+  if (!a.proj_only) {
+    // ---- G1: W3 [h, agg]^T -> accumulator 0 ---------------------------------------------------------------------------
+    if (tid == 0) {
+      const uint8_t* xs[4] = {xa_hi, xa_hi, xb_hi, xb_hi};
+      issue(0, 4, xs, 0, 0);
+    }
+    mbar_wait(bar_acc, 0);
+    tc_fence_after();
+    mark(1);   // G1 accumulator ready
+    float s2;
+    {
+      const float ds = a.w3_descale / s1;
+      const float bias = __ldg(a.b3 + c);
+      auto epi1 = [&](float scale) -> float {           // hid = silu(D*ds + b3) -> XB (agg operand is dead: G1 is complete)
+        float mx = 0.f;
+        uint32_t r[2][16];
+        TMEM_LD_X16(trow, r[0]);
+  #pragma unroll
+        for (int k = 0; k < CW / 16; ++k) {
+          tmem_ld_wait();
+          if (k + 1 < CW / 16) TMEM_LD_X16(trow + (k + 1) * 16, r[(k + 1) & 1]);
+  #pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const float v = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
+            mx = fmaxf(mx, fabsf(v));                    // |silu(v)| <= |v|
+            store_elem(xb_hi, xb_lo, c, ncol0 + k * 16 + u, silu_f(v) * scale);
+          }
+        }
+        return mx;
+      };
+      s2 = pow2_scale_for(tile_max(epi1(1.0f)));
+      if (s2 != 1.0f) epi1(s2);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    workers_sync();
+    mark(2);   // epilogue 1 done
+
+    // ---- G2: W4 hid^T -> accumulator 1; residual, mask ------------------------------------------------------------------------
+    if (tid == 0) {
+      const uint8_t* xs[2] = {xb_hi, xb_hi};
+      issue(4, 2, xs, 128, 1);
+    }
+    mbar_wait(bar_acc + 8, 0);
+    tc_fence_after();
+    mark(3);   // G2 accumulator ready
+    {
+      const float ds = a.w4_descale / s2;
+      const float bias = __ldg(a.b4 + c);
+      float* hcol = a.h + (size_t)g0 * H + c;            // h[(g0+n)*128 + c]: a warp covers 128 contiguous bytes per node
       float mx = 0.f;
       uint32_t r[2][16];
-      TMEM_LD_X16(trow, r[0]);
-#pragma unroll
+      float hv[2][16];
+  #pragma unroll
+      for (int u = 0; u < 16; ++u) hv[0][u] = (ncol0 + u < n_live) ? hcol[(size_t)(ncol0 + u) * H] : 0.f;
+      TMEM_LD_X16(trow + 128, r[0]);
+  #pragma unroll
       for (int k = 0; k < CW / 16; ++k) {
         tmem_ld_wait();
-        if (k + 1 < CW / 16) TMEM_LD_X16(trow + (k + 1) * 16, r[(k + 1) & 1]);
-#pragma unroll
+        if (k + 1 < CW / 16) {
+          TMEM_LD_X16(trow + 128 + (k + 1) * 16, r[(k + 1) & 1]);
+  #pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            const int nn = ncol0 + (k + 1) * 16 + u;
+            hv[(k + 1) & 1][u] = (nn < n_live) ? hcol[(size_t)nn * H] : 0.f;
+          }
+        }
+  #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const float v = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
-          mx = fmaxf(mx, fabsf(v));                    // |silu(v)| <= |v|
-          store_elem(xb_hi, xb_lo, c, ncol0 + k * 16 + u, silu_f(v) * scale);
+          const int n = ncol0 + k * 16 + u;
+          const float o = (hv[k & 1][u] + fmaf(__uint_as_float(r[k & 1][u]), ds, bias)) * nms[n];     // egnn.py:71,78-79
+          if (n < n_live) hcol[(size_t)n * H] = o;
+          mx = fmaxf(mx, fabsf(o));
+          store_elem(xa_hi, xa_lo, c, n, o);
         }
       }
-      return mx;
-    };
-    s2 = pow2_scale_for(tile_max(epi1(1.0f)));
-    if (s2 != 1.0f) epi1(s2);
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  workers_sync();
-  mark(2);   // epilogue 1 done
-
-  // ---- G2: W4 hid^T -> accumulator 1; residual, mask ------------------------------------------------------------------------
-  if (tid == 0) {
-    const uint8_t* xs[2] = {xb_hi, xb_hi};
-    issue(4, 2, xs, 128, 1);
-  }
-  mbar_wait(bar_acc + 8, 0);
-  tc_fence_after();
-  mark(3);   // G2 accumulator ready
-  float s3;
-  {
-    const float ds = a.w4_descale / s2;
-    const float bias = __ldg(a.b4 + c);
-    float* hcol = a.h + (size_t)g0 * H + c;            // h[(g0+n)*128 + c]: a warp covers 128 contiguous bytes per node
-    float mx = 0.f;
-    uint32_t r[2][16];
-    float hv[2][16];
-#pragma unroll
-    for (int u = 0; u < 16; ++u) hv[0][u] = (ncol0 + u < n_live) ? hcol[(size_t)(ncol0 + u) * H] : 0.f;
-    TMEM_LD_X16(trow + 128, r[0]);
-#pragma unroll
-    for (int k = 0; k < CW / 16; ++k) {
-      tmem_ld_wait();
-      if (k + 1 < CW / 16) {
-        TMEM_LD_X16(trow + 128 + (k + 1) * 16, r[(k + 1) & 1]);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int nn = ncol0 + (k + 1) * 16 + u;
-          hv[(k + 1) & 1][u] = (nn < n_live) ? hcol[(size_t)nn * H] : 0.f;
-        }
-      }
-#pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        const int n = ncol0 + k * 16 + u;
-        const float o = (hv[k & 1][u] + fmaf(__uint_as_float(r[k & 1][u]), ds, bias)) * nms[n];     // egnn.py:71,78-79
-        if (n < n_live) hcol[(size_t)n * H] = o;
-        mx = fmaxf(mx, fabsf(o));
-        store_elem(xa_hi, xa_lo, c, n, o);
+      s3 = pow2_scale_for(tile_max(mx));
+      if (s3 != 1.0f) {                                  // rare: rewrite h' scaled (own global writes, program order)
+        for (int n = ncol0; n < ncol0 + CW; ++n) store_elem(xa_hi, xa_lo, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
       }
     }
-    s3 = pow2_scale_for(tile_max(mx));
-    if (s3 != 1.0f) {                                  // rare: rewrite h' scaled (own global writes, program order)
-      for (int n = ncol0; n < ncol0 + CW; ++n) store_elem(xa_hi, xa_lo, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
-    }
+    fence_proxy_async();
+    tc_fence_before();
+    workers_sync();
+    mark(4);   // epilogue 2 done (h' stored, operand rewritten)
   }
-  fence_proxy_async();
-  tc_fence_before();
-  workers_sync();
-  mark(4);   // epilogue 2 done (h' stored, operand rewritten)
 
   // ---- projections: A -> accumulator 2, B -> accumulator 3 (second consumer reuses 0 / 1) --------------------------------
   if (tid == 0) {
     const uint8_t* xs[2] = {xa_hi, xa_hi};
-    issue(6, 2, xs, 256, 2);
-    issue(8, 2, xs, 384, 3);
+    const int r0 = 2 * (3 - blk0);                   // ring position of the first projection half-block
+    issue(r0, 2, xs, 256, 2);
+    issue(r0 + 2, 2, xs, 384, 3);
     if (a.n_proj > 1) {
-      issue(10, 2, xs, 0, 0);
-      issue(12, 2, xs, 128, 1);
+      issue(r0 + 4, 2, xs, 0, 0);
+      issue(r0 + 6, 2, xs, 128, 1);
     }
   }
   for (int p = 0; p < a.n_proj; ++p) {
@@ -312,7 +317,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
 #pragma unroll 1
     for (int part = 0; part < 2; ++part) {
       const int accn = p == 0 ? 2 + part : part;
-      mbar_wait(bar_acc + 8 * accn, p == 0 ? 0 : 1);
+      mbar_wait(bar_acc + 8 * accn, (p == 0 || a.proj_only) ? 0 : 1);   // accumulators 0/1 were used by G1/G2 before
       tc_fence_after();
       const float bias = part == 0 ? __ldg(a.pb1[p] + c) : 0.f;
       float* abcol = a.AB[p] + (size_t)g0 * 2 * H + part * H + c;

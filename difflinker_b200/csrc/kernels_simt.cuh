@@ -280,7 +280,8 @@ __global__ void __launch_bounds__(256) k_prep(Geom gm, PrepArgs a) {
     }
   }
   __syncwarp();
-  project_ab(hs + warp * 4 * LDX, a.proj, a.AB, a.ABmax, g0, n_total, warp, lane);
+  // tcgen05 path: the projection of the first edge MLP runs on the tensor cores right after (k_node_tc, proj_only)
+  if (a.AB != nullptr) project_ab(hs + warp * 4 * LDX, a.proj, a.AB, a.ABmax, g0, n_total, warp, lane);
 }
 
 // GCL.node_model + node_mask (egnn.py:62-80), then the first-layer projections of whatever edge MLP
