@@ -493,3 +493,16 @@ def test_bond_orders_match_reference_golden(name):
     n = int(a["node_mask"][1].sum())
     X, A, E1 = mb.build_xae_molecule(a["positions"][1, :n].to(d), a["types"][1, :n].to(d), meta["is_geom"])
     assert torch.equal(E1.cpu().to(torch.int8), a["E"][1, :n, :n]) and torch.equal(A.cpu(), a["E"][1, :n, :n] != 0)
+
+
+def test_draw_noise_on_cuda_equals_the_reference_call_sequence():
+    """The sampler's own noise on the GPU is the reference's torch.randn call sequence (same seed -> same CUDA stream)."""
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    ddpm, hp = helpers.build_ddpm(spec, 0)
+    d = dev()
+    g = torch.Generator(device=d).manual_seed(77)
+    got = ddpm.edm.draw_noise(5, 4, 30, d, generator=g)
+    g2 = torch.Generator(device=d).manual_seed(77)
+    for r in range(5):
+        assert torch.equal(got[r, :, :, :3], torch.randn((4, 30, 3), device=d, generator=g2))
+        assert torch.equal(got[r, :, :, 3:], torch.randn((4, 30, spec.F), device=d, generator=g2))

@@ -224,3 +224,12 @@ def test_batched_template_creation_equals_per_molecule_formulation(spec_name, nb
                 assert a[k].dtype == b[k].dtype and a[k].shape == b[k].shape and torch.equal(a[k], b[k]), k
             else:
                 assert a[k] == b[k], k
+
+
+def test_draw_noise_follows_the_reference_call_order():
+    """edm.py:328-340 / utils.py:189-192: per draw randn(B,N,3) then randn(B,N,F); same seed -> same stream."""
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    ddpm, hp = helpers.build_ddpm(spec, 0)
+    g = torch.Generator().manual_seed(1000)
+    got = ddpm.edm.draw_noise(7, 4, 30, torch.device('cpu'), generator=g)
+    assert torch.equal(got, helpers.noise_tensor(1000, 5, 4, 30, spec.F))
