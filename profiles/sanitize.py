@@ -1,6 +1,6 @@
-"""compute-sanitizer target: one small call of every native entry point (run: compute-sanitizer --tool memcheck python scratch/sanitize.py)."""
+"""compute-sanitizer target: one small call of every native entry point (run: compute-sanitizer --tool memcheck python profiles/sanitize.py)."""
 import os, sys
-ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')
+ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), '..')  # repo root
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
 import dl_helpers as helpers
