@@ -47,6 +47,7 @@ SYMBOLS = {
     "dl_last_elapsed_ms": (_F, [_P]),
     "dl_time_edge_kernel": (_F, [_P, _I32]),
     "dl_selftest_tc": (_I32, [_P, C.POINTER(_F), C.POINTER(_F)]),
+    "dl_selftest_tc_layout": (_I32, [_P, _I32, C.POINTER(_F), C.POINTER(_F)]),
     "dl_cut_graph_stats": (_I32, [_P, C.POINTER(_I64)]),
     "dl_sizegnn_create": (_I32, [C.POINTER(DLSizeGNNConfig), C.POINTER(_P)]),
     "dl_sizegnn_destroy": (_I32, [_P]),

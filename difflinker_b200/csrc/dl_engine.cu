@@ -872,7 +872,13 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
 dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err) {
   if (!e) { set_err("null engine"); return DL_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device));
-  return tc::selftest(e->num_sms, max_abs_err, max_rel_err);
+  return tc::selftest(e->num_sms, max_abs_err, max_rel_err, false);
+}
+
+dl_status dl_selftest_tc_layout(dl_engine* e, int32_t b_mn_major, float* max_abs_err, float* max_rel_err) {
+  if (!e) { set_err("null engine"); return DL_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device));
+  return tc::selftest(e->num_sms, max_abs_err, max_rel_err, b_mn_major != 0);
 }
 
 }  // extern "C"

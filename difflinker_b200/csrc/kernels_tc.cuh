@@ -867,6 +867,10 @@ constexpr int PN = 256;                          // probe: B operand rows (UMMA 
 constexpr int P_LBO = PN * 16 + 16;
 constexpr int P_OFF_BHI = 2 * W_BYTES, P_OFF_BLO = P_OFF_BHI + KC * P_LBO, P_OFF_BAR = P_OFF_BLO + KC * P_LBO;
 constexpr int P_SMEM_BYTES = P_OFF_BAR + 64 + 1024;
+// B_MN = true: the B operand is laid out MN-major (canonical no-swizzle form ((8,n),(8,k)):((1,SBO),(8,LBO)) in halves: 8
+// consecutive N-rows of one k are contiguous 16 bytes; b_major bit of the instruction descriptor set) -- the layout a
+// lane = channel producer could fill with 16-byte stores (DESIGN.md, next-round analysis).
+template <bool B_MN>
 __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict__ A /*[2][kc][128][8]*/,
                                                        const __half* __restrict__ Bm /*[2][kc][256][8]*/,
                                                        float* __restrict__ D /*[128][256]*/) {
@@ -884,10 +888,17 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
     *reinterpret_cast<uint4*>(sm + (copy ? OFF_WLO : OFF_WHI) + kcx * W_LBO + row * 16) =
         *reinterpret_cast<const uint4*>(A + (size_t)idx * 8);
   }
+  constexpr int MN_LBO = (PN / 8) * 128;             // MN-major: pitch between 8-wide K groups; SBO = 128 B between 8-row N groups
   for (int idx = tid; idx < 2 * KC * PN; idx += 128) {
     const int copy = idx / (KC * PN), rem = idx % (KC * PN), kcx = rem / PN, row = rem % PN;
-    *reinterpret_cast<uint4*>(sm + (copy ? P_OFF_BLO : P_OFF_BHI) + kcx * P_LBO + row * 16) =
-        *reinterpret_cast<const uint4*>(Bm + (size_t)idx * 8);
+    if (!B_MN) {
+      *reinterpret_cast<uint4*>(sm + (copy ? P_OFF_BLO : P_OFF_BHI) + kcx * P_LBO + row * 16) =
+          *reinterpret_cast<const uint4*>(Bm + (size_t)idx * 8);
+    } else {
+      for (int u = 0; u < 8; ++u)                      // element (n = row, k = kcx*8 + u)
+        *reinterpret_cast<__half*>(sm + (copy ? P_OFF_BLO : P_OFF_BHI) + kcx * MN_LBO + (row >> 3) * 128 + u * 16 + (row & 7) * 2) =
+            Bm[(size_t)idx * 8 + u];
+    }
   }
   fence_proxy_async();
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
@@ -896,10 +907,11 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   if (tid == 0) {
-    const uint32_t idesc = umma_idesc(128, 256);
+    const uint32_t idesc = umma_idesc(128, 256) | (B_MN ? (1u << 16) : 0u);      // bit 16: B operand MN-major
+    const uint32_t blbo = B_MN ? MN_LBO : P_LBO;
     for (int ks = 0; ks < 8; ++ks) {
       const uint64_t a_hi = umma_desc(sbase + OFF_WHI + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(sbase + OFF_WLO + ks * 2 * W_LBO, W_LBO, SBO);
-      const uint64_t b_hi = umma_desc(sbase + P_OFF_BHI + ks * 2 * P_LBO, P_LBO, SBO), b_lo = umma_desc(sbase + P_OFF_BLO + ks * 2 * P_LBO, P_LBO, SBO);
+      const uint64_t b_hi = umma_desc(sbase + P_OFF_BHI + ks * 2 * blbo, blbo, SBO), b_lo = umma_desc(sbase + P_OFF_BLO + ks * 2 * blbo, blbo, SBO);
       umma_f16(tmem, a_lo, b_hi, idesc, ks > 0);
       umma_f16(tmem, a_hi, b_lo, idesc, 1);
       umma_f16(tmem, a_hi, b_hi, idesc, 1);
@@ -920,7 +932,7 @@ __global__ void __launch_bounds__(128, 1) k_umma_probe(const __half* __restrict_
   if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
-inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_err) {
+inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_err, bool b_mn_major = false) {
   std::vector<float> A((size_t)H * H), Bv((size_t)PN * H);
   uint32_t s = 12345u;
   auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
@@ -947,8 +959,13 @@ inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_er
   cudaMemcpy(dA, Ap.data(), Ap.size() * 2, cudaMemcpyHostToDevice);
   cudaMemcpy(dB, Bp.data(), Bp.size() * 2, cudaMemcpyHostToDevice);
   cudaMemset(dD, 0, (size_t)H * PN * 4);
-  cudaFuncSetAttribute(k_umma_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
-  k_umma_probe<<<1, 128, P_SMEM_BYTES>>>(dA, dB, dD);
+  if (b_mn_major) {
+    cudaFuncSetAttribute(k_umma_probe<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    k_umma_probe<true><<<1, 128, P_SMEM_BYTES>>>(dA, dB, dD);
+  } else {
+    cudaFuncSetAttribute(k_umma_probe<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+    k_umma_probe<false><<<1, 128, P_SMEM_BYTES>>>(dA, dB, dD);
+  }
   cudaError_t err = cudaDeviceSynchronize();
   std::vector<float> D((size_t)H * PN);
   cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
@@ -968,7 +985,8 @@ inline dl_status selftest(int /*num_sms*/, float* max_abs_err, float* max_rel_er
   mr = ma / std::max(mref, 1e-30);
   if (max_abs_err) *max_abs_err = (float)ma;
   if (max_rel_err) *max_rel_err = (float)mr;
-  fprintf(stderr, "[dl selftest] 3xFP16 UMMA 128x256x128: max abs err %.3e (rel to max |ref| %.3e)\n", ma, mr);
+  fprintf(stderr, "[dl selftest] 3xFP16 UMMA 128x256x128 (B %s-major): max abs err %.3e (rel to max |ref| %.3e)\n",
+          b_mn_major ? "MN" : "K", ma, mr);
   return DL_OK;
 }
 

@@ -171,6 +171,9 @@ dl_status dl_cut_graph_stats(dl_engine* e, int64_t* out);
 /* Self-test of the tcgen05 edge-MLP tile against the SIMT path on random data. Blocking.
  * Returns DL_OK and writes the max abs/rel error. */
 dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err);
+/* Same with the B operand in the MN-major canonical layout (b_mn_major != 0; instruction-descriptor bit 16): the layout a
+ * lane = channel producer can fill with 16-byte stores -- groundwork for running the first Linear on the tensor cores. */
+dl_status dl_selftest_tc_layout(dl_engine* e, int32_t b_mn_major, float* max_abs_err, float* max_rel_err);
 
 /*
  * Output stage (the step right after sample_chain in every generation script).

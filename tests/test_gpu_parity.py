@@ -288,17 +288,21 @@ def test_full_size_forward_vs_oracle_sampled_molecules():
     assert rel_err(got[idx], want) <= REL_TOL
 
 
-def test_umma_selftest_3xfp16():
-    """tcgen05 building block in isolation: one 128x256x128 hi/lo-split UMMA chain vs fp64 on the host."""
+@pytest.mark.parametrize("b_mn_major", [0, 1])
+def test_umma_selftest_3xfp16(b_mn_major):
+    """tcgen05 building block in isolation: one 128x256x128 hi/lo-split UMMA chain vs fp64 on the host, with the B operand
+    in the K-major layout the kernels use and in the MN-major canonical layout (next step of the producer redesign)."""
     import ctypes as C
     from difflinker_b200 import _native
     dyn, hp = helpers.build_dynamics(helpers.EXTRA_SPECS["small_fc"], 0)
     eng = dyn.engine(0)
     lib = _native.load_library()
     ea, er = C.c_float(-1), C.c_float(-1)
-    st = lib.dl_selftest_tc(eng, C.byref(ea), C.byref(er))
+    st = lib.dl_selftest_tc_layout(eng, b_mn_major, C.byref(ea), C.byref(er))
     assert st == 0, lib.dl_last_error()
     assert 0 <= er.value < 2e-6, (ea.value, er.value)
+    if not b_mn_major:
+        assert lib.dl_selftest_tc(eng, C.byref(ea), C.byref(er)) == 0 and 0 <= er.value < 2e-6
 
 
 def test_simt_and_tcgen05_edge_paths_agree():
