@@ -2,6 +2,7 @@
 reference's interface (constructor kwargs, state_dict keys, exception attributes); sharding logic under gloo."""
 import os
 import re
+import shutil
 import subprocess
 import sys
 
@@ -233,3 +234,33 @@ def test_draw_noise_follows_the_reference_call_order():
     g = torch.Generator().manual_seed(1000)
     got = ddpm.edm.draw_noise(7, 4, 30, torch.device('cpu'), generator=g)
     assert torch.equal(got, helpers.noise_tensor(1000, 5, 4, 30, spec.F))
+
+
+def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
+    """The drop-in boundary is a C ABI: include/difflinker_b200.h must compile as strict C99 (and C++), and a C program that
+    only includes the header links against libdifflinker_b200.so and reaches the version / error entry points."""
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    lib = _native.LIB_PATH
+    _native.load_library()
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "difflinker_b200.h"\n'
+        "int main(void) {\n"
+        "  dl_config c; dl_sizegnn_config s; dl_engine* e = 0; dl_status st;\n"
+        "  (void)s; if (sizeof(dl_step_coef) != 32) return 2;\n"
+        "  c.n_dims = 3; c.in_node_nf = 8; c.context_node_nf = 1; c.hidden_nf = 64; c.n_layers = 1; c.inv_sublayers = 1;\n"
+        "  c.condition_time = 1; c.centering = 0; c.graph_type = DL_GRAPH_FC; c.device = 0; c.edge_impl = DL_EDGE_AUTO;\n"
+        "  c.norm_constant = 0.f; c.normalization_factor = 1.f;\n"
+        "  st = dl_create(&c, &e);            /* hidden_nf = 64 is refused before any CUDA call */\n"
+        '  printf("%s|%d|%s\\n", dl_version(), (int)st, dl_last_error());\n'
+        "  return st < 0 ? 0 : 3;\n}\n")
+    exe = tmp_path / "abi"
+    inc = os.path.join(ROOT, "include")
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", f"-I{inc}", str(src), "-o", str(exe), lib,
+                    f"-Wl,-rpath,{os.path.dirname(lib)}"], check=True, capture_output=True)
+    res = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert res.returncode == 0, (res.stdout, res.stderr)
+    version, status, err = res.stdout.strip().split("|", 2)
+    assert version.startswith("difflinker_b200") and int(status) < 0 and "hidden_nf" in err
