@@ -124,6 +124,43 @@ def test_step_coefficients_match_reference_golden(name):
     assert all(f != 0 for f in frames) and rows[T].frame == -1
 
 
+def test_inpainting_step_coefficients_and_noise_order_match_the_oracle():
+    """InpaintingEDM host side: q(z_s|z_t,x) coefficients (edm.py:655-668, 716), chain-frame bookkeeping (edm.py:596-598: every
+    step writes its frame after the COM projection, the last writer wins, chain[0] is overwritten at the end) and the order of
+    the prepared noise slabs (edm.py:565,645,669,689,706)."""
+    meta, a = helpers.load_golden("inpaint_chain_cfg1")
+    spec = helpers.spec_by_name(meta["spec"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"], inpainting=True)
+    T, keep, B = meta["T"], meta["keep_frames"], meta["batch"]
+    rows = ddpm.edm.step_coefficients(keep, B)
+    gam = orc.gamma_table(hp['diffusion_noise_schedule'], hp['diffusion_steps'], hp['diffusion_noise_precision'])
+    for r in range(T):
+        s = T - 1 - r
+        s_arr = torch.full((B, 1), fill_value=s)
+        t_arr = (s_arr + 1) / T
+        s_arr = s_arr / T
+        g_s, g_t = orc.gamma_lookup(gam, s_arr, T), orc.gamma_lookup(gam, t_arr, T)
+        sig2_ts, sig_ts, a_ts = orc._sigma_alpha_t_given_s(g_t, g_s)
+        sig_s, sig_t, al_s = orc._sigma(g_s), orc._sigma(g_t), orc._alpha(g_s)
+        assert rows[r].qa == float((a_ts * (sig_s ** 2) / (sig_t ** 2))[0])
+        assert rows[r].qb == float((al_s * sig2_ts / (sig_t ** 2))[0])
+        assert rows[r].a == float(a_ts[0]) and rows[r].c == float((sig_ts * sig_s / sig_t)[0])
+    g0 = orc.gamma_lookup(gam, torch.zeros((B, 1)), T)
+    assert rows[T].qa == float((orc._sigma(g0) / orc._alpha(g0))[0])
+    frames = [rows[r].frame for r in range(T)]
+    for f in range(1, keep):
+        assert [T - 1 - r for r in range(T) if frames[r] == f] == [min(s for s in range(T) if (s * keep) // T == f)]
+    assert all(f != 0 for f in frames)
+    # prepared noise: same generator -> the slabs the GPU test injects
+    from difflinker_b200.batching import collate
+    data = collate(synthetic.make_items(spec, batch=B))
+    N = data['positions'].shape[1]
+    g = torch.Generator().manual_seed(meta["noise_seed"])
+    got = ddpm.edm.draw_noise_inpaint(B, N, torch.device('cpu'), data['atom_mask'], data['fragment_mask'], generator=g)
+    want = helpers.inpaint_noise_tensor(meta["noise_seed"], T, B, N, spec.F, data['atom_mask'], data['fragment_mask'])
+    assert got.shape == (2 * T + 3, B, N, 3 + spec.F) and torch.equal(got, want)
+
+
 @pytest.mark.parametrize("spec_name,nb", [("cfg1_plumbing", 4), ("cfg2_zinc_ragged", 6), ("cfg4_pockets", 2)])
 def test_batching_matches_oracle_contract(spec_name, nb):
     spec = synthetic.SPECS[spec_name]
