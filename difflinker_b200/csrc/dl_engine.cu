@@ -287,7 +287,8 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ta.b3 = w0.b3; ta.b4 = w0.b4; ta.w3_descale = 1.f; ta.w4_descale = 1.f;
     ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(w0.W1_tc); ta.pb1[0] = w0.b1;
     ta.p_descale[0] = w0.w1_descale; ta.AB[0] = ws.ABg; ta.ABmax[0] = ws.ABgmax;
-    tcn::k_node_tc<<<(n + tcn::TM - 1) / tcn::TM, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
+    ta.tile_nodes = tcn::pick_tile_nodes(n, e->num_sms);
+    tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
     LAUNCH_CHECK();
     e->launches += 1;
   }
@@ -344,7 +345,10 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         if (node_prof_left > 0) cudaStreamIsCapturing(st, &cap);
         if (node_prof_left > 0 && cap == cudaStreamCaptureStatusNone) { --node_prof_left; tcn::profile_node(n, ta, st); }
-        else tcn::k_node_tc<<<(n + tcn::TM - 1) / tcn::TM, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
+        else {
+          ta.tile_nodes = tcn::pick_tile_nodes(n, e->num_sms);
+          tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
+        }
       } else {
         NodeArgs na{};
         na.h = ws.h; na.agg = ws.agg; na.nm = ws.nm; na.W3_t = w.W3_t; na.b3 = w.b3; na.W4_t = w.W4_t; na.b4 = w.b4;

@@ -51,6 +51,7 @@ struct NodeTcArgs {
   const __half* w4;      // 1 packed block
   const float *b3, *b4;
   float w3_descale, w4_descale;
+  int tile_nodes;        // nodes per CTA (multiple of 8, <= 128; 0 = 128): chosen by the host so that one wave fills the SMs
   int proj_only;         // 1: skip the node MLP -- h is only projected (first layer of a forward: replaces the SIMT projection of k_prep)
   int n_proj;            // 1 or 2
   const __half* pw[2];   // 2 packed blocks each (W1a, W1b), common scale
@@ -88,8 +89,10 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const long long t0 = prof ? clock64() : 0;
   auto mark = [&](int i) { if (prof && tid == 0) prof[(size_t)blockIdx.x * 8 + i] = clock64() - t0; };
-  const int g0 = blockIdx.x * TM;
-  const int n_live = min(TM, n_total - g0);
+  const int tile = a.tile_nodes > 0 ? a.tile_nodes : TM;   // nodes of this CTA's tile (<= TM)
+  const int g0 = blockIdx.x * tile;
+  const int n_live = min(tile, n_total - g0);
+  const int n_pad = (tile + 15) & ~15;                     // UMMA N: operand rows [0, n_pad) are read by the tensor core
 
   const uint32_t bar_full = sbase + N_OFF_BAR, bar_empty = bar_full + 8 * N_RING, bar_acc = bar_empty + 8 * N_RING;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + N_OFF_BAR + 8 * (2 * N_RING + 4));
@@ -136,8 +139,11 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   }
 
   const int c = tid & (TM - 1);                        // this thread's output channel = TMEM lane
-  const int part = tid >> 7;                           // which CW-wide slice of the node columns this thread serves
-  const int ncol0 = part * CW;
+  const int part = tid >> 7;                           // which slice of the node columns this thread serves
+  const int cw = (((tile + NPART - 1) / NPART) + 7) & ~7;  // slice width: a multiple of 8 (TMEM loads are 8 columns wide)
+  const int ncol0 = part * cw;
+  const int ncols = max(0, min(cw, tile - ncol0));     // this slice's columns (warp-uniform; 0 = idle slice)
+  const int ng = (ncols + 7) >> 3;                     // 8-column groups, <= CW / 8
   const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ncol0;
 
   // ---- operand rows: h -> XA, agg -> XB; coalesced row loads (one row per warp iteration) -----------------------------
@@ -158,6 +164,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int r = warp + NW * (rb + j);
+        if (r >= n_pad) continue;                        // (warp-uniform) rows beyond the UMMA N extent are never read
         mx = fmaxf(mx, fmaxf(fmaxf(fabsf(hv[j].x), fabsf(hv[j].y)), fmaxf(fabsf(hv[j].z), fabsf(hv[j].w))));
         mx = fmaxf(mx, fmaxf(fmaxf(fabsf(av[j].x), fabsf(av[j].y)), fmaxf(fabsf(av[j].z), fabsf(av[j].w))));
         const int off = (lane >> 1) * X_LBO + r * 16 + (lane & 1) * 8;     // channels 4*lane..4*lane+3 of row r
@@ -190,7 +197,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   mark(0);   // rows loaded / converted
 
   // ---- MMA issue helper (thread 0): consume `nh` half-blocks of the ring starting at ring index i0 ------------------
-  const uint32_t idesc = umma_idesc(128, 128);
+  const uint32_t idesc = umma_idesc(128, n_pad);
   auto issue = [&](int i0, int nh, const uint8_t* const* xhi_of, uint32_t acc_col, int acc_bar) {
     // xhi_of[j]: node-operand hi base for half-block j of this GEMM (lo = hi + X_BYTES); kc offset = 8*(j&1)
     tc_fence_after();
@@ -229,17 +236,19 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
       const float bias = __ldg(a.b3 + c);
       auto epi1 = [&](float scale) -> float {           // hid = silu(D*ds + b3) -> XB (agg operand is dead: G1 is complete)
         float mx = 0.f;
-        uint32_t r[2][16];
-        TMEM_LD_X16(trow, r[0]);
-  #pragma unroll
-        for (int k = 0; k < CW / 16; ++k) {
-          tmem_ld_wait();
-          if (k + 1 < CW / 16) TMEM_LD_X16(trow + (k + 1) * 16, r[(k + 1) & 1]);
-  #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const float v = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
-            mx = fmaxf(mx, fabsf(v));                    // |silu(v)| <= |v|
-            store_elem(xb_hi, xb_lo, c, ncol0 + k * 16 + u, silu_f(v) * scale);
+        uint32_t r[2][8];
+        if (ng > 0) TMEM_LD_X8(trow, r[0]);
+        #pragma unroll
+        for (int k = 0; k < CW / 8; ++k) {
+          if (k < ng) {                                  // warp-uniform
+            tmem_ld_wait();
+            if (k + 1 < ng) TMEM_LD_X8(trow + (k + 1) * 8, r[(k + 1) & 1]);
+        #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const float v = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
+              mx = fmaxf(mx, fabsf(v));                  // |silu(v)| <= |v|
+              store_elem(xb_hi, xb_lo, c, ncol0 + k * 8 + u, silu_f(v) * scale);
+            }
           }
         }
         return mx;
@@ -265,34 +274,38 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
       const float bias = __ldg(a.b4 + c);
       float* hcol = a.h + (size_t)g0 * H + c;            // h[(g0+n)*128 + c]: a warp covers 128 contiguous bytes per node
       float mx = 0.f;
-      uint32_t r[2][16];
-      float hv[2][16];
-  #pragma unroll
-      for (int u = 0; u < 16; ++u) hv[0][u] = (ncol0 + u < n_live) ? hcol[(size_t)(ncol0 + u) * H] : 0.f;
-      TMEM_LD_X16(trow + 128, r[0]);
-  #pragma unroll
-      for (int k = 0; k < CW / 16; ++k) {
-        tmem_ld_wait();
-        if (k + 1 < CW / 16) {
-          TMEM_LD_X16(trow + 128 + (k + 1) * 16, r[(k + 1) & 1]);
-  #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int nn = ncol0 + (k + 1) * 16 + u;
-            hv[(k + 1) & 1][u] = (nn < n_live) ? hcol[(size_t)nn * H] : 0.f;
+      uint32_t r[2][8];
+      float hv[2][8];
+      if (ng > 0) {
+      #pragma unroll
+        for (int u = 0; u < 8; ++u) hv[0][u] = (ncol0 + u < n_live) ? hcol[(size_t)(ncol0 + u) * H] : 0.f;
+        TMEM_LD_X8(trow + 128, r[0]);
+      }
+      #pragma unroll
+      for (int k = 0; k < CW / 8; ++k) {
+        if (k < ng) {                                    // warp-uniform
+          tmem_ld_wait();
+          if (k + 1 < ng) {
+            TMEM_LD_X8(trow + 128 + (k + 1) * 8, r[(k + 1) & 1]);
+      #pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int nn = ncol0 + (k + 1) * 8 + u;
+              hv[(k + 1) & 1][u] = (nn < n_live) ? hcol[(size_t)nn * H] : 0.f;
+            }
           }
-        }
-  #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int n = ncol0 + k * 16 + u;
-          const float o = (hv[k & 1][u] + fmaf(__uint_as_float(r[k & 1][u]), ds, bias)) * nms[n];     // egnn.py:71,78-79
-          if (n < n_live) hcol[(size_t)n * H] = o;
-          mx = fmaxf(mx, fabsf(o));
-          store_elem(xa_hi, xa_lo, c, n, o);
+      #pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int n = ncol0 + k * 8 + u;
+            const float o = (hv[k & 1][u] + fmaf(__uint_as_float(r[k & 1][u]), ds, bias)) * nms[n];     // egnn.py:71,78-79
+            if (n < n_live) hcol[(size_t)n * H] = o;
+            mx = fmaxf(mx, fabsf(o));
+            store_elem(xa_hi, xa_lo, c, n, o);
+          }
         }
       }
       s3 = pow2_scale_for(tile_max(mx));
       if (s3 != 1.0f) {                                  // rare: rewrite h' scaled (own global writes, program order)
-        for (int n = ncol0; n < ncol0 + CW; ++n) store_elem(xa_hi, xa_lo, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
+        for (int n = ncol0; n < ncol0 + 8 * ng; ++n) store_elem(xa_hi, xa_lo, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
       }
     }
     fence_proxy_async();
@@ -322,17 +335,19 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
       const float bias = part == 0 ? __ldg(a.pb1[p] + c) : 0.f;
       float* abcol = a.AB[p] + (size_t)g0 * 2 * H + part * H + c;
       float mx = 0.f;
-      uint32_t r[2][16];
-      TMEM_LD_X16(trow + accn * 128, r[0]);
-#pragma unroll
-      for (int k = 0; k < CW / 16; ++k) {
-        tmem_ld_wait();
-        if (k + 1 < CW / 16) TMEM_LD_X16(trow + accn * 128 + (k + 1) * 16, r[(k + 1) & 1]);
-#pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int n = ncol0 + k * 16 + u;
-          const float o = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
-          if (n < n_live) { abcol[(size_t)n * 2 * H] = o; mx = fmaxf(mx, fabsf(o)); }
+      uint32_t r[2][8];
+      if (ng > 0) TMEM_LD_X8(trow + accn * 128, r[0]);
+      #pragma unroll
+      for (int k = 0; k < CW / 8; ++k) {
+        if (k < ng) {                                  // warp-uniform
+          tmem_ld_wait();
+          if (k + 1 < ng) TMEM_LD_X8(trow + accn * 128 + (k + 1) * 8, r[(k + 1) & 1]);
+      #pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int n = ncol0 + k * 8 + u;
+            const float o = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
+            if (n < n_live) { abcol[(size_t)n * 2 * H] = o; mx = fmaxf(mx, fabsf(o)); }
+          }
         }
       }
       // range bound for the consumer's fp16 operands: the TILE maximum of |A| (|B|) is written for every node of the
@@ -374,6 +389,13 @@ inline size_t pack_blocks(const std::vector<float>& W, int in_stride, int nblk, 
           blob[off + b * per + (size_t)KC * H * 8 + ((size_t)kc * H + c) * 8 + u] = lo;
         }
   return off;
+}
+
+// Nodes per CTA: the smallest multiple of 8 that lets one wave of `num_sms` CTAs cover all n nodes (<= 128). Fewer, fuller
+// tiles would leave SMs idle (cfg 2: 80 tiles of 128 on 148 SMs); every phase of the per-tile chain shortens with the tile.
+inline int pick_tile_nodes(int n, int num_sms) {
+  const int per = (n + num_sms - 1) / std::max(num_sms, 1);
+  return std::min(TM, std::max(8, (per + 7) & ~7));
 }
 
 // Debug: one timed launch; prints the phase boundaries (cycles from kernel entry, thread 0, averaged over CTAs).
