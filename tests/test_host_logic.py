@@ -264,3 +264,21 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
     assert res.returncode == 0, (res.stdout, res.stderr)
     version, status, err = res.stdout.strip().split("|", 2)
     assert version.startswith("difflinker_b200") and int(status) < 0 and "hidden_nf" in err
+
+
+def test_bench_reference_arm_contract_on_cpu():
+    """`bench.py --impl reference` (the reference's CPU path = the oracle port) prints ONE JSON line with the contract's keys;
+    it needs no GPU, so the arm itself is checked here on the plumbing config."""
+    import json
+    res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1_plumbing",
+                          "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [l for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in d, k
+    assert d["impl"] == "reference" and d["unit"] == "molecules/s" and d["value"] > 0 and d["higher_is_better"] is True
+    assert d["config"]["workload"] == "cfg1_plumbing" and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
