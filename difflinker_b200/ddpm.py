@@ -125,6 +125,29 @@ class DDPM(nn.Module):
     def forward(self, *a, **k):
         raise NotImplementedError("training is outside the difflinker_b200 hot path")
 
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **overrides):
+        """`DDPM.load_from_checkpoint(args.model, map_location=device)` (generate.py:101, sample.py:84) without
+        pytorch_lightning: a Lightning checkpoint is a dict with `hyper_parameters` (what `save_hyperparameters()` stored,
+        lightning.py:51) and `state_dict`. Keyword overrides replace saved hyper-parameters, as in Lightning."""
+        return _load_lightning_checkpoint(cls, checkpoint_path, map_location, strict, overrides)
+
+
+def _load_lightning_checkpoint(cls, checkpoint_path, map_location, strict, overrides):
+    try:
+        ckpt = torch.load(checkpoint_path, map_location='cpu', weights_only=False)
+    except TypeError:                                        # older torch without the weights_only argument
+        ckpt = torch.load(checkpoint_path, map_location='cpu')
+    if 'state_dict' not in ckpt or 'hyper_parameters' not in ckpt:
+        raise KeyError("not a Lightning checkpoint: expected the keys 'state_dict' and 'hyper_parameters'")
+    hp = dict(ckpt['hyper_parameters'])
+    hp.update(overrides)
+    model = cls(**hp)
+    model.load_state_dict(ckpt['state_dict'], strict=strict)
+    if map_location is not None:
+        model = model.to(map_location)
+    return model
+
 
 def accelerate(ddpm, edge_impl='auto'):
     """Replace `ddpm.edm` of a *reference* DDPM (src/lightning.py) by the native EDM, copying its weights

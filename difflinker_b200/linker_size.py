@@ -190,6 +190,12 @@ class SizeClassifier(nn.Module):
             labels.append(label)
         return torch.tensor(labels, device=linker_mask.device, dtype=torch.long)
 
+    @classmethod
+    def load_from_checkpoint(cls, checkpoint_path, map_location=None, strict=True, **overrides):
+        """`SizeClassifier.load_from_checkpoint(linker_size, map_location=device)` (generate.py:88) without Lightning."""
+        from .ddpm import _load_lightning_checkpoint
+        return _load_lightning_checkpoint(cls, checkpoint_path, map_location, strict, overrides)
+
     @torch.no_grad()
     def sample_sizes(self, data, generator=None):
         """The `sample_fn` of generate.py:90-99: softmax -> Categorical -> linker sizes (int8, on the batch's device)."""

@@ -282,3 +282,29 @@ def test_bench_reference_arm_contract_on_cpu():
     assert d["impl"] == "reference" and d["unit"] == "molecules/s" and d["value"] > 0 and d["higher_is_better"] is True
     assert d["config"]["workload"] == "cfg1_plumbing" and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+
+
+def test_load_from_checkpoint_reads_lightning_checkpoints(tmp_path):
+    """generate.py:101 / :88 -- `DDPM.load_from_checkpoint(path, map_location)` and `SizeClassifier.load_from_checkpoint`
+    on the Lightning checkpoint layout ({'hyper_parameters', 'state_dict', ...}), strict key match, overrides as kwargs."""
+    from difflinker_b200 import DDPM, SizeClassifier
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    m, hp = helpers.build_ddpm(spec, 0)
+    path = str(tmp_path / "difflinker.ckpt")
+    torch.save({"epoch": 3, "global_step": 7, "hyper_parameters": hp, "state_dict": m.state_dict()}, path)
+    m2 = DDPM.load_from_checkpoint(path, map_location="cpu")
+    assert list(m2.state_dict()) == list(m.state_dict())
+    assert all(torch.equal(a, b) for a, b in zip(m.state_dict().values(), m2.state_dict().values()))
+    assert m2.edm.T == hp['diffusion_steps'] and m2.inpainting is False
+    assert DDPM.load_from_checkpoint(path, center_of_mass='anchors').center_of_mass == 'anchors'
+    bad = dict(m.state_dict()); bad.pop(next(iter(bad)))
+    torch.save({"hyper_parameters": hp, "state_dict": bad}, path)
+    with pytest.raises(RuntimeError):
+        DDPM.load_from_checkpoint(path)                                   # strict=True: a missing key is an error
+    torch.save({"state_dict": m.state_dict()}, path)
+    with pytest.raises(KeyError):
+        DDPM.load_from_checkpoint(path)
+    sc = SizeClassifier(in_node_nf=8, out_node_nf=10, n_layers=3, normalization='batch_norm')
+    torch.save({"hyper_parameters": sc.hparams, "state_dict": sc.state_dict()}, path)
+    sc2 = SizeClassifier.load_from_checkpoint(path)
+    assert all(torch.equal(a, b) for a, b in zip(sc.state_dict().values(), sc2.state_dict().values()))
