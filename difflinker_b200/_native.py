@@ -55,6 +55,7 @@ SYMBOLS = {
     "dl_sizegnn_finalize_weights": (_I32, [_P]),
     "dl_sizegnn_forward": (_I32, [_P, _I32, _I32, _P, _P, _P, _P, _P]),
     "dl_restore_frame": (_I32, [_I32, _I32, _I32, _P, _P, _P, _P, _P]),
+    "dl_restore_frame2": (_I32, [_I32, _I32, _I32, _I32, _P, _P, _P, _P, _P]),
     "dl_bond_orders": (_I32, [_I32, _I32, _I32, _P, _I32, _P, _P, _P, _P, _P, _P, _P]),
     "dl_format_xyz": (_I64, [_I32, _I32, _I32, _P, _I32, _P, _I32, _P, C.POINTER(C.c_char_p), _I32, _P, _I64, _P]),
 }

@@ -39,6 +39,22 @@ __device__ __forceinline__ float2 sigmoid_pair_log2(float2 u) {
   const float r = rcp_approx(den.x * den.y);
   return __fmul2_rn(make_float2(r, r), make_float2(den.y, den.x));
 }
+// Four sigmoids for FIVE MUFU ops (4 ex2 + 1 rcp): with a,b,c,d the four denominators 1 + 2^u,
+//   m = (a,b)*(c,d) = (ac, bd),  r = 1/(ac*bd),  (r*bd, r*ac) = (1/(ac), 1/(bd)),  times (c,d) -> (1/a, 1/b), times (a,b) -> (1/c, 1/d).
+// Every product is one packed instruction on register pairs that already exist (no shuffling of halves). The exponent is
+// clamped at 31 so the product of four denominators stays below 2^125; that only alters u*sigmoid for u > 31
+// (pre-activation < -21.5), where it changes the result by less than |u| * 4.7e-10 -- below fp32 resolution of the O(1)
+// activations it is added to.
+__device__ __forceinline__ void usig4(float2 u01, float2 u23, float2& s01, float2& s23) {
+  const float2 one = make_float2(1.0f, 1.0f);
+  const float2 ab = __fadd2_rn(make_float2(ex2_approx(fminf(u01.x, 31.0f)), ex2_approx(fminf(u01.y, 31.0f))), one);
+  const float2 cd = __fadd2_rn(make_float2(ex2_approx(fminf(u23.x, 31.0f)), ex2_approx(fminf(u23.y, 31.0f))), one);
+  const float2 m = __fmul2_rn(ab, cd);
+  const float r = rcp_approx(m.x * m.y);
+  const float2 rm = __fmul2_rn(make_float2(r, r), make_float2(m.y, m.x));
+  s01 = __fmul2_rn(u01, __fmul2_rn(rm, cd));
+  s23 = __fmul2_rn(u23, __fmul2_rn(rm, ab));
+}
 // (u0, u1) -> (u0/(1+2^u0), u1/(1+2^u1)): two sigmoids in the log2 domain
 __device__ __forceinline__ float2 usig2(float2 u) { return __fmul2_rn(u, sigmoid_pair_log2(u)); }
 // (x0, x1) -> (silu(x0), silu(x1))
@@ -66,6 +82,12 @@ struct GclW {
   const void* W3_tc;   // node_mlp.0.weight as two packed blocks
   const void* W4_tc;   // node_mlp.2.weight as one packed block
   float w1_descale, w3_descale, w4_descale;
+  // tcgen05 path, log2-domain first layer (kernels_tc.cuh pack_w2): b1, wd, w0 times -log2(e); W1_tc is packed from the
+  // scaled matrix, W2_tc / W2_v3 carry the compensating -ln2.
+  const float* b1_u;
+  const float* wd_u;
+  const float* w0_u;
+  const void* W2_v3;   // [hi | lo][out][64 words], K-permuted (kernels_edge_v3.cuh); same scale as W2_tc
 };
 
 // Packed weights of one EquivariantUpdate (src/egnn.py:90-97).
@@ -83,6 +105,9 @@ struct EqW {
   float wdmax, w0max;
   const void* W1_tc;   // coord_mlp.0.weight[:, 0:2H] as two packed blocks
   float w1_descale;
+  const float* b1_u;   // log2-domain copies (see GclW)
+  const float* wd_u;
+  const float* w0_u;
 };
 
 // First-layer projection of an edge MLP applied per node: A = h W1a^T + b1, B = h W1b^T.

@@ -17,6 +17,7 @@
 #include "kernels_simt.cuh"
 #include "kernels_tc.cuh"
 #include "kernels_node_tc.cuh"
+#include "kernels_edge_v3.cuh"
 
 using namespace dl;
 
@@ -53,6 +54,9 @@ struct Workspace {
   int4* xitems = nullptr;
   int* tile_ctr = nullptr;
   void* tc_scratch = nullptr;
+  // third-generation GCL kernel (kernels_edge_v3.cuh): FC graphs with N <= 64; tensor map of ABg's B halves
+  bool v3 = false;
+  CUtensorMap tm_abg;
   std::vector<void*> allocs;
 };
 
@@ -83,6 +87,7 @@ struct dl_engine {
   int64_t launches = 0;
   HostStage stage;
   bool use_tc = false;
+  bool allow_v3 = true;        // DL_EDGE_V3=0 keeps the second-generation kernel (A/B measurements)
   // pointers of the most recent forward (for dl_time_edge_kernel)
   const int8_t* last_edge_mask = nullptr;
   const float* last_linker_mask = nullptr;
@@ -167,6 +172,8 @@ void free_workspace(Workspace& ws) {
   ws = Workspace();
 }
 
+Geom make_geom(const dl_engine* e, int B, int N);
+
 dl_status ensure_workspace(dl_engine* e, int B, int N) {
   Workspace& ws = e->ws;
   if (ws.B == B && ws.N == N) return DL_OK;
@@ -182,6 +189,11 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   if (e->use_tc && e->cfg.graph_type != 0) { WSA(nbr, n * N); WSA(recs, n * CUT_REC); WSA(xrecs, n * CUT_REC); WSA(n_recs, 2); }
 #undef WSA
   ws.B = B; ws.N = N;
+  ws.v3 = false;
+  if (e->use_tc && e->allow_v3 && tc3::supports(make_geom(e, B, N))) {
+    if (tc3::make_panel_map(&ws.tm_abg, ws.ABg, B, N) != DL_OK) { set_err("cuTensorMapEncodeTiled failed for the projection buffer"); return DL_ERR_CUDA; }
+    ws.v3 = true;
+  }
   return DL_OK;
 }
 
@@ -220,8 +232,9 @@ dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const 
   LAUNCH_CHECK();
   const int tile_edges = e->use_tc ? tc::TN : ET;
   const int max_rows = e->use_tc ? tc::MAXR : MAXR;
-  k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols,
-                                ws.n_xmols, ws.xitems, ws.n_xitems);
+  // GCL items of the v3 kernel: rows padded to a multiple of four columns, at most MAXR3 rows per tile
+  k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, ws.v3 ? 4 : 1, ws.v3 ? tc3::MAXR3 : max_rows, ws.nr, ws.nc, ws.nxr,
+                                ws.items, ws.n_items, ws.xmols, ws.n_xmols, ws.xitems, ws.n_xitems);
   LAUNCH_CHECK();
   e->launches += 2;
   return DL_OK;
@@ -243,8 +256,10 @@ ProjW proj_of(const GclW& w) { return ProjW{w.W1a_t, w.W1b_t, w.b1}; }
 ProjW proj_of(const EqW& w) { return ProjW{w.W1a_t, w.W1b_t, w.b1}; }
 
 dl_status launch_edge(dl_engine* e, const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc,
-                      cudaStream_t st) {
-  if (e->use_tc) {
+                      cudaStream_t st, const void* w2_v3 = nullptr) {
+  if (e->use_tc && !coord && e->ws.v3) {
+    tc3::launch_edge_v3(gm, ea, w2_v3, e->ws.tm_abg, e->num_sms, st);
+  } else if (e->use_tc) {
     dl_status s = tc::launch_edge_tc(gm, ea, coord, w2_tc, e->num_sms, st);
     if (s != DL_OK) return s;
   } else {
@@ -285,7 +300,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ta.h = ws.h; ta.agg = ws.h; ta.nm = ws.nm; ta.proj_only = 1;
     ta.w3 = reinterpret_cast<const __half*>(w0.W3_tc); ta.w4 = reinterpret_cast<const __half*>(w0.W4_tc);
     ta.b3 = w0.b3; ta.b4 = w0.b4; ta.w3_descale = 1.f; ta.w4_descale = 1.f;
-    ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(w0.W1_tc); ta.pb1[0] = w0.b1;
+    ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(w0.W1_tc); ta.pb1[0] = w0.b1_u;
     ta.p_descale[0] = w0.w1_descale; ta.AB[0] = ws.ABg; ta.ABmax[0] = ws.ABgmax;
     ta.tile_nodes = tcn::pick_tile_nodes(n, e->num_sms);
     tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
@@ -308,17 +323,18 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   float4* xin4 = ws.xa4;
   float4* xout4 = ws.xb4;
   const Plan plan = make_plan(ws);
+  const float ksc = e->use_tc ? 1.4426950408889634f : 1.0f;   // log2-domain first layer on the tcgen05 path
   e->last_edge_mask = io.edge_mask; e->last_linker_mask = io.linker_mask; e->last_B = B; e->last_N = N;
   for (int l = 0; l < L; ++l) {
     for (int s = 0; s < S; ++s) {
       const GclW& w = e->gcl[l * S + s];
       EdgeArgs ea{};
-      ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
+      ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax * ksc; ea.w0max = w.w0max * ksc;
       ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = nullptr;
       ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
-      ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
+      ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = e->use_tc ? w.wd_u : w.wd; ea.w0 = e->use_tc ? w.w0_u : w.w0; ea.w5 = nullptr;
       ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
-      dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st);
+      dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st, w.W2_v3);
       if (st2 != DL_OK) return st2;
 
       const bool last_sub = s + 1 >= S;
@@ -329,15 +345,15 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
         ta.b3 = w.b3; ta.b4 = w.b4; ta.w3_descale = w.w3_descale; ta.w4_descale = w.w4_descale;
         if (!last_sub) {
           const GclW& nx = e->gcl[l * S + s + 1];
-          ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[0] = nx.b1;
+          ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[0] = nx.b1_u;
           ta.p_descale[0] = nx.w1_descale; ta.AB[0] = ws.ABg; ta.ABmax[0] = ws.ABgmax;
         } else {
           const EqW& q = e->eq[l];
-          ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(q.W1_tc); ta.pb1[0] = q.b1;
+          ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(q.W1_tc); ta.pb1[0] = q.b1_u;
           ta.p_descale[0] = q.w1_descale; ta.AB[0] = ws.ABc; ta.ABmax[0] = ws.ABcmax;
           if (l + 1 < L) {
             const GclW& nx = e->gcl[(l + 1) * S];
-            ta.n_proj = 2; ta.pw[1] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[1] = nx.b1;
+            ta.n_proj = 2; ta.pw[1] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[1] = nx.b1_u;
             ta.p_descale[1] = nx.w1_descale; ta.AB[1] = ws.ABg; ta.ABmax[1] = ws.ABgmax;
           }
         }
@@ -369,10 +385,10 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     e->launches += 1;
     const EqW& w = e->eq[l];
     EdgeArgs ea{};
-    ea.AB = ws.ABc; ea.ABmax = ws.ABcmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
+    ea.AB = ws.ABc; ea.ABmax = ws.ABcmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax * ksc; ea.w0max = w.w0max * ksc;
     ea.x = xin; ea.x0 = ws.x0; ea.x4 = xin4; ea.x04 = ws.x04; ea.x4_out = xout4;
     ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
-    ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = w.w5;
+    ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = e->use_tc ? w.wd_u : w.wd; ea.w0 = e->use_tc ? w.w0_u : w.w0; ea.w5 = w.w5;
     ea.plan = plan; ea.agg = nullptr; ea.x_out = xout; ea.nbr = ws.nbr; ea.recs = ws.xrecs; ea.n_recs = ws.n_recs ? ws.n_recs + 1 : nullptr;
     dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st);
     if (st2 != DL_OK) return st2;
@@ -479,8 +495,10 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaFuncSetAttribute(k_edge_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_edge_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * CUT_SMEM_PER_NODE));
+  if (const char* v = getenv("DL_EDGE_V3")) e->allow_v3 = atoi(v) != 0;
   dl_status s = tc::configure();
   if (s == DL_OK) s = tcn::configure_node();
+  if (s == DL_OK) s = tc3::configure3();
   if (s != DL_OK) { set_err("cudaFuncSetAttribute failed for the tcgen05 kernels"); delete e; return s; }
   *out = e;
   return DL_OK;
@@ -538,7 +556,9 @@ dl_status dl_finalize_weights(dl_engine* e) {
   const int IN1 = 2 * H + 2;
   Packer pk;
   std::vector<__half> tcblob;
-  struct GOff { size_t W1a, W1b, b1, wd, w0, W2, b2, W3, b3, W4, b4, w5, tc, tc1, tc3, tc4; float descale, wdmax, w0max, d1, d3, d4; };
+  struct GOff { size_t W1a, W1b, b1, wd, w0, W2, b2, W3, b3, W4, b4, w5, tc, tc1, tc3, tc4, b1u, wdu, w0u, v3; float descale, wdmax, w0max, d1, d3, d4; };
+  // log2-domain copies for the tcgen05 path (kernels_tc.cuh pack_w2): everything that feeds the first Linear of an edge MLP
+  auto scaled = [](const std::vector<float>& v) { std::vector<float> o(v.size()); for (size_t i = 0; i < v.size(); ++i) o[i] = (float)((double)v[i] * tc::NEG_LOG2E); return o; };
   auto absmax = [](const std::vector<float>& v) { float m = 0.f; for (float x : v) m = std::max(m, std::fabs(x)); return m; };
   std::vector<GOff> goff(L * S), eoff(L);
   auto R = [&](const std::string& k) -> const std::vector<float>& { return e->raw[k]; };
@@ -565,7 +585,11 @@ dl_status dl_finalize_weights(dl_engine* e) {
       o.W4 = pk.add(transpose_block(R(p + "node_mlp.2.weight"), H, H, 0, H));
       o.b4 = pk.add(R(p + "node_mlp.2.bias"));
       o.tc = tc::pack_w2(R(p + "edge_mlp.2.weight"), tcblob, &o.descale);
-      o.tc1 = tcn::pack_blocks(W1, IN1, 2, tcblob, &o.d1);
+      { float d3v = 0.f; o.v3 = tc3::pack_w2_v3(R(p + "edge_mlp.2.weight"), tcblob, &d3v); }   // same scale rule as pack_w2
+      o.tc1 = tcn::pack_blocks(scaled(W1), IN1, 2, tcblob, &o.d1);
+      o.b1u = pk.add(scaled(R(p + "edge_mlp.0.bias")));
+      o.wdu = pk.add(scaled(column(W1, H, IN1, 2 * H)));
+      o.w0u = pk.add(scaled(column(W1, H, IN1, 2 * H + 1)));
       o.tc3 = tcn::pack_blocks(R(p + "node_mlp.0.weight"), 2 * H, 2, tcblob, &o.d3);
       o.tc4 = tcn::pack_blocks(R(p + "node_mlp.2.weight"), H, 1, tcblob, &o.d4);
       o.wdmax = absmax(column(W1, H, IN1, 2 * H)); o.w0max = absmax(column(W1, H, IN1, 2 * H + 1));
@@ -583,7 +607,10 @@ dl_status dl_finalize_weights(dl_engine* e) {
     o.b2 = pk.add(R(p + "coord_mlp.2.bias"));
     o.w5 = pk.add(R(p + "coord_mlp.4.weight"));
     o.tc = tc::pack_w2(R(p + "coord_mlp.2.weight"), tcblob, &o.descale);
-    o.tc1 = tcn::pack_blocks(W1, IN1, 2, tcblob, &o.d1);
+    o.tc1 = tcn::pack_blocks(scaled(W1), IN1, 2, tcblob, &o.d1);
+    o.b1u = pk.add(scaled(R(p + "coord_mlp.0.bias")));
+    o.wdu = pk.add(scaled(column(W1, H, IN1, 2 * H)));
+    o.w0u = pk.add(scaled(column(W1, H, IN1, 2 * H + 1)));
     o.wdmax = absmax(column(W1, H, IN1, 2 * H)); o.w0max = absmax(column(W1, H, IN1, 2 * H + 1));
   }
   if (e->wblob) { cudaFree(e->wblob); e->wblob = nullptr; }
@@ -601,12 +628,14 @@ dl_status dl_finalize_weights(dl_engine* e) {
     const GOff& o = goff[i];
     e->gcl[i] = GclW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0, base + o.W2, base + o.b2,
                      base + o.W3,  base + o.b3,  base + o.W4, base + o.b4, tbase + o.tc, o.descale, o.wdmax, o.w0max,
-                     tbase + o.tc1, tbase + o.tc3, tbase + o.tc4, o.d1, o.d3, o.d4};
+                     tbase + o.tc1, tbase + o.tc3, tbase + o.tc4, o.d1, o.d3, o.d4,
+                     base + o.b1u, base + o.wdu, base + o.w0u, tbase + o.v3};
   }
   for (int l = 0; l < L; ++l) {
     const GOff& o = eoff[l];
     e->eq[l] = EqW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0,
-                   base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc, o.descale, o.wdmax, o.w0max, tbase + o.tc1, o.d1};
+                   base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc, o.descale, o.wdmax, o.w0max, tbase + o.tc1, o.d1,
+                   base + o.b1u, base + o.wdu, base + o.w0u};
   }
   e->finalized = true;
   return DL_OK;
@@ -842,12 +871,16 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   const Geom gm = make_geom(e, e->last_B, e->last_N);
   const GclW& w = e->gcl[0];
   EdgeArgs ea{};
-  ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax; ea.w0max = w.w0max;
+  const float ksc = e->use_tc ? 1.4426950408889634f : 1.0f;
+  ea.AB = ws.ABg; ea.ABmax = ws.ABgmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax * ksc; ea.w0max = w.w0max * ksc;
   ea.x = ws.xa; ea.x0 = ws.x0; ea.x4 = ws.xa4; ea.x04 = ws.x04; ea.x4_out = nullptr; ea.edge_mask = e->last_edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
-  ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = w.wd; ea.w0 = w.w0; ea.w5 = nullptr;
+  ea.linker_mask = e->last_linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = e->use_tc ? w.wd_u : w.wd; ea.w0 = e->use_tc ? w.w0_u : w.w0; ea.w5 = nullptr;
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
   cudaStream_t st = e->loop_stream;
-  if (e->use_tc && getenv("DL_PROFILE_EDGE")) tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
+  if (e->use_tc && getenv("DL_PROFILE_EDGE")) {
+    if (ws.v3) tc3::profile_edge_v3(gm, ea, w.W2_v3, ws.tm_abg, e->num_sms, st);
+    else tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
+  }
   if (e->use_tc && getenv("DL_PROFILE_NODE")) {
     for (int np = 1; np <= (e->cfg.n_layers > 1 ? 2 : 1); ++np) {
       tcn::NodeTcArgs ta{};
@@ -855,17 +888,17 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
       ta.w3 = reinterpret_cast<const __half*>(w.W3_tc); ta.w4 = reinterpret_cast<const __half*>(w.W4_tc);
       ta.b3 = w.b3; ta.b4 = w.b4; ta.w3_descale = w.w3_descale; ta.w4_descale = w.w4_descale;
       const EqW& q = e->eq[0];
-      ta.n_proj = np; ta.pw[0] = reinterpret_cast<const __half*>(q.W1_tc); ta.pb1[0] = q.b1;
+      ta.n_proj = np; ta.pw[0] = reinterpret_cast<const __half*>(q.W1_tc); ta.pb1[0] = q.b1_u;
       ta.p_descale[0] = q.w1_descale; ta.AB[0] = ws.ABc; ta.ABmax[0] = ws.ABcmax;
       const GclW& nx = e->gcl[e->cfg.n_layers > 1 ? e->cfg.inv_sublayers : 0];
-      ta.pw[1] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[1] = nx.b1;
+      ta.pw[1] = reinterpret_cast<const __half*>(nx.W1_tc); ta.pb1[1] = nx.b1_u;
       ta.p_descale[1] = nx.w1_descale; ta.AB[1] = ws.ABg; ta.ABmax[1] = ws.ABgmax;
       tcn::profile_node(e->last_B * e->last_N, ta, st);
     }
   }
-  for (int i = 0; i < 2; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;
+  for (int i = 0; i < 2; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st, w.W2_v3) != DL_OK) return -1.f;
   if (cudaEventRecord(e->ev_t0, st) != cudaSuccess) return -1.f;
-  for (int i = 0; i < reps; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st) != DL_OK) return -1.f;
+  for (int i = 0; i < reps; ++i) if (launch_edge(e, gm, ea, false, w.W2_tc, st, w.W2_v3) != DL_OK) return -1.f;
   if (cudaEventRecord(e->ev_t1, st) != cudaSuccess) return -1.f;
   if (cudaStreamSynchronize(st) != cudaSuccess) { set_err("dl_time_edge_kernel: %s", cudaGetErrorString(cudaGetLastError())); return -1.f; }
   float ms = -1.f;
@@ -882,6 +915,7 @@ dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err) {
 dl_status dl_selftest_tc_layout(dl_engine* e, int32_t b_mn_major, float* max_abs_err, float* max_rel_err) {
   if (!e) { set_err("null engine"); return DL_ERR_INVALID; }
   CK(cudaSetDevice(e->cfg.device));
+  if (b_mn_major == 2) return tc3::selftest_ts(max_abs_err, max_rel_err);   // A operand in tensor memory (k_edge_v3)
   return tc::selftest(e->num_sms, max_abs_err, max_rel_err, b_mn_major != 0);
 }
 

@@ -1,0 +1,632 @@
+// GCL edge kernel, third generation (fully connected graphs with N <= 64: BASELINE configs 1-3 and the small end of
+// the padded-N sweep). Same algorithm and numerics as tc::k_edge_tc (kernels_tc.cuh; reference egnn.py:45-60,
+// 62-72, 295-320), restructured so that no role of the pipeline waits on an L2 round trip:
+//
+//   * the molecule's column projections B_j (N x 128 fp32) are staged in shared memory by ONE 2-D tiled TMA load
+//     (cp.async.bulk.tensor, SASS UTMALDG) per molecule, double-buffered so the next molecule's panel lands while the
+//     current one is consumed; the producers gather B_j with conflict-free LDS.128 instead of per-edge __ldg from L2;
+//   * the row projections A_i of a tile's (<= 8) rows arrive by 512-byte bulk copies issued by the table warp into the
+//     tile's table slot, completing on the same mbarrier as the tables;
+//   * W2 (hi | lo fp16) lives in TENSOR MEMORY as the A operand of tcgen05.mma (TS form): 64 KB of shared memory and half
+//     of the tensor core's shared-memory read traffic are gone, and with them the 64 KB bulk load at every launch;
+//   * both SiLUs use the four-sigmoids-per-reciprocal form (usig4: 1.25 MUFU per SiLU instead of 1.5), the first layer
+//     runs in the log2 domain (weights pre-scaled by -log2 e: no scaling multiply), tile rows are padded to a multiple
+//     of four columns (weight-0 mirror edges) so the epilogue only has the 8- and 4-column paths, and the epilogue's
+//     TMEM loads are software-pipelined.
+//
+// K permutation: producer thread kc owns channels {4kc..4kc+3} u {64+4kc..64+4kc+3} (two conflict-free 16-byte reads of
+// a 512-byte panel row per half-warp) and writes them as operand positions 8kc..8kc+7; W2 is packed with the same
+// permutation of its K index (pack_w2_v3), so the contraction is unchanged.
+#pragma once
+#include <cuda.h>
+
+#include "kernels_tc.cuh"
+
+namespace dl {
+namespace tc3 {
+
+using namespace dl::tc;
+
+constexpr int MAXR3 = 8;                       // rows per tile (A rows staged per table slot)
+constexpr int NACC3 = 3;                       // TMEM accumulator stages: columns 128 + 128 a (columns 0..127 hold W2 hi | lo)
+constexpr int NSLOT3 = 4;                      // table ring depth
+constexpr int PANEL_N = 64;                    // largest molecule whose B panel is double-buffered in shared memory
+constexpr int PANEL_BYTES = PANEL_N * H * 4;   // 32 KB per buffer
+constexpr int TM_W = 0, TM_ACC = 128;          // TMEM columns
+
+constexpr int O3_ST = 0;                                   // 2 x [hi | lo] activation operand stages
+constexpr int O3_PANEL = O3_ST + N_STAGE * STAGE_BYTES;    // 2 x B panel
+constexpr int O3_TBL = O3_PANEL + 2 * PANEL_BYTES;         // NSLOT3 x table slot
+constexpr int T3_HDR = 0;                                  // int[16]: Et, nrt, ncc4, b, first-of-molecule, q, rescale
+constexpr int T3_REC = 64;                                 // float4[TN]: d, d0, (B row offset | A row offset << 16), operand scale
+constexpr int T3_EW = T3_REC + TN * 16;                    // f32[TN]: edge weight * -ln2
+constexpr int T3_DS = T3_EW + TN * 4;                      // f32[TN]: accumulator descale * -log2 e (read only in rescaled tiles)
+constexpr int T3_ROWNODE = T3_DS + TN * 4;                 // int[MAXR3] (+ pad)
+constexpr int T3_A = T3_ROWNODE + 64;                      // f32[MAXR3][128]: A_i rows of the tile (bulk copies)
+constexpr int T3_BYTES = T3_A + MAXR3 * H * 4;
+constexpr int O3_B2 = O3_TBL + NSLOT3 * T3_BYTES;          // f32[128]: b2 * -log2 e
+constexpr int O3_BAR = O3_B2 + H * 4;
+constexpr int B3_FULL = 0, B3_EMPTY = B3_FULL + 8 * N_STAGE, B3_TBL = B3_EMPTY + 8 * N_STAGE, B3_TFREE = B3_TBL + 8 * NSLOT3,
+              B3_TFULL = B3_TFREE + 8 * NSLOT3, B3_TEMPTY = B3_TFULL + 8 * NACC3, B3_PFULL = B3_TEMPTY + 8 * NACC3,
+              B3_PEMPTY = B3_PFULL + 16, B3_W = B3_PEMPTY + 16, B3_TMEMSLOT = B3_W + 8;
+constexpr int SMEM3_BYTES = O3_BAR + B3_TMEMSLOT + 16 + 1024;
+static_assert(SMEM3_BYTES <= 232448, "k_edge_v3 exceeds the 227 KB of shared memory a CTA can opt into");
+static_assert(O3_PANEL % 128 == 0 && T3_A % 16 == 0 && T3_BYTES % 16 == 0 && O3_TBL % 16 == 0, "TMA destinations need their alignment");
+constexpr int REGS3_EPI = 56, REGS3_CTRL = 56, REGS3_PROD = 80;   // 8 x 32 x 56 + 4 x 32 x 56 + 16 x 32 x 80 = 62,464
+
+// operand position p (0..127) -> channel (see "K permutation" above)
+__host__ __device__ constexpr int chan_of_pos(int p) { return (p & 4) ? 64 + 4 * (p >> 3) + (p & 3) : 4 * (p >> 3) + (p & 3); }
+
+struct Tile3 {
+  int b, nc, ncc4, slot0, nrt;
+  const int* rows;
+};
+
+// Warp-synchronous walk over the CTA's contiguous slice of the GCL work items (one item = one tile: k_plan_items
+// builds them with the same rows-per-tile rule, col_pad = 4, max_rows = MAXR3).
+struct TileIter3 {
+  const int4* list;
+  const int* rowlist;
+  int N, wi_end, wi, rt, cache_base, lane;
+  int4 cache;
+  __device__ TileIter3(const Plan& p, int N_) : N(N_), rt(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31) {
+    list = p.items;
+    rowlist = p.rowidx;
+    const int total = *p.n_items;
+    const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
+    wi = c * per + min(c, extra);
+    wi_end = wi + per + (c < extra ? 1 : 0);
+    cache = make_int4(0, 0, 0, 0);
+  }
+  __device__ bool next(Tile3& t) {
+    while (wi < wi_end) {
+      if (wi - cache_base >= 32) {
+        cache_base = wi;
+        cache = list[min(wi + lane, wi_end - 1)];
+      }
+      const int src = wi - cache_base;
+      const int b = __shfl_sync(0xffffffffu, cache.x, src), r_begin = __shfl_sync(0xffffffffu, cache.y, src);
+      const int r_count = __shfl_sync(0xffffffffu, cache.z, src), nc = __shfl_sync(0xffffffffu, cache.w, src);
+      const int ncc4 = (nc + 3) & ~3;
+      const int per = min(TN / max(ncc4, 4), MAXR3);
+      if (rt >= r_count || nc <= 0) { wi += 1; rt = 0; continue; }
+      t.b = b; t.nc = nc; t.ncc4 = ncc4; t.slot0 = r_begin + rt; t.nrt = min(per, r_count - rt);
+      t.rows = rowlist + (size_t)b * N;
+      rt += per;
+      return true;
+    }
+    return false;
+  }
+};
+
+template <bool PROF = false>
+__global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArgs a, const uint32_t* __restrict__ w2p,
+                                                                const __grid_constant__ CUtensorMap tm_b,
+                                                                unsigned long long* __restrict__ prof = nullptr) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int N = gm.N;
+  const uint32_t bars = sbase + O3_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + O3_BAR + B3_TMEMSLOT);
+  float* b2s = reinterpret_cast<float*>(sm + O3_B2);
+
+  unsigned long long pc[4] = {0, 0, 0, 0};
+  const long long t_begin = PROF ? clock64() : 0;
+  auto wait_on = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (PROF) { const long long c0 = clock64(); mbar_wait(bar, parity); pc[slot] += (unsigned long long)(clock64() - c0); }
+    else mbar_wait(bar, parity);
+  };
+  auto wait_relaxed = [&](uint32_t bar, uint32_t parity, int slot) {
+    if (PROF) { const long long c0 = clock64(); mbar_wait_relaxed(bar, parity); pc[slot] += (unsigned long long)(clock64() - c0); }
+    else mbar_wait_relaxed(bar, parity);
+  };
+  auto prof_flush = [&](int base) {
+    if (PROF && lane == 0) {
+      unsigned long long* o = prof + (size_t)blockIdx.x * 16 + base;
+      o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = (unsigned long long)(clock64() - t_begin);
+    }
+  };
+
+  if (tid == 0) {
+    for (int i = 0; i < N_STAGE; ++i) { mbar_init(bars + B3_FULL + 8 * i, N_PROD_WARPS); mbar_init(bars + B3_EMPTY + 8 * i, 1); }
+    for (int i = 0; i < NSLOT3; ++i) { mbar_init(bars + B3_TBL + 8 * i, 1); mbar_init(bars + B3_TFREE + 8 * i, N_EPI_WARPS); }
+    for (int i = 0; i < NACC3; ++i) { mbar_init(bars + B3_TFULL + 8 * i, 1); mbar_init(bars + B3_TEMPTY + 8 * i, N_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bars + B3_PFULL + 8 * i, 1); mbar_init(bars + B3_PEMPTY + 8 * i, N_PROD_WARPS); }
+    mbar_init(bars + B3_W, N_EPI_WARPS);
+    fence_barrier_init();
+  }
+  if (tid < H) b2s[tid] = a.b2[tid] * -1.4426950408889634f;
+  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp >= W_MMA && warp < W_PROD) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS3_CTRL));
+    if (warp >= W_TBL && warp < W_TBL + N_TBL_WARPS) {
+      // =================================== table warps =================================================================
+      const int tw = warp - W_TBL;
+      TileIter3 iter(a.plan, N);
+      Tile3 cur;
+      int q = -1, prev_b = -1;
+      for (int t = 0;; ++t) {
+        const int slot = t & (NSLOT3 - 1);
+        const bool more = iter.next(cur);
+        bool first = false;
+        if (more && cur.b != prev_b) { first = true; ++q; prev_b = cur.b; }
+        if (t % N_TBL_WARPS != tw) { if (!more) break; continue; }
+        if (t >= NSLOT3) wait_relaxed(bars + B3_TFREE + 8 * slot, ((t - NSLOT3) / NSLOT3) & 1, 0);
+        uint8_t* tb = sm + O3_TBL + slot * T3_BYTES;
+        int* hdr = reinterpret_cast<int*>(tb + T3_HDR);
+        if (more) {
+          const size_t gb = (size_t)cur.b * N;
+          const int Et = cur.nrt * cur.ncc4;
+          if (first) {                                       // this molecule's B panel: one tiled TMA load
+            const int buf = q & 1;
+            if (q >= 2) wait_relaxed(bars + B3_PEMPTY + 8 * buf, ((q - 2) >> 1) & 1, 1);   // producers left molecule q-2
+            if (lane == 0) {
+              mbar_expect_tx(bars + B3_PFULL + 8 * buf, (uint32_t)N * H * 4);
+              tma_load_2d(sbase + O3_PANEL + buf * PANEL_BYTES, &tm_b, H, cur.b * N, bars + B3_PFULL + 8 * buf);
+            }
+          }
+          if (lane == 0) {
+            hdr[0] = Et; hdr[1] = cur.nrt; hdr[2] = cur.ncc4; hdr[3] = cur.b; hdr[4] = first ? 1 : 0; hdr[5] = q;
+            mbar_expect_tx_only(bars + B3_TBL + 8 * slot, (uint32_t)cur.nrt * H * 4);
+          }
+          __syncwarp();
+          int node_r = 0;
+          if (lane < cur.nrt) {                              // A_i rows of the tile: 512-byte bulk copies into the slot
+            node_r = cur.rows[cur.slot0 + lane];
+            reinterpret_cast<int*>(tb + T3_ROWNODE)[lane] = node_r;
+            bulk_g2s(smem_u32(tb + T3_A) + lane * (H * 4), a.AB + (gb + node_r) * 2 * H, H * 4, bars + B3_TBL + 8 * slot);
+          }
+          bool any_rescale = false;
+          const int8_t* em = a.edge_mask ? a.edge_mask + gb * N : nullptr;
+#pragma unroll 2
+          for (int e = lane; e < TN; e += 32) {
+            int rr = e / cur.ncc4;
+            int jj = e - rr * cur.ncc4;
+            const bool valid = rr < cur.nrt && jj < cur.nc;    // padding slots mirror a real edge with weight 0
+            rr = min(rr, cur.nrt - 1); jj = min(jj, cur.nc - 1);
+            const int i = __shfl_sync(0xffffffffu, node_r, rr);
+            const int j = a.plan.colidx[gb + jj];
+            const float4 xi = a.x4[gb + i], xj = a.x4[gb + j], yi = a.x04[gb + i], yj = a.x04[gb + j];
+            const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            const float d = dx * dx + dy * dy + dz * dz;                       // egnn.py:297-298
+            const float ex = yi.x - yj.x, ey = yi.y - yj.y, ez = yi.z - yj.z;
+            const float d0 = ex * ex + ey * ey + ez * ez;                      // egnn.py:220
+            const float bound = a.ABmax[(gb + i) * 2] + a.ABmax[(gb + j) * 2 + 1] + d * a.wdmax + d0 * a.w0max;
+            float sc = 1.0f;
+            if (!(bound <= F16_TARGET)) {
+              const int ex2 = ((__float_as_int(bound) >> 23) & 0xff) - 127;
+              sc = __int_as_float(max(127 + 13 - ex2, 1) << 23);
+            }
+            any_rescale |= (sc != 1.0f);
+            float ew = 0.f;
+            if (valid) ew = em ? (float)em[(size_t)i * N + j] : 1.0f;          // egnn.py:55-58 (int8 value, multiplied)
+            reinterpret_cast<float4*>(tb + T3_REC)[e] =
+                make_float4(d, d0, __int_as_float((j * (H * 4)) | ((rr * (H * 4)) << 16)), sc);
+            reinterpret_cast<float*>(tb + T3_EW)[e] = ew * -0.6931471805599453f;
+            reinterpret_cast<float*>(tb + T3_DS)[e] = (a.w2_descale / sc) * -1.4426950408889634f;
+          }
+          any_rescale = __any_sync(0xffffffffu, any_rescale);
+          if (lane == 0) hdr[6] = any_rescale ? 1 : 0;
+        } else if (lane == 0) {
+          hdr[0] = 0;                                        // end marker travels through the whole pipeline
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bars + B3_TBL + 8 * slot);
+        if (!more) break;
+      }
+      if (warp == W_TBL) prof_flush(0);
+    } else if (warp == W_MMA) {
+      // =================================== MMA issuer ===================================================================
+      if (lane == 0) {
+        mbar_wait(bars + B3_W, 0);                           // W2 hi | lo are in tensor memory
+        tc_fence_after();
+        int acc = 0, use = 0;
+        for (int t = 0;; ++t) {
+          const int s = t & (N_STAGE - 1), slot = t & (NSLOT3 - 1);
+          wait_relaxed(bars + B3_FULL + 8 * s, (t / N_STAGE) & 1, 0);
+          // the epilogue drained this accumulator (also before the end marker: its plain arrive below must not land in the
+          // phase a still-running commit of tile t-3 is about to complete)
+          if (use > 0) wait_on(bars + B3_TEMPTY + 8 * acc, (use - 1) & 1, 1);
+          const int Et = reinterpret_cast<const int*>(sm + O3_TBL + slot * T3_BYTES + T3_HDR)[0];
+          if (Et <= 0) { mbar_arrive(bars + B3_TFULL + 8 * acc); break; }
+          tc_fence_after();
+          const uint32_t bhi = sbase + O3_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
+          const uint32_t dcol = tmem + TM_ACC + acc * TN;
+          const uint32_t idesc = umma_idesc(128, max(16, (Et + 15) & ~15));
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint64_t b_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
+            const uint32_t a_hi = tmem + TM_W + ks * 8, a_lo = tmem + TM_W + 64 + ks * 8;
+            umma_f16_ts(dcol, a_lo, b_hi, idesc, ks > 0);
+            umma_f16_ts(dcol, a_hi, b_lo, idesc, 1);
+            umma_f16_ts(dcol, a_hi, b_hi, idesc, 1);
+          }
+          umma_commit(bars + B3_EMPTY + 8 * s);
+          umma_commit(bars + B3_TFULL + 8 * acc);
+          pc[2] += 1;
+          if (++acc == NACC3) { acc = 0; ++use; }
+        }
+        prof_flush(8);
+      }
+    }
+  } else if (warp >= W_PROD) {
+    // =================================== producers =======================================================================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS3_PROD));
+    const int pw = warp - W_PROD;
+    const int kc = lane & 15, esub = lane >> 4;
+    float2 wdr[4], w0r[4];
+    {
+      const float4 d0v = __ldg(reinterpret_cast<const float4*>(a.wd + 4 * kc)), d1v = __ldg(reinterpret_cast<const float4*>(a.wd + 64 + 4 * kc));
+      const float4 z0v = __ldg(reinterpret_cast<const float4*>(a.w0 + 4 * kc)), z1v = __ldg(reinterpret_cast<const float4*>(a.w0 + 64 + 4 * kc));
+      wdr[0] = make_float2(d0v.x, d0v.y); wdr[1] = make_float2(d0v.z, d0v.w); wdr[2] = make_float2(d1v.x, d1v.y); wdr[3] = make_float2(d1v.z, d1v.w);
+      w0r[0] = make_float2(z0v.x, z0v.y); w0r[1] = make_float2(z0v.z, z0v.w); w0r[2] = make_float2(z1v.x, z1v.y); w0r[3] = make_float2(z1v.z, z1v.w);
+    }
+    const uint8_t* panel = sm + O3_PANEL + kc * 16;
+    const int e_base = 4 * (2 * pw + esub);                  // this thread's four consecutive edges (one tile row: rows are padded to x4)
+    for (int t = 0;; ++t) {
+      const int s = t & (N_STAGE - 1), slot = t & (NSLOT3 - 1);
+      wait_on(bars + B3_TBL + 8 * slot, (t / NSLOT3) & 1, 0);
+      const uint8_t* tb = sm + O3_TBL + slot * T3_BYTES;
+      const int* hdr = reinterpret_cast<const int*>(tb + T3_HDR);
+      const int Et = hdr[0];
+      if (Et > 0 && hdr[4]) {                                // first tile of a molecule: switch panel buffers
+        const int q = hdr[5], buf = q & 1;
+        if (q >= 1) { __syncwarp(); if (lane == 0) mbar_arrive(bars + B3_PEMPTY + 8 * (buf ^ 1)); }
+        wait_on(bars + B3_PFULL + 8 * buf, (q >> 1) & 1, 2);
+        panel = sm + O3_PANEL + buf * PANEL_BYTES + kc * 16;
+      }
+      if (t >= N_STAGE) wait_on(bars + B3_EMPTY + 8 * s, ((t - N_STAGE) / N_STAGE) & 1, 1);
+      if (Et > 0) {
+        if (e_base < Et) {
+          const float4* recs = reinterpret_cast<const float4*>(tb + T3_REC);
+          uint8_t* bhi = sm + O3_ST + s * STAGE_BYTES + kc * B_LBO;
+          uint8_t* blo = bhi + B_BYTES;
+          const bool rescale = hdr[6] != 0;
+          const float4 r0 = recs[e_base];
+          const uint8_t* arow = tb + T3_A + kc * 16 + (__float_as_int(r0.z) >> 16);
+          const float4 a0 = *reinterpret_cast<const float4*>(arow), a1 = *reinterpret_cast<const float4*>(arow + 256);
+          const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const int e = e_base + it;
+            const float4 rec = it == 0 ? r0 : recs[e];
+            const uint8_t* bp = panel + (__float_as_int(rec.z) & 0xffff);
+            const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 256);
+            const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+            const float2 dd = make_float2(rec.x, rec.x), dd0 = make_float2(rec.y, rec.y);
+            float2 u[4], sv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)                       // egnn.py:49-50 in the log2 domain, two channels per instruction
+              u[k] = __ffma2_rn(dd0, w0r[k], __ffma2_rn(dd, wdr[k], __fadd2_rn(av[k], bv[k])));
+            usig4(u[0], u[1], sv[0], sv[1]);
+            usig4(u[2], u[3], sv[2], sv[3]);
+            if (rescale) {                                   // rare: diverging samples only (tile-uniform)
+#pragma unroll
+              for (int k = 0; k < 4; ++k) sv[k] = __fmul2_rn(sv[k], make_float2(rec.w, rec.w));
+            }
+            uint4 hi, lo;
+            split2v(sv[0], hi.x, lo.x); split2v(sv[1], hi.y, lo.y);
+            split2v(sv[2], hi.z, lo.z); split2v(sv[3], hi.w, lo.w);
+            *reinterpret_cast<uint4*>(bhi + e * 16) = hi;
+            *reinterpret_cast<uint4*>(blo + e * 16) = lo;
+          }
+        }
+        fence_proxy_async();
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + B3_FULL + 8 * s);
+      if (Et <= 0) break;
+    }
+    if (warp == W_PROD) prof_flush(4);
+  } else {
+    // =================================== epilogue warps ====================================================================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS3_EPI));   // first: the producers' increase waits for it
+    const int q = warp & 3;                                  // TMEM lane quarter
+    const int hw = warp >> 2;                                // prologue: 0 -> W2 hi, 1 -> W2 lo; main loop: row parity
+    const int c = q * 32 + lane;                             // output channel = TMEM lane
+    {
+      // W2 (this thread's output row, hi or lo half: 64 packed words) -> tensor memory columns [64 hw, 64 hw + 64)
+      const uint4* src = reinterpret_cast<const uint4*>(w2p + ((size_t)hw * H + c) * 64);
+      const uint32_t tw = tmem + ((uint32_t)(q * 32) << 16) + TM_W + hw * 64;
+#pragma unroll 1
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint4 v = __ldg(src + g * 4 + i);
+          r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
+        }
+        TMEM_ST_X16(tw + g * 16, r);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bars + B3_W);
+    }
+    const float bias = b2s[c];
+    const float2 bias2 = make_float2(bias, bias);
+    const float ds0 = a.w2_descale * -1.4426950408889634f;
+    int acc = 0, use = 0;
+    for (int t = 0;; ++t) {
+      const int slot = t & (NSLOT3 - 1);
+      wait_on(bars + B3_TBL + 8 * slot, (t / NSLOT3) & 1, 0);
+      wait_on(bars + B3_TFULL + 8 * acc, use & 1, 1);
+      tc_fence_after();
+      const uint8_t* tb = sm + O3_TBL + slot * T3_BYTES;
+      const int* hdr = reinterpret_cast<const int*>(tb + T3_HDR);
+      const int Et = hdr[0];
+      if (Et <= 0) break;
+      const int nrt = hdr[1], ncc4 = hdr[2];
+      const size_t gb = (size_t)hdr[3] * N;
+      const bool rescale = hdr[6] != 0;
+      const float* ews = reinterpret_cast<const float*>(tb + T3_EW);
+      const float* dss = reinterpret_cast<const float*>(tb + T3_DS);
+      const int* rownode = reinterpret_cast<const int*>(tb + T3_ROWNODE);
+      const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + acc * TN;
+      // four edges of this thread's channel: u = -log2e (D descale + b2) (one packed FMA each pair), u * sigmoid, times the
+      // edge weight (which carries the -ln2), into two packed partial sums -- fixed order, deterministic.
+      auto quad = [&](const uint32_t* r, int col, float2& sa, float2& sb) {
+        const float4 ew = *reinterpret_cast<const float4*>(ews + col);
+        float2 d01 = make_float2(ds0, ds0), d23 = d01;
+        if (rescale) { const float4 dv = *reinterpret_cast<const float4*>(dss + col); d01 = make_float2(dv.x, dv.y); d23 = make_float2(dv.z, dv.w); }
+        const float2 u01 = __ffma2_rn(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), d01, bias2);
+        const float2 u23 = __ffma2_rn(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), d23, bias2);
+        float2 s01, s23;
+        usig4(u01, u23, s01, s23);
+        sa = __ffma2_rn(s01, make_float2(ew.x, ew.y), sa);
+        sb = __ffma2_rn(s23, make_float2(ew.z, ew.w), sb);
+      };
+      for (int rr = (hw + t) & 1; rr < nrt; rr += 2) {       // the two warp halves take alternate rows
+        const int col0 = rr * ncc4;
+        const int n8 = ncc4 >> 3;
+        float2 sa = make_float2(0.f, 0.f), sb = sa;
+        uint32_t ra[8], rb[8];
+        if (n8 > 0) TMEM_LD_X8(tacc + col0, ra);
+        for (int k = 0; k < n8; k += 2) {                    // software-pipelined: the next 8 columns load while these are reduced
+          tmem_ld_wait();
+          if (k + 1 < n8) TMEM_LD_X8(tacc + col0 + (k + 1) * 8, rb);
+          quad(ra, col0 + k * 8, sa, sb);
+          quad(ra + 4, col0 + k * 8 + 4, sa, sb);
+          if (k + 1 < n8) {
+            tmem_ld_wait();
+            if (k + 2 < n8) TMEM_LD_X8(tacc + col0 + (k + 2) * 8, ra);
+            quad(rb, col0 + (k + 1) * 8, sa, sb);
+            quad(rb + 4, col0 + (k + 1) * 8 + 4, sa, sb);
+          }
+        }
+        if (ncc4 & 4) {
+          uint32_t r4[4];
+          TMEM_LD_X4(tacc + col0 + n8 * 8, r4);
+          tmem_ld_wait();
+          quad(r4, col0 + n8 * 8, sa, sb);
+        }
+        const float accv = (sa.x + sa.y) + (sb.x + sb.y);
+        a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(bars + B3_TEMPTY + 8 * acc); mbar_arrive(bars + B3_TFREE + 8 * slot); }
+      if (++acc == NACC3) { acc = 0; ++use; }
+    }
+    if (warp == W_EPI) prof_flush(12);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_MMA) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------------------
+// edge_mlp.2 weight (out = 128 rows, in = 128, row-major) -> [hi | lo][out][64 words], word w of a row = fp16 pair of
+// operand positions (2w, 2w+1), positions permuted by chan_of_pos, values scaled by -ln2 (log2-domain first layer,
+// kernels_tc.cuh) and by the power of two that puts max|W| in [2^13, 2^14). Returns the offset in halves; *descale = 1/scale.
+inline size_t pack_w2_v3(const std::vector<float>& W_in, std::vector<__half>& blob, float* descale) {
+  while (blob.size() % 64) blob.push_back(__float2half(0.f));
+  const size_t off = blob.size();
+  blob.resize(off + 2 * (size_t)H * H);
+  std::vector<float> W(W_in.size());
+  float mx = 0.f;
+  for (size_t i = 0; i < W.size(); ++i) { W[i] = (float)((double)W_in[i] * NEG_LN2); mx = std::max(mx, std::fabs(W[i])); }
+  int ex = 0;
+  if (mx > 0.f && std::isfinite(mx)) { std::frexp(mx, &ex); ex -= 1; }
+  const int sh = std::min(std::max(13 - ex, -40), 40);
+  const float scale = std::ldexp(1.0f, sh);
+  *descale = std::ldexp(1.0f, -sh);
+  for (int c = 0; c < H; ++c)
+    for (int p = 0; p < H; ++p) {
+      const float v = W[(size_t)c * H + chan_of_pos(p)] * scale;
+      const __half hi = __float2half_rn(v);
+      blob[off + (size_t)c * H + p] = hi;
+      blob[off + (size_t)H * H + (size_t)c * H + p] = __float2half_rn(v - __half2float(hi));
+    }
+  return off;
+}
+
+inline bool supports(const Geom& gm) { return gm.graph_type == 0 && gm.N <= PANEL_N; }
+
+// Tensor map of one (B*N, 256) fp32 projection buffer: box = the B half (128 floats) of one molecule's N rows.
+typedef CUresult (*encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline encode_tiled_fn get_encode_tiled() {
+  static encode_tiled_fn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<encode_tiled_fn>(p);
+  return fn;
+}
+inline dl_status make_panel_map(CUtensorMap* out, const float* AB, int B, int N) {
+  encode_tiled_fn enc = get_encode_tiled();
+  if (!enc) return DL_ERR_CUDA;
+  const cuuint64_t gdim[2] = {(cuuint64_t)(2 * H), (cuuint64_t)B * N};
+  const cuuint64_t gstride[1] = {(cuuint64_t)(2 * H) * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)H, (cuuint32_t)N};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(AB), gdim, gstride, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? DL_OK : DL_ERR_CUDA;
+}
+
+inline dl_status configure3() {
+  const bool ok = cudaFuncSetAttribute(k_edge_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
+  return ok ? DL_OK : DL_ERR_CUDA;
+}
+
+inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, int num_sms, cudaStream_t st) {
+  k_edge_v3<false><<<num_sms, EDGE_TC_THREADS, SMEM3_BYTES, st>>>(gm, ea, reinterpret_cast<const uint32_t*>(w2_v3), tm, nullptr);
+}
+
+inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, int num_sms, cudaStream_t st) {
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, (size_t)num_sms * 16 * 8) != cudaSuccess) return DL_ERR_CUDA;
+  cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
+  k_edge_v3<true><<<num_sms, EDGE_TC_THREADS, SMEM3_BYTES, st>>>(gm, ea, reinterpret_cast<const uint32_t*>(w2_v3), tm, d);
+  if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
+  std::vector<unsigned long long> h((size_t)num_sms * 16);
+  cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  double avg[16] = {0};
+  for (int b = 0; b < num_sms; ++b) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)b * 16 + i] / num_sms;
+  fprintf(stderr, "[dl prof v3] cycles per CTA (avg over %d), tiles %.1f\n", num_sms, avg[10]);
+  fprintf(stderr, "[dl prof v3]  table   : wait tfree %.0f, wait pempty %.0f | total %.0f\n", avg[0], avg[1], avg[3]);
+  fprintf(stderr, "[dl prof v3]  producer: wait tbl %.0f, wait empty %.0f, wait panel %.0f | total %.0f\n", avg[4], avg[5], avg[6], avg[7]);
+  fprintf(stderr, "[dl prof v3]  mma     : wait full %.0f, wait tempty %.0f | total %.0f\n", avg[8], avg[9], avg[11]);
+  fprintf(stderr, "[dl prof v3]  epilogue: wait tbl %.0f, wait tfull %.0f | total %.0f\n", avg[12], avg[13], avg[15]);
+  return DL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Self test of the TS form: A (128 x 128, hi | lo) written to tensor memory with tcgen05.st in the layout k_edge_v3
+// uses, B (256 rows, K-major canonical layout) in shared memory, 3xFP16 chain, against fp64 on the host.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) k_umma_probe_ts(const uint32_t* __restrict__ A /*[2][128][64] words*/,
+                                                          const __half* __restrict__ Bm /*[2][kc][256][8]*/,
+                                                          float* __restrict__ D /*[128][256]*/) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const uint32_t sbase = smem_u32(sm);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t bar = sbase + P_OFF_BAR;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + P_OFF_BAR + 32);
+  if (tid == 0) { mbar_init(bar, 1); fence_barrier_init(); }
+  for (int idx = tid; idx < 2 * KC * PN; idx += 128) {
+    const int copy = idx / (KC * PN), rem = idx % (KC * PN), kcx = rem / PN, row = rem % PN;
+    *reinterpret_cast<uint4*>(sm + (copy ? P_OFF_BLO : P_OFF_BHI) + kcx * P_LBO + row * 16) =
+        *reinterpret_cast<const uint4*>(Bm + (size_t)idx * 8);
+  }
+  fence_proxy_async();
+  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  {
+    const int c = warp * 32 + lane;
+    for (int half = 0; half < 2; ++half) {
+      const uint32_t tw = tmem + ((uint32_t)(warp * 32) << 16) + 256 + half * 64;   // A at columns 256..383, D at 0..255
+      for (int g = 0; g < 4; ++g) {
+        uint32_t r[16];
+        for (int i = 0; i < 16; ++i) r[i] = A[((size_t)half * H + c) * 64 + g * 16 + i];
+        TMEM_ST_X16(tw + g * 16, r);
+      }
+    }
+    tmem_st_wait();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (tid == 0) {
+    const uint32_t idesc = umma_idesc(128, 256);
+    for (int ks = 0; ks < 8; ++ks) {
+      const uint64_t b_hi = umma_desc(sbase + P_OFF_BHI + ks * 2 * P_LBO, P_LBO, SBO), b_lo = umma_desc(sbase + P_OFF_BLO + ks * 2 * P_LBO, P_LBO, SBO);
+      const uint32_t a_hi = tmem + 256 + ks * 8, a_lo = tmem + 256 + 64 + ks * 8;
+      umma_f16_ts(tmem, a_lo, b_hi, idesc, ks > 0);
+      umma_f16_ts(tmem, a_hi, b_lo, idesc, 1);
+      umma_f16_ts(tmem, a_hi, b_hi, idesc, 1);
+    }
+    umma_commit(bar);
+  }
+  mbar_wait(bar, 0);
+  tc_fence_after();
+  const uint32_t tlane = tmem + ((uint32_t)(warp * 32) << 16);
+  for (int c0 = 0; c0 < PN; c0 += 8) {
+    uint32_t r[8];
+    TMEM_LD_X8(tlane + c0, r);
+    tmem_ld_wait();
+    for (int u = 0; u < 8; ++u) D[(size_t)(warp * 32 + lane) * PN + c0 + u] = __uint_as_float(r[u]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+inline dl_status selftest_ts(float* max_abs_err, float* max_rel_err) {
+  std::vector<float> A((size_t)H * H), Bv((size_t)PN * H);
+  uint32_t s = 4321u;
+  auto rnd = [&]() { s = s * 1664525u + 1013904223u; return ((s >> 8) & 0xFFFF) / 65536.0f - 0.5f; };
+  for (auto& v : A) v = rnd() * 0.2f;
+  for (auto& v : Bv) v = rnd() * 3.0f;
+  std::vector<__half> Ap(2 * (size_t)H * H), Bp(2 * (size_t)KC * PN * 8);
+  for (int c = 0; c < H; ++c)
+    for (int k = 0; k < H; ++k) {
+      const float v = A[(size_t)c * H + k];
+      const __half hi = __float2half_rn(v);
+      Ap[(size_t)c * H + k] = hi;
+      Ap[(size_t)H * H + (size_t)c * H + k] = __float2half_rn(v - __half2float(hi));
+    }
+  for (int kc = 0; kc < KC; ++kc)
+    for (int r = 0; r < PN; ++r)
+      for (int u = 0; u < 8; ++u) {
+        const float v = Bv[(size_t)r * H + kc * 8 + u];
+        const __half hi = __float2half_rn(v);
+        Bp[((size_t)kc * PN + r) * 8 + u] = hi;
+        Bp[(size_t)KC * PN * 8 + ((size_t)kc * PN + r) * 8 + u] = __float2half_rn(v - __half2float(hi));
+      }
+  __half *dA = nullptr, *dB = nullptr;
+  float* dD = nullptr;
+  if (cudaMalloc(&dA, Ap.size() * 2) != cudaSuccess || cudaMalloc(&dB, Bp.size() * 2) != cudaSuccess ||
+      cudaMalloc(&dD, (size_t)H * PN * 4) != cudaSuccess)
+    return DL_ERR_CUDA;
+  cudaMemcpy(dA, Ap.data(), Ap.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, Bp.data(), Bp.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemset(dD, 0, (size_t)H * PN * 4);
+  cudaFuncSetAttribute(k_umma_probe_ts, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES);
+  k_umma_probe_ts<<<1, 128, P_SMEM_BYTES>>>(reinterpret_cast<const uint32_t*>(dA), dB, dD);
+  cudaError_t err = cudaDeviceSynchronize();
+  std::vector<float> D((size_t)H * PN);
+  cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost);
+  cudaFree(dA); cudaFree(dB); cudaFree(dD);
+  if (err != cudaSuccess) {
+    fprintf(stderr, "[dl selftest] k_umma_probe_ts failed: %s\n", cudaGetErrorString(err));
+    return DL_ERR_CUDA;
+  }
+  double ma = 0, mref = 0;
+  for (int m = 0; m < H; ++m)
+    for (int n = 0; n < PN; ++n) {
+      double ref = 0;
+      for (int k = 0; k < H; ++k) ref += (double)A[(size_t)m * H + k] * (double)Bv[(size_t)n * H + k];
+      ma = std::max(ma, std::fabs(ref - (double)D[(size_t)m * PN + n]));
+      mref = std::max(mref, std::fabs(ref));
+    }
+  if (max_abs_err) *max_abs_err = (float)ma;
+  if (max_rel_err) *max_rel_err = (float)(ma / std::max(mref, 1e-30));
+  fprintf(stderr, "[dl selftest] 3xFP16 UMMA 128x256x128, A in tensor memory: max abs err %.3e (rel to max |ref| %.3e)\n", ma,
+          ma / std::max(mref, 1e-30));
+  return DL_OK;
+}
+
+}  // namespace tc3
+}  // namespace dl

@@ -59,7 +59,7 @@ __global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edg
 
 // Single thread: flatten per-molecule row groups into the GCL work list. A work item is `rows_per_tile`
 // complete rows (so the segment sum over j never crosses CTAs and stays order-deterministic).
-__global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __restrict__ nr,
+__global__ void k_plan_items(int B, int tile_edges, int max_rows, int col_pad, int max_rows_gcl, const int* __restrict__ nr,
                              const int* __restrict__ nc, const int* __restrict__ nxr, int4* __restrict__ items,
                              int* __restrict__ n_items, int* __restrict__ xmols, int* __restrict__ n_xmols,
                              int4* __restrict__ xitems, int* __restrict__ n_xitems) {
@@ -68,8 +68,9 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, const int* __r
   for (int b = 0; b < B; ++b) {
     int r = nr[b], c = nc[b];
     if (r > 0 && c > 0) {
-      int per = c >= tile_edges ? 1 : tile_edges / c;
-      if (per > max_rows) per = max_rows;
+      const int cp = (c + col_pad - 1) / col_pad * col_pad;   // GCL tiles of the v3 kernel pad rows to x4 columns
+      int per = cp >= tile_edges ? 1 : tile_edges / cp;
+      if (per > max_rows_gcl) per = max_rows_gcl;
       for (int r0 = 0; r0 < r; r0 += per) items[cnt++] = make_int4(b, r0, min(per, r - r0), c);
     }
     if (nxr[b] > 0 && c > 0) {

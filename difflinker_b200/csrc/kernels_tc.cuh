@@ -172,6 +172,38 @@ __device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t adesc, uint64
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Same with the A operand read from TENSOR MEMORY (128 lanes = M rows; one 32-bit column holds two consecutive K
+// elements of a row, so a K=16 step spans 8 columns): a stationary weight matrix then costs no shared-memory space and
+// no shared-memory read bandwidth per MMA.
+__device__ __forceinline__ void umma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// registers -> tensor memory: lane l of warp w writes 16 consecutive columns of TMEM lane 32 * (w % 4) + l
+#define TMEM_ST_X16(taddr, r)                                                                                     \
+  asm volatile(                                                                                                   \
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"    \
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),       \
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])             \
+      : "memory")
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 2-D tiled TMA load (cp.async.bulk.tensor, SASS: UTMALDG): box at (c0 = innermost coordinate, c1 = row) of the tensor
+// described by `tmap` -> dense [rows][inner] box in shared memory, completion on an mbarrier.
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const void* tmap, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst),
+      "l"(tmap), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+// add to the barrier's pending transaction bytes without arriving (the arrive follows once the tables are written)
+__device__ __forceinline__ void mbar_expect_tx_only(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -593,7 +625,7 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_tc(Geom gm, EdgeArg
             float2 sv[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q)                     // egnn.py:49-50, two channels per packed instruction
-              sv[q] = silu2(__ffma2_rn(dd0, w0r[q], __ffma2_rn(dd, wdr[q], __fadd2_rn(av[q], bv[q]))));
+              sv[q] = usig2(__ffma2_rn(dd0, w0r[q], __ffma2_rn(dd, wdr[q], __fadd2_rn(av[q], bv[q]))));   // log2 domain (see pack_w2)
             if (rescale) {                                 // rare: diverging samples only (tile-uniform)
               const float sc = scv[e];
 #pragma unroll
@@ -788,9 +820,18 @@ inline dl_status configure() {
   return ok ? DL_OK : DL_ERR_CUDA;
 }
 
+// Log2-domain first layer (tcgen05 path): the node kernel's projection weights, b1, wd and w0 are pre-multiplied by
+// -log2(e) (dl_finalize_weights), so the producers form u = -log2(e) * pre directly and s' = u / (1 + 2^u) =
+// -log2(e) * silu(pre) costs no scaling multiply; the -ln(2) that undoes it is folded into this operand
+// (W2' = -ln2 * W2, computed in double before the fp16 hi/lo split).
+constexpr double NEG_LN2 = -0.6931471805599453094;
+constexpr double NEG_LOG2E = -1.4426950408889634074;
+
 // edge_mlp.2 / coord_mlp.2 weight (out=128, in=128, row-major) -> [hi|lo][kc][out][8] fp16, scaled by the power of
 // two that puts max|W| in [2^13, 2^14). Returns the offset (in halves) inside `blob`; *descale = 1/scale.
-inline size_t pack_w2(const std::vector<float>& W, std::vector<__half>& blob, float* descale) {
+inline size_t pack_w2(const std::vector<float>& W_in, std::vector<__half>& blob, float* descale) {
+  std::vector<float> W(W_in.size());
+  for (size_t i = 0; i < W.size(); ++i) W[i] = (float)((double)W_in[i] * NEG_LN2);
   while (blob.size() % 64) blob.push_back(__float2half(0.f));           // keep 128-byte alignment for the bulk copy
   const size_t off = blob.size();
   blob.resize(off + 2 * (size_t)KC * H * 8);

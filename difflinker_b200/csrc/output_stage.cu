@@ -14,7 +14,7 @@
 namespace {
 
 // One CTA per molecule; fixed-shape reduction (lane-strided partials, shuffle tree, 8 warp partials in order).
-__global__ void __launch_bounds__(256) k_restore_frame(int N, int xd, float* __restrict__ xh,
+__global__ void __launch_bounds__(256) k_restore_frame(int N, int N_pos, int xd, float* __restrict__ xh,
                                                        const float* __restrict__ positions,
                                                        const float* __restrict__ com_mask,
                                                        const int8_t* __restrict__ node_mask) {
@@ -22,12 +22,13 @@ __global__ void __launch_bounds__(256) k_restore_frame(int N, int xd, float* __r
   __shared__ float mean[3];
   const int b = blockIdx.x, tid = threadIdx.x;
   const size_t g0 = (size_t)b * N;
+  const size_t p0 = (size_t)b * N_pos;   // positions / com_mask keep the INPUT batch's padding (generate.py:165-171)
   float s[4] = {0.f, 0.f, 0.f, 0.f};
-  for (int n = tid; n < N; n += 256) {
-    const float m = com_mask[g0 + n];
-    s[0] += positions[(g0 + n) * 3 + 0] * m;
-    s[1] += positions[(g0 + n) * 3 + 1] * m;
-    s[2] += positions[(g0 + n) * 3 + 2] * m;
+  for (int n = tid; n < N_pos; n += 256) {
+    const float m = com_mask[p0 + n];
+    s[0] += positions[(p0 + n) * 3 + 0] * m;
+    s[1] += positions[(p0 + n) * 3 + 1] * m;
+    s[2] += positions[(p0 + n) * 3 + 2] * m;
     s[3] += m;
   }
 #pragma unroll
@@ -58,11 +59,17 @@ inline int fmt9(char* p, size_t cap, float v) {
 
 }  // namespace
 
+extern "C" dl_status dl_restore_frame2(int32_t B, int32_t N, int32_t N_pos, int32_t row_stride, float* xh,
+                                       const float* positions, const float* com_mask, const int8_t* node_mask,
+                                       void* stream) {
+  if (B <= 0 || N <= 0 || N_pos <= 0 || row_stride < 3 || !xh || !positions || !com_mask || !node_mask) return DL_ERR_INVALID;
+  k_restore_frame<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(N, N_pos, row_stride, xh, positions, com_mask, node_mask);
+  return cudaGetLastError() == cudaSuccess ? DL_OK : DL_ERR_CUDA;
+}
+
 extern "C" dl_status dl_restore_frame(int32_t B, int32_t N, int32_t row_stride, float* xh, const float* positions,
                                       const float* com_mask, const int8_t* node_mask, void* stream) {
-  if (B <= 0 || N <= 0 || row_stride < 3 || !xh || !positions || !com_mask || !node_mask) return DL_ERR_INVALID;
-  k_restore_frame<<<B, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(N, row_stride, xh, positions, com_mask, node_mask);
-  return cudaGetLastError() == cudaSuccess ? DL_OK : DL_ERR_CUDA;
+  return dl_restore_frame2(B, N, N, row_stride, xh, positions, com_mask, node_mask, stream);
 }
 
 extern "C" int64_t dl_format_xyz(int32_t B, int32_t N, int32_t F, const float* positions, int32_t pos_row_stride,

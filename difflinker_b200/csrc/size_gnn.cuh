@@ -185,7 +185,7 @@ dl_status dl_sizegnn_forward(dl_sizegnn* e, int32_t B, int32_t N, const float* x
   k_plan_mol<<<B, 256, 2 * N * sizeof(int), st>>>(N, gm.graph_type, edge_mask, fragment_mask, nullptr, ws.rowidx, ws.colidx,
                                                   ws.xrowidx, ws.nr, ws.nc, ws.nxr);
   LAUNCH_CHECK();
-  k_plan_items<<<1, 1, 0, st>>>(B, ET, MAXR, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols, ws.n_xmols, ws.xitems,
+  k_plan_items<<<1, 1, 0, st>>>(B, ET, MAXR, 1, MAXR, ws.nr, ws.nc, ws.nxr, ws.items, ws.n_items, ws.xmols, ws.n_xmols, ws.xitems,
                                 ws.n_xitems);
   LAUNCH_CHECK();
 

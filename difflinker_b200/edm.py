@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from . import _native
 from .noise import PredefinedNoiseSchedule
-from .utils import FoundNaNException
+from .utils import FoundNaNException, nan_exception_class
 
 
 class EDM(torch.nn.Module):
@@ -175,7 +175,7 @@ class EDM(torch.nn.Module):
             bad = st == _native.DL_NAN_DETECTED
         self.last_loop_ms = float(lib.dl_last_elapsed_ms(eng))
         if bad:
-            raise FoundNaNException(flags=flags.cpu().tolist())
+            raise nan_exception_class()(flags=flags.cpu().tolist())
         return chain
 
 
@@ -278,5 +278,5 @@ class InpaintingEDM(EDM):
             bad = st == _native.DL_NAN_DETECTED
         self.last_loop_ms = float(lib.dl_last_elapsed_ms(eng))
         if bad:
-            raise FoundNaNException(flags=flags.cpu().tolist())
+            raise nan_exception_class()(flags=flags.cpu().tolist())
         return chain

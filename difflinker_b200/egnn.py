@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _native
-from .utils import FoundNaNException
+from .utils import FoundNaNException, nan_exception_class
 
 
 class _GCLParams(nn.Module):
@@ -71,10 +71,12 @@ class Dynamics(nn.Module):
         if tanh: unsupported.append("tanh=True")
         if sin_embedding: unsupported.append("sin_embedding=True")
         if aggregation_method != 'sum': unsupported.append(f"aggregation_method={aggregation_method!r}")
-        if normalization is not None: unsupported.append(f"normalization={normalization!r}")
+        # `normalization` is accepted and ignored exactly as the reference does for model='egnn_dynamics': it is only
+        # forwarded to GNN (src/egnn.py:355-368); every configs/*.yml and train_difflinker.py's default set
+        # normalization='batch_norm', so every published checkpoint carries it in its hyper-parameters.
         if not isinstance(activation, nn.SiLU): unsupported.append(f"activation={activation!r}")
         if unsupported:
-            # none of the published configs (configs/*.yml) uses these; refuse rather than silently differ
+            # no published config (configs/*.yml) uses these; refuse rather than silently differ
             raise NotImplementedError("difflinker_b200 hot path does not implement: " + ", ".join(unsupported))
         self.device = device
         self.n_dims = n_dims
@@ -196,7 +198,7 @@ class Dynamics(nn.Module):
             _native.check(st, "dl_dynamics_forward_host")
             bad = st == _native.DL_NAN_DETECTED
         if bad:
-            raise FoundNaNException(flags=flags.cpu().tolist())
+            raise nan_exception_class()(flags=flags.cpu().tolist())
         return out
 
     def get_edges(self, n_nodes, batch_size):

@@ -18,7 +18,9 @@ GEOM_IDX2ATOM = {0: 'C', 1: 'O', 2: 'N', 3: 'F', 4: 'S', 5: 'Cl', 6: 'Br', 7: 'I
 
 def restore_frame(chain0, positions, com_mask, node_mask):
     """In place on a CUDA tensor: chain0[..., :3] += mean(positions * com_mask over atoms) * node_mask
-    (generate.py:165-171). `chain0` is (B,N,3) or (B,N,3+F) -- e.g. `chain[0]` straight from `sample_chain`."""
+    (generate.py:165-171). `chain0` is (B,N,3) or (B,N,3+F) -- e.g. `chain[0]` straight from `sample_chain`.
+    `positions` / `com_mask` may have another padded length than `chain0` / `node_mask`: generate.py passes the INPUT
+    batch's positions and masks while the chain has the template's length (sampled linker sizes)."""
     if not chain0.is_cuda:
         raise RuntimeError("restore_frame runs on the GPU (no CPU fallback); move the tensors to the device")
     if chain0.dtype != torch.float32 or not chain0.is_contiguous():
@@ -26,13 +28,16 @@ def restore_frame(chain0, positions, com_mask, node_mask):
     B, N, xd = chain0.shape
     dev = chain0.device
     pos = positions.to(device=dev, dtype=torch.float32).contiguous()
-    cm = com_mask.to(device=dev, dtype=torch.float32).reshape(B, N).contiguous()
+    if pos.dim() != 3 or pos.shape[0] != B or pos.shape[2] != 3:
+        raise ValueError(f"positions must be (B, N_pos, 3), got {tuple(pos.shape)}")
+    n_pos = pos.shape[1]
+    cm = com_mask.to(device=dev, dtype=torch.float32).reshape(B, n_pos).contiguous()
     nm = node_mask.to(device=dev).reshape(B, N).to(torch.int8).contiguous()
     lib = _native.load_library()
     with torch.cuda.device(dev):
         st = torch.cuda.current_stream().cuda_stream
-        _native.check(lib.dl_restore_frame(B, N, xd, chain0.data_ptr(), pos.data_ptr(), cm.data_ptr(), nm.data_ptr(), st),
-                      "dl_restore_frame")
+        _native.check(lib.dl_restore_frame2(B, N, n_pos, xd, chain0.data_ptr(), pos.data_ptr(), cm.data_ptr(),
+                                            nm.data_ptr(), st), "dl_restore_frame2")
     return chain0
 
 

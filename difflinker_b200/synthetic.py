@@ -64,6 +64,7 @@ def model_hparams(spec: WorkloadSpec) -> dict:
         train_data_prefix='MOAD_train.full' if spec.pocket else ('geom_train' if spec.F == 9 else 'zinc_train'),
         val_data_prefix='val', center_of_mass='fragments', inpainting=False, anchors_context=spec.anchors_context,
         graph_type=spec.graph_type,
+        normalization='batch_norm',   # every configs/*.yml sets it; the reference ignores it for egnn_dynamics (egnn.py:355-368)
     )
     hp.update(spec.hparams)
     return hp

@@ -171,8 +171,8 @@ dl_status dl_cut_graph_stats(dl_engine* e, int64_t* out);
 /* Self-test of the tcgen05 edge-MLP tile against the SIMT path on random data. Blocking.
  * Returns DL_OK and writes the max abs/rel error. */
 dl_status dl_selftest_tc(dl_engine* e, float* max_abs_err, float* max_rel_err);
-/* Same with the B operand in the MN-major canonical layout (b_mn_major != 0; instruction-descriptor bit 16): the layout a
- * lane = channel producer can fill with 16-byte stores -- groundwork for running the first Linear on the tensor cores. */
+/* Same with the B operand in the MN-major canonical layout (b_mn_major == 1; instruction-descriptor bit 16), or with the
+ * A operand in tensor memory (b_mn_major == 2: the TS form the third-generation GCL kernel uses for the stationary W2). */
 dl_status dl_selftest_tc_layout(dl_engine* e, int32_t b_mn_major, float* max_abs_err, float* max_rel_err);
 
 /*
@@ -185,6 +185,11 @@ dl_status dl_selftest_tc_layout(dl_engine* e, int32_t b_mn_major, float* max_abs
  */
 dl_status dl_restore_frame(int32_t B, int32_t N, int32_t row_stride, float* xh, const float* positions,
                            const float* com_mask, const int8_t* node_mask, void* stream);
+/* Same when the sampled batch was re-templated with sampled linker sizes (create_templates_for_linker_generation,
+ * datasets.py:483-512): `xh` / `node_mask` have the template's padded length N while `positions` / `com_mask` keep the
+ * input batch's padded length N_pos (generate.py:165-171 mixes exactly these two). */
+dl_status dl_restore_frame2(int32_t B, int32_t N, int32_t N_pos, int32_t row_stride, float* xh, const float* positions,
+                            const float* com_mask, const int8_t* node_mask, void* stream);
 
 /*
  * dl_format_xyz -- visualizer.save_xyz_file (src/visualizer.py:14-31) for a whole batch: the text of the B .xyz files

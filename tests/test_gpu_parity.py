@@ -288,10 +288,11 @@ def test_full_size_forward_vs_oracle_sampled_molecules():
     assert rel_err(got[idx], want) <= REL_TOL
 
 
-@pytest.mark.parametrize("b_mn_major", [0, 1])
+@pytest.mark.parametrize("b_mn_major", [0, 1, 2])
 def test_umma_selftest_3xfp16(b_mn_major):
     """tcgen05 building block in isolation: one 128x256x128 hi/lo-split UMMA chain vs fp64 on the host, with the B operand
-    in the K-major layout the kernels use and in the MN-major canonical layout (next step of the producer redesign)."""
+    in the K-major layout the kernels use (0), in the MN-major canonical layout (1), and with the A operand (the
+    stationary W2) in tensor memory as k_edge_v3 keeps it (2)."""
     import ctypes as C
     from difflinker_b200 import _native
     dyn, hp = helpers.build_dynamics(helpers.EXTRA_SPECS["small_fc"], 0)
@@ -438,6 +439,27 @@ def test_restore_frame_vs_oracle():
         assert torch.equal(got[..., 3:], chain0[..., 3:])
         got3 = output.restore_frame(chain0[..., :3].contiguous().to(dev()), positions, com_mask, data['atom_mask']).cpu()
         assert torch.equal(got3, got[..., :3])
+
+
+def test_restore_frame_with_sampled_linker_sizes():
+    """generate.py:165-171 with `sample_fn` set: chain[0] / node_mask have the TEMPLATE's padded length, positions and
+    com_mask the input batch's (create_templates_for_linker_generation re-pads, datasets.py:483-512)."""
+    from difflinker_b200 import output
+    from difflinker_b200.batching import create_templates_for_linker_generation
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    data = collate(synthetic.make_items(spec))
+    sizes = torch.tensor([9, 2, 12, 5])[:data['positions'].shape[0]]
+    tpl = create_templates_for_linker_generation(data, sizes)
+    n_old, n_new = data['positions'].shape[1], tpl['positions'].shape[1]
+    assert n_old != n_new
+    g = torch.Generator().manual_seed(6)
+    chain0 = torch.randn((tpl['positions'].shape[0], n_new, 3 + spec.F), generator=g)
+    positions = data['positions'] + torch.tensor([4.0, -2.0, 9.5])
+    com_mask = data['fragment_mask']
+    mean = (positions * com_mask).sum(1, keepdim=True) / com_mask.sum(1, keepdim=True)
+    want = chain0[..., :3] + mean * tpl['atom_mask']                       # generate.py:167-171 verbatim
+    got = output.restore_frame(chain0.clone().to(dev()), positions, com_mask, tpl['atom_mask']).cpu()
+    assert rel_err(got[..., :3], want) <= 1e-6 and torch.equal(got[..., 3:], chain0[..., 3:])
 
 
 @pytest.mark.parametrize("name", ["size_gnn_zinc", "size_gnn_zinc_bn"])

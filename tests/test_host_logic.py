@@ -68,6 +68,46 @@ def test_no_cpu_fallback_without_gpu():
         dyn(torch.zeros(1, 1), z, torch.ones(1, 4, 1), torch.ones(1, 4, 1), torch.ones(16, 1), torch.ones(1, 4, 1))
 
 
+def test_normalization_hyperparameter_is_ignored_like_the_reference():
+    """Every published config / checkpoint carries normalization='batch_norm'; for model='egnn_dynamics' the reference
+    never reads it (src/egnn.py:340-368), so neither constructor may refuse it."""
+    d = difflinker_b200.Dynamics(n_dims=3, in_node_nf=8, context_node_nf=1, hidden_nf=128, normalization='batch_norm')
+    assert isinstance(d, torch.nn.Module)
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    hp = synthetic.model_hparams(spec)
+    assert hp['normalization'] == 'batch_norm'
+    m, _ = helpers.build_ddpm(spec, 0)
+    assert isinstance(m.edm.dynamics, difflinker_b200.Dynamics)
+
+
+def test_nan_exception_is_catchable_as_the_reference_class():
+    """generate.py:154-159 retries on `except FoundNaNException` with the class imported from src.utils; the native
+    sampler must raise something that clause catches (and that this package's own class catches too)."""
+    import sys, types
+    from difflinker_b200.utils import nan_exception_class
+    saved = sys.modules.get('src.utils')
+    try:
+        sys.modules.pop('src.utils', None)
+        assert nan_exception_class() is FoundNaNException
+        mod = types.ModuleType('src.utils')
+
+        class RefNaN(Exception):                     # constructor signature of src/utils.py:274-282
+            def __init__(self, x, h):
+                self.x_h_nan_idx = set()
+        mod.FoundNaNException = RefNaN
+        sys.modules['src.utils'] = mod
+        cls = nan_exception_class()
+        assert issubclass(cls, RefNaN) and issubclass(cls, FoundNaNException) and nan_exception_class() is cls
+        with pytest.raises(RefNaN) as ei:
+            raise cls(flags=[0, 1, 3])
+        assert ei.value.only_x_nan_idx == {1} and ei.value.x_h_nan_idx == {2}
+    finally:
+        if saved is not None:
+            sys.modules['src.utils'] = saved
+        else:
+            sys.modules.pop('src.utils', None)
+
+
 def test_nan_exception_mapping():
     e = FoundNaNException(flags=[0, 1, 2, 3 | (7 << 8), 1 | (9 << 8)])
     assert e.x_h_nan_idx == {3} and e.only_x_nan_idx == {1, 4} and e.only_h_nan_idx == {2}
