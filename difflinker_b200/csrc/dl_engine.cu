@@ -57,6 +57,9 @@ struct Workspace {
   // third-generation GCL kernel (kernels_edge_v3.cuh): FC graphs with N <= 64; tensor map of ABg's B halves
   bool v3 = false;
   CUtensorMap tm_abg;
+  uint8_t* ts = nullptr;      // per-tile tables of the v3 kernel (tc3::TileTables)
+  int2* tij = nullptr;
+  float *td = nullptr, *td0 = nullptr, *tdmax = nullptr, *td0max = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -192,6 +195,12 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   ws.v3 = false;
   if (e->use_tc && e->allow_v3 && tc3::supports(make_geom(e, B, N))) {
     if (tc3::make_panel_map(&ws.tm_abg, ws.ABg, B, N) != DL_OK) { set_err("cuTensorMapEncodeTiled failed for the projection buffer"); return DL_ERR_CUDA; }
+    dl_status s2;
+    // at most one tile per live row
+    if ((s2 = dev_alloc(ws, &ws.ts, n * tc3::TS_BYTES)) != DL_OK || (s2 = dev_alloc(ws, &ws.tij, n * tc::TN)) != DL_OK ||
+        (s2 = dev_alloc(ws, &ws.td, n * tc::TN)) != DL_OK || (s2 = dev_alloc(ws, &ws.td0, n * tc::TN)) != DL_OK ||
+        (s2 = dev_alloc(ws, &ws.tdmax, n)) != DL_OK || (s2 = dev_alloc(ws, &ws.td0max, n)) != DL_OK)
+      return s2;
     ws.v3 = true;
   }
   return DL_OK;
@@ -237,7 +246,18 @@ dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const 
                                 ws.items, ws.n_items, ws.xmols, ws.n_xmols, ws.xitems, ws.n_xitems);
   LAUNCH_CHECK();
   e->launches += 2;
+  if (ws.v3) {
+    tc3::k_tiles_static<<<B * N, tc::TN, 0, st>>>(N, make_plan(ws), edge_mask, ws.ts, ws.tij);
+    LAUNCH_CHECK();
+    e->launches += 1;
+  }
   return DL_OK;
+}
+
+tc3::TileTables make_tile_tables(const Workspace& ws) {
+  tc3::TileTables t;
+  t.ts = ws.ts; t.td = ws.td; t.td0 = ws.td0; t.tdmax = ws.tdmax; t.td0max = ws.td0max;
+  return t;
 }
 
 struct FwdIO {
@@ -258,7 +278,7 @@ ProjW proj_of(const EqW& w) { return ProjW{w.W1a_t, w.W1b_t, w.b1}; }
 dl_status launch_edge(dl_engine* e, const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc,
                       cudaStream_t st, const void* w2_v3 = nullptr) {
   if (e->use_tc && !coord && e->ws.v3) {
-    tc3::launch_edge_v3(gm, ea, w2_v3, e->ws.tm_abg, e->num_sms, st);
+    tc3::launch_edge_v3(gm, ea, w2_v3, e->ws.tm_abg, make_tile_tables(e->ws), e->num_sms, st);
   } else if (e->use_tc) {
     dl_status s = tc::launch_edge_tc(gm, ea, coord, w2_tc, e->num_sms, st);
     if (s != DL_OK) return s;
@@ -326,6 +346,14 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   const float ksc = e->use_tc ? 1.4426950408889634f : 1.0f;   // log2-domain first layer on the tcgen05 path
   e->last_edge_mask = io.edge_mask; e->last_linker_mask = io.linker_mask; e->last_B = B; e->last_N = N;
   for (int l = 0; l < L; ++l) {
+    if (ws.v3) {
+      // tile tables of this block (squared distances from the block's coordinates; block 0 also fills the input-distance
+      // table: x == x0 there) + the x -> x_next copy that precedes the block's coordinate update
+      tc3::k_tiles_d<<<B * N, tc::TN, 0, st>>>(ws.n_items, ws.tij, xin4, ws.td, ws.tdmax, l == 0 ? ws.td0 : nullptr,
+                                               l == 0 ? ws.td0max : nullptr, n * 3, xin, xout, xin4, xout4);
+      LAUNCH_CHECK();
+      e->launches += 1;
+    }
     for (int s = 0; s < S; ++s) {
       const GclW& w = e->gcl[l * S + s];
       EdgeArgs ea{};
@@ -380,9 +408,11 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       LAUNCH_CHECK();
       e->launches += 1;
     }
-    k_copy_x<<<(n * 3 + 255) / 256, 256, 0, st>>>(n * 3, xin, xout, e->use_tc ? xin4 : nullptr, xout4);
-    LAUNCH_CHECK();
-    e->launches += 1;
+    if (!ws.v3) {
+      k_copy_x<<<(n * 3 + 255) / 256, 256, 0, st>>>(n * 3, xin, xout, e->use_tc ? xin4 : nullptr, xout4);
+      LAUNCH_CHECK();
+      e->launches += 1;
+    }
     const EqW& w = e->eq[l];
     EdgeArgs ea{};
     ea.AB = ws.ABc; ea.ABmax = ws.ABcmax; ea.w2_descale = w.w2_descale; ea.wdmax = w.wdmax * ksc; ea.w0max = w.w0max * ksc;
@@ -878,7 +908,7 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
   cudaStream_t st = e->loop_stream;
   if (e->use_tc && getenv("DL_PROFILE_EDGE")) {
-    if (ws.v3) tc3::profile_edge_v3(gm, ea, w.W2_v3, ws.tm_abg, e->num_sms, st);
+    if (ws.v3) tc3::profile_edge_v3(gm, ea, w.W2_v3, ws.tm_abg, make_tile_tables(ws), e->num_sms, st);
     else tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
   }
   if (e->use_tc && getenv("DL_PROFILE_NODE")) {

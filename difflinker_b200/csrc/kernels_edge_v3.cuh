@@ -5,14 +5,19 @@
 //   * the molecule's column projections B_j (N x 128 fp32) are staged in shared memory by ONE 2-D tiled TMA load
 //     (cp.async.bulk.tensor, SASS UTMALDG) per molecule, double-buffered so the next molecule's panel lands while the
 //     current one is consumed; the producers gather B_j with conflict-free LDS.128 instead of per-edge __ldg from L2;
-//   * the row projections A_i of a tile's (<= 8) rows arrive by 512-byte bulk copies issued by the table warp into the
-//     tile's table slot, completing on the same mbarrier as the tables;
+//   * everything about a tile that does not depend on the layer lives in global "tile tables" (static part per plan,
+//     d0 per forward, d per block: k_tiles_static / k_tiles_d) and the table warps only STREAM it into their ring
+//     slots with bulk copies (UBLKCP), together with the 512-byte A_i rows of the tile; they compute nothing per edge;
 //   * W2 (hi | lo fp16) lives in TENSOR MEMORY as the A operand of tcgen05.mma (TS form): 64 KB of shared memory and half
 //     of the tensor core's shared-memory read traffic are gone, and with them the 64 KB bulk load at every launch;
 //   * both SiLUs use the four-sigmoids-per-reciprocal form (usig4: 1.25 MUFU per SiLU instead of 1.5), the first layer
 //     runs in the log2 domain (weights pre-scaled by -log2 e: no scaling multiply), tile rows are padded to a multiple
-//     of four columns (weight-0 mirror edges) so the epilogue only has the 8- and 4-column paths, and the epilogue's
-//     TMEM loads are software-pipelined.
+//     of four columns (weight-0 mirror edges) so the epilogue only has the 8- and 4-column paths;
+//   * 12 epilogue warps (three per TMEM lane quarter, rotating over the tile's rows) next to 16 producer warps: both
+//     roles are dependency-latency bound per warp, so the split is chosen to balance them (measured: 8 epilogue warps
+//     with deeper software pipelining per warp were 35 % slower);
+//   * the producer-side and epilogue-side table slots are separate rings (3 and 8 deep) so the table warps run as far
+//     ahead of the epilogue as the epilogue-side ring allows instead of being throttled by the slowest consumer.
 //
 // K permutation: producer thread kc owns channels {4kc..4kc+3} u {64+4kc..64+4kc+3} (two conflict-free 16-byte reads of
 // a 512-byte panel row per half-warp) and writes them as operand positions 8kc..8kc+7; W2 is packed with the same
@@ -27,38 +32,71 @@ namespace tc3 {
 
 using namespace dl::tc;
 
-constexpr int MAXR3 = 8;                       // rows per tile (A rows staged per table slot)
+constexpr int MAXR3 = 8;                       // rows per tile (A rows staged per producer-side slot)
 constexpr int NACC3 = 3;                       // TMEM accumulator stages: columns 128 + 128 a (columns 0..127 hold W2 hi | lo)
-constexpr int NSLOT3 = 4;                      // table ring depth
+constexpr int NPS3 = 3;                        // ring of producer-side table slots (freed by the producers)
+constexpr int NES3 = 8;                        // ring of epilogue-side table slots (freed by the epilogue): how far the table
+                                               // warps may run ahead of the pipeline's last stage
 constexpr int PANEL_N = 64;                    // largest molecule whose B panel is double-buffered in shared memory
 constexpr int PANEL_BYTES = PANEL_N * H * 4;   // 32 KB per buffer
 constexpr int TM_W = 0, TM_ACC = 128;          // TMEM columns
 
 constexpr int O3_ST = 0;                                   // 2 x [hi | lo] activation operand stages
 constexpr int O3_PANEL = O3_ST + N_STAGE * STAGE_BYTES;    // 2 x B panel
-constexpr int O3_TBL = O3_PANEL + 2 * PANEL_BYTES;         // NSLOT3 x table slot
-constexpr int T3_HDR = 0;                                  // int[16]: Et, nrt, ncc4, b, first-of-molecule, q, rescale
-constexpr int T3_REC = 64;                                 // float4[TN]: d, d0, (B row offset | A row offset << 16), operand scale
-constexpr int T3_EW = T3_REC + TN * 16;                    // f32[TN]: edge weight * -ln2
-constexpr int T3_DS = T3_EW + TN * 4;                      // f32[TN]: accumulator descale * -log2 e (read only in rescaled tiles)
-constexpr int T3_ROWNODE = T3_DS + TN * 4;                 // int[MAXR3] (+ pad)
-constexpr int T3_A = T3_ROWNODE + 64;                      // f32[MAXR3][128]: A_i rows of the tile (bulk copies)
-constexpr int T3_BYTES = T3_A + MAXR3 * H * 4;
-constexpr int O3_B2 = O3_TBL + NSLOT3 * T3_BYTES;          // f32[128]: b2 * -log2 e
+constexpr int O3_PT = O3_PANEL + 2 * PANEL_BYTES;          // NPS3 x producer-side slot
+constexpr int P3_D = 0;                                    // f32[TN]  |x_i - x_j|^2 of this block          (bulk copy of td[tile])
+constexpr int P3_D0 = P3_D + TN * 4;                       // f32[TN]  |x0_i - x0_j|^2 of the call's input  (bulk copy of td0[tile])
+constexpr int P3_BOFF = P3_D0 + TN * 4;                    // int[TN]  byte offset of B_j inside the panel   } one bulk copy of the
+constexpr int P3_GRP = P3_BOFF + TN * 4;                   // int[TN/4] A-row byte offset of each 4-edge group } tile's static part
+constexpr int P3_A = P3_GRP + TN;                          // f32[MAXR3][128]: A_i rows of the tile (bulk copies from AB)
+constexpr int P3_BYTES = P3_A + MAXR3 * H * 4;
+constexpr int TS_P_BYTES = P3_A - P3_BOFF;                 // 640: static producer-side part of a tile in global memory
+constexpr int O3_ET = O3_PT + NPS3 * P3_BYTES;             // NES3 x epilogue-side slot
+constexpr int E3_HDR = 0;                                  // int[16]: Et, nrt, ncc4, b                      } one bulk copy of the
+constexpr int E3_EW = 64;                                  // f32[TN]  edge weight * -ln2                     } tile's static part
+constexpr int E3_ROWNODE = E3_EW + TN * 4;                 // int[16]  node of each tile row                  }
+constexpr int TS_E_BYTES = E3_ROWNODE + 64;                // 640: static epilogue-side part of a tile in global memory
+constexpr int E3_DYN = TS_E_BYTES;                         // int[8]: first-of-molecule, q, rescale, f32 operand scale, f32 descale * -log2 e
+constexpr int E3_BYTES = E3_DYN + 32;
+constexpr int TS_BYTES = TS_P_BYTES + TS_E_BYTES;          // per-tile static record in global memory: [P part | E part]
+constexpr int O3_B2 = O3_ET + NES3 * E3_BYTES;             // f32[128]: b2 * -log2 e
 constexpr int O3_BAR = O3_B2 + H * 4;
-constexpr int B3_FULL = 0, B3_EMPTY = B3_FULL + 8 * N_STAGE, B3_TBL = B3_EMPTY + 8 * N_STAGE, B3_TFREE = B3_TBL + 8 * NSLOT3,
-              B3_TFULL = B3_TFREE + 8 * NSLOT3, B3_TEMPTY = B3_TFULL + 8 * NACC3, B3_PFULL = B3_TEMPTY + 8 * NACC3,
-              B3_PEMPTY = B3_PFULL + 16, B3_W = B3_PEMPTY + 16, B3_TMEMSLOT = B3_W + 8;
+constexpr int B3_FULL = 0, B3_EMPTY = B3_FULL + 8 * N_STAGE, B3_TBL = B3_EMPTY + 8 * N_STAGE, B3_TFREE = B3_TBL + 8 * NES3,
+              B3_PFREE = B3_TFREE + 8 * NES3, B3_TFULL = B3_PFREE + 8 * NPS3, B3_TEMPTY = B3_TFULL + 8 * NACC3,
+              B3_PFULL = B3_TEMPTY + 8 * NACC3, B3_PEMPTY = B3_PFULL + 16, B3_W = B3_PEMPTY + 16, B3_TMEMSLOT = B3_W + 8;
 constexpr int SMEM3_BYTES = O3_BAR + B3_TMEMSLOT + 16 + 1024;
 static_assert(SMEM3_BYTES <= 232448, "k_edge_v3 exceeds the 227 KB of shared memory a CTA can opt into");
-static_assert(O3_PANEL % 128 == 0 && T3_A % 16 == 0 && T3_BYTES % 16 == 0 && O3_TBL % 16 == 0, "TMA destinations need their alignment");
-constexpr int REGS3_EPI = 56, REGS3_CTRL = 56, REGS3_PROD = 80;   // 8 x 32 x 56 + 4 x 32 x 56 + 16 x 32 x 80 = 62,464
+static_assert(O3_PANEL % 128 == 0 && P3_A % 16 == 0 && P3_BYTES % 16 == 0 && O3_PT % 16 == 0 && O3_ET % 16 == 0 && E3_BYTES % 16 == 0 &&
+              TS_P_BYTES % 16 == 0 && TS_E_BYTES % 16 == 0, "TMA destinations need their alignment");
+
+// Per-tile tables in global memory (tile = GCL work item of the plan): see the header comment.
+struct TileTables {
+  const uint8_t* ts;      // [tiles][TS_BYTES] static records
+  const float* td;        // [tiles][TN] squared distances of the current block
+  const float* td0;       // [tiles][TN] squared distances of the call's input coordinates
+  const float* tdmax;     // [tiles] max of td over the tile
+  const float* td0max;    // [tiles]
+};
+
+// Warp layout: producers 0..15, MMA issuer 16, table warps 17..19, epilogue 20..20+NEPI-1 (20 % 4 == 0: an epilogue warp's TMEM
+// lane quarter is warp % 4). NEPI = 8: 896 threads (72 registers at launch); NEPI = 12: 1024 threads (64 at launch).
+// Registers after setmaxnreg: 16 x 32 x PROD + 4 x 32 x CTRL + NEPI x 32 x EPI <= 65,536.
+constexpr int W3_PROD = 0, W3_MMA = 16, W3_TBL = 17, W3_EPI = 20;
+template <int NEPI> struct Regs3;
+template <> struct Regs3<8> { static constexpr int EPI = 64, CTRL = 56, PROD = 80; };    // 16,384 + 7,168 + 40,960 = 64,512
+template <> struct Regs3<12> { static constexpr int EPI = 48, CTRL = 48, PROD = 80; };   // 18,432 + 6,144 + 40,960 = 65,536
 
 // operand position p (0..127) -> channel (see "K permutation" above)
 __host__ __device__ constexpr int chan_of_pos(int p) { return (p & 4) ? 64 + 4 * (p >> 3) + (p & 3) : 4 * (p >> 3) + (p & 3); }
 
+__device__ __forceinline__ float4 lds128(const void* p) {   // volatile: stays where it is written relative to the tcgen05 asm
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+  return v;
+}
+
 struct Tile3 {
-  int b, nc, ncc4, slot0, nrt;
+  int b, nc, ncc4, slot0, nrt, gidx;
   const int* rows;
 };
 
@@ -92,6 +130,7 @@ struct TileIter3 {
       if (rt >= r_count || nc <= 0) { wi += 1; rt = 0; continue; }
       t.b = b; t.nc = nc; t.ncc4 = ncc4; t.slot0 = r_begin + rt; t.nrt = min(per, r_count - rt);
       t.rows = rowlist + (size_t)b * N;
+      t.gidx = wi;                                         // one item = one tile (k_plan_items uses the same rows-per-tile rule)
       rt += per;
       return true;
     }
@@ -99,15 +138,17 @@ struct TileIter3 {
   }
 };
 
-template <bool PROF = false>
-__global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArgs a, const uint32_t* __restrict__ w2p,
-                                                                const __grid_constant__ CUtensorMap tm_b,
-                                                                unsigned long long* __restrict__ prof = nullptr) {
+template <bool PROF, int NEPI>
+__global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, EdgeArgs a, const uint32_t* __restrict__ w2p,
+                                                                    const __grid_constant__ CUtensorMap tm_b, TileTables tt,
+                                                                    unsigned long long* __restrict__ prof = nullptr) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const uint32_t sbase = smem_u32(sm);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = gm.N;
+  constexpr int NG = NEPI / 4;                             // epilogue warps per TMEM lane quarter: they take the tile rows round-robin
+  using RG = Regs3<NEPI>;
   const uint32_t bars = sbase + O3_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + O3_BAR + B3_TMEMSLOT);
   float* b2s = reinterpret_cast<float*>(sm + O3_B2);
@@ -131,39 +172,50 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArg
 
   if (tid == 0) {
     for (int i = 0; i < N_STAGE; ++i) { mbar_init(bars + B3_FULL + 8 * i, N_PROD_WARPS); mbar_init(bars + B3_EMPTY + 8 * i, 1); }
-    for (int i = 0; i < NSLOT3; ++i) { mbar_init(bars + B3_TBL + 8 * i, 1); mbar_init(bars + B3_TFREE + 8 * i, N_EPI_WARPS); }
-    for (int i = 0; i < NACC3; ++i) { mbar_init(bars + B3_TFULL + 8 * i, 1); mbar_init(bars + B3_TEMPTY + 8 * i, N_EPI_WARPS); }
+    for (int i = 0; i < NES3; ++i) { mbar_init(bars + B3_TBL + 8 * i, 1); mbar_init(bars + B3_TFREE + 8 * i, NEPI); }
+    for (int i = 0; i < NPS3; ++i) mbar_init(bars + B3_PFREE + 8 * i, N_PROD_WARPS);
+    for (int i = 0; i < NACC3; ++i) { mbar_init(bars + B3_TFULL + 8 * i, 1); mbar_init(bars + B3_TEMPTY + 8 * i, NEPI); }
     for (int i = 0; i < 2; ++i) { mbar_init(bars + B3_PFULL + 8 * i, 1); mbar_init(bars + B3_PEMPTY + 8 * i, N_PROD_WARPS); }
-    mbar_init(bars + B3_W, N_EPI_WARPS);
+    mbar_init(bars + B3_W, 8);
     fence_barrier_init();
   }
   if (tid < H) b2s[tid] = a.b2[tid] * -1.4426950408889634f;
-  if (warp == W_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
+  if (warp == W3_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
 
-  if (warp >= W_MMA && warp < W_PROD) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS3_CTRL));
-    if (warp >= W_TBL && warp < W_TBL + N_TBL_WARPS) {
+  if (warp >= W3_MMA && warp < W3_EPI) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::CTRL));
+    if (warp >= W3_TBL) {
       // =================================== table warps =================================================================
-      const int tw = warp - W_TBL;
+      // Tile-parallel: table warp k serves tiles t = k, k+3, ...; all three walk the same tile sequence.
+      const int tw = warp - W3_TBL;
       TileIter3 iter(a.plan, N);
       Tile3 cur;
-      int q = -1, prev_b = -1;
-      for (int t = 0;; ++t) {
-        const int slot = t & (NSLOT3 - 1);
+      int q = -1, prev_b = -1, ps = 0, pu = 0;              // ps = t % NPS3, pu = t / NPS3
+      float mol_bmax = 0.f;                                 // max |B_j| over the current molecule (range bound)
+      for (int t = 0;; ++t, ps = (ps + 1 == NPS3 ? 0 : ps + 1), pu += (ps == 0)) {
+        const int slot = t & (NES3 - 1);
         const bool more = iter.next(cur);
         bool first = false;
         if (more && cur.b != prev_b) { first = true; ++q; prev_b = cur.b; }
+        if (more && first) {                                 // every table warp tracks the molecule bound (cheap, keeps them in step)
+          float m = 0.f;
+          for (int j = lane; j < N; j += 32) m = fmaxf(m, a.ABmax[((size_t)cur.b * N + j) * 2 + 1]);
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+          mol_bmax = m;
+        }
         if (t % N_TBL_WARPS != tw) { if (!more) break; continue; }
-        if (t >= NSLOT3) wait_relaxed(bars + B3_TFREE + 8 * slot, ((t - NSLOT3) / NSLOT3) & 1, 0);
-        uint8_t* tb = sm + O3_TBL + slot * T3_BYTES;
-        int* hdr = reinterpret_cast<int*>(tb + T3_HDR);
+        if (t >= NES3) wait_relaxed(bars + B3_TFREE + 8 * slot, ((t - NES3) / NES3) & 1, 0);     // epilogue done with tile t - 8
+        if (pu > 0) wait_relaxed(bars + B3_PFREE + 8 * ps, (pu - 1) & 1, 2);                         // producers done with tile t - 3
+        uint8_t* tb = sm + O3_ET + slot * E3_BYTES;            // epilogue-side slot (+ headers)
+        uint8_t* pb = sm + O3_PT + ps * P3_BYTES;              // producer-side slot
+        const uint32_t bar = bars + B3_TBL + 8 * slot;
         if (more) {
           const size_t gb = (size_t)cur.b * N;
-          const int Et = cur.nrt * cur.ncc4;
           if (first) {                                       // this molecule's B panel: one tiled TMA load
             const int buf = q & 1;
             if (q >= 2) wait_relaxed(bars + B3_PEMPTY + 8 * buf, ((q - 2) >> 1) & 1, 1);   // producers left molecule q-2
@@ -172,69 +224,59 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArg
               tma_load_2d(sbase + O3_PANEL + buf * PANEL_BYTES, &tm_b, H, cur.b * N, bars + B3_PFULL + 8 * buf);
             }
           }
-          if (lane == 0) {
-            hdr[0] = Et; hdr[1] = cur.nrt; hdr[2] = cur.ncc4; hdr[3] = cur.b; hdr[4] = first ? 1 : 0; hdr[5] = q;
-            mbar_expect_tx_only(bars + B3_TBL + 8 * slot, (uint32_t)cur.nrt * H * 4);
-          }
+          if (lane == 0) mbar_expect_tx_only(bar, (uint32_t)(cur.nrt * H * 4 + TS_BYTES + 2 * TN * 4));
           __syncwarp();
-          int node_r = 0;
+          float amax = 0.f;
           if (lane < cur.nrt) {                              // A_i rows of the tile: 512-byte bulk copies into the slot
-            node_r = cur.rows[cur.slot0 + lane];
-            reinterpret_cast<int*>(tb + T3_ROWNODE)[lane] = node_r;
-            bulk_g2s(smem_u32(tb + T3_A) + lane * (H * 4), a.AB + (gb + node_r) * 2 * H, H * 4, bars + B3_TBL + 8 * slot);
+            const int node_r = cur.rows[cur.slot0 + lane];
+            bulk_g2s(smem_u32(pb + P3_A) + lane * (H * 4), a.AB + (gb + node_r) * 2 * H, H * 4, bar);
+            amax = a.ABmax[(gb + node_r) * 2];
+          } else if (lane == 8) {
+            bulk_g2s(smem_u32(pb + P3_BOFF), tt.ts + (size_t)cur.gidx * TS_BYTES, TS_P_BYTES, bar);
+          } else if (lane == 9) {
+            bulk_g2s(smem_u32(tb + E3_HDR), tt.ts + (size_t)cur.gidx * TS_BYTES + TS_P_BYTES, TS_E_BYTES, bar);
+          } else if (lane == 10) {
+            bulk_g2s(smem_u32(pb + P3_D), tt.td + (size_t)cur.gidx * TN, TN * 4, bar);
+          } else if (lane == 11) {
+            bulk_g2s(smem_u32(pb + P3_D0), tt.td0 + (size_t)cur.gidx * TN, TN * 4, bar);
           }
-          bool any_rescale = false;
-          const int8_t* em = a.edge_mask ? a.edge_mask + gb * N : nullptr;
-#pragma unroll 2
-          for (int e = lane; e < TN; e += 32) {
-            int rr = e / cur.ncc4;
-            int jj = e - rr * cur.ncc4;
-            const bool valid = rr < cur.nrt && jj < cur.nc;    // padding slots mirror a real edge with weight 0
-            rr = min(rr, cur.nrt - 1); jj = min(jj, cur.nc - 1);
-            const int i = __shfl_sync(0xffffffffu, node_r, rr);
-            const int j = a.plan.colidx[gb + jj];
-            const float4 xi = a.x4[gb + i], xj = a.x4[gb + j], yi = a.x04[gb + i], yj = a.x04[gb + j];
-            const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            const float d = dx * dx + dy * dy + dz * dz;                       // egnn.py:297-298
-            const float ex = yi.x - yj.x, ey = yi.y - yj.y, ez = yi.z - yj.z;
-            const float d0 = ex * ex + ey * ey + ez * ez;                      // egnn.py:220
-            const float bound = a.ABmax[(gb + i) * 2] + a.ABmax[(gb + j) * 2 + 1] + d * a.wdmax + d0 * a.w0max;
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));   // lanes 0..7 hold the rows
+          if (lane == 0) {
+            // |u| <= max|A_i| + max|B_j| + d max|wd| + d0 max|w0| over the tile: ONE exact power-of-two scale per tile keeps
+            // the fp16 hi/lo operands below 2^14 (only ever != 1 for diverging samples)
+            const float bound = amax + mol_bmax + tt.tdmax[cur.gidx] * a.wdmax + tt.td0max[cur.gidx] * a.w0max;
             float sc = 1.0f;
             if (!(bound <= F16_TARGET)) {
               const int ex2 = ((__float_as_int(bound) >> 23) & 0xff) - 127;
               sc = __int_as_float(max(127 + 13 - ex2, 1) << 23);
             }
-            any_rescale |= (sc != 1.0f);
-            float ew = 0.f;
-            if (valid) ew = em ? (float)em[(size_t)i * N + j] : 1.0f;          // egnn.py:55-58 (int8 value, multiplied)
-            reinterpret_cast<float4*>(tb + T3_REC)[e] =
-                make_float4(d, d0, __int_as_float((j * (H * 4)) | ((rr * (H * 4)) << 16)), sc);
-            reinterpret_cast<float*>(tb + T3_EW)[e] = ew * -0.6931471805599453f;
-            reinterpret_cast<float*>(tb + T3_DS)[e] = (a.w2_descale / sc) * -1.4426950408889634f;
+            int* dyn = reinterpret_cast<int*>(tb + E3_DYN);
+            dyn[0] = first ? 1 : 0; dyn[1] = q; dyn[2] = sc != 1.0f ? 1 : 0;
+            dyn[3] = __float_as_int(sc);
+            dyn[4] = __float_as_int((a.w2_descale / sc) * -1.4426950408889634f);
           }
-          any_rescale = __any_sync(0xffffffffu, any_rescale);
-          if (lane == 0) hdr[6] = any_rescale ? 1 : 0;
         } else if (lane == 0) {
-          hdr[0] = 0;                                        // end marker travels through the whole pipeline
+          reinterpret_cast<int*>(tb + E3_HDR)[0] = 0;         // end marker travels through the whole pipeline
         }
         __syncwarp();
-        if (lane == 0) mbar_arrive(bars + B3_TBL + 8 * slot);
+        if (lane == 0) mbar_arrive(bar);
         if (!more) break;
       }
-      if (warp == W_TBL) prof_flush(0);
-    } else if (warp == W_MMA) {
+      if (warp == W3_TBL) prof_flush(0);
+    } else {
       // =================================== MMA issuer ===================================================================
       if (lane == 0) {
         mbar_wait(bars + B3_W, 0);                           // W2 hi | lo are in tensor memory
         tc_fence_after();
         int acc = 0, use = 0;
         for (int t = 0;; ++t) {
-          const int s = t & (N_STAGE - 1), slot = t & (NSLOT3 - 1);
+          const int s = t & (N_STAGE - 1), slot = t & (NES3 - 1);
           wait_relaxed(bars + B3_FULL + 8 * s, (t / N_STAGE) & 1, 0);
           // the epilogue drained this accumulator (also before the end marker: its plain arrive below must not land in the
           // phase a still-running commit of tile t-3 is about to complete)
           if (use > 0) wait_on(bars + B3_TEMPTY + 8 * acc, (use - 1) & 1, 1);
-          const int Et = reinterpret_cast<const int*>(sm + O3_TBL + slot * T3_BYTES + T3_HDR)[0];
+          const int Et = reinterpret_cast<const int*>(sm + O3_ET + slot * E3_BYTES + E3_HDR)[0];
           if (Et <= 0) { mbar_arrive(bars + B3_TFULL + 8 * acc); break; }
           tc_fence_after();
           const uint32_t bhi = sbase + O3_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
@@ -256,10 +298,10 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArg
         prof_flush(8);
       }
     }
-  } else if (warp >= W_PROD) {
+  } else if (warp < W3_MMA) {
     // =================================== producers =======================================================================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(REGS3_PROD));
-    const int pw = warp - W_PROD;
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RG::PROD));
+    const int pw = warp - W3_PROD;
     const int kc = lane & 15, esub = lane >> 4;
     float2 wdr[4], w0r[4];
     {
@@ -269,15 +311,18 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArg
       w0r[0] = make_float2(z0v.x, z0v.y); w0r[1] = make_float2(z0v.z, z0v.w); w0r[2] = make_float2(z1v.x, z1v.y); w0r[3] = make_float2(z1v.z, z1v.w);
     }
     const uint8_t* panel = sm + O3_PANEL + kc * 16;
-    const int e_base = 4 * (2 * pw + esub);                  // this thread's four consecutive edges (one tile row: rows are padded to x4)
-    for (int t = 0;; ++t) {
-      const int s = t & (N_STAGE - 1), slot = t & (NSLOT3 - 1);
-      wait_on(bars + B3_TBL + 8 * slot, (t / NSLOT3) & 1, 0);
-      const uint8_t* tb = sm + O3_TBL + slot * T3_BYTES;
-      const int* hdr = reinterpret_cast<const int*>(tb + T3_HDR);
+    const int grp = 2 * pw + esub;                           // this thread's group of four consecutive edges (same tile row)
+    const int e_base = 4 * grp;
+    int ps = 0;
+    for (int t = 0;; ++t, ps = (ps + 1 == NPS3 ? 0 : ps + 1)) {
+      const int s = t & (N_STAGE - 1), slot = t & (NES3 - 1);
+      wait_on(bars + B3_TBL + 8 * slot, (t / NES3) & 1, 0);
+      const uint8_t* tb = sm + O3_PT + ps * P3_BYTES;        // producer-side slot
+      const int* hdr = reinterpret_cast<const int*>(sm + O3_ET + slot * E3_BYTES + E3_HDR);
+      const int* dyn = reinterpret_cast<const int*>(sm + O3_ET + slot * E3_BYTES + E3_DYN);
       const int Et = hdr[0];
-      if (Et > 0 && hdr[4]) {                                // first tile of a molecule: switch panel buffers
-        const int q = hdr[5], buf = q & 1;
+      if (Et > 0 && dyn[0]) {                                // first tile of a molecule: switch panel buffers
+        const int q = dyn[1], buf = q & 1;
         if (q >= 1) { __syncwarp(); if (lane == 0) mbar_arrive(bars + B3_PEMPTY + 8 * (buf ^ 1)); }
         wait_on(bars + B3_PFULL + 8 * buf, (q >> 1) & 1, 2);
         panel = sm + O3_PANEL + buf * PANEL_BYTES + kc * 16;
@@ -285,65 +330,74 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArg
       if (t >= N_STAGE) wait_on(bars + B3_EMPTY + 8 * s, ((t - N_STAGE) / N_STAGE) & 1, 1);
       if (Et > 0) {
         if (e_base < Et) {
-          const float4* recs = reinterpret_cast<const float4*>(tb + T3_REC);
-          uint8_t* bhi = sm + O3_ST + s * STAGE_BYTES + kc * B_LBO;
+          uint8_t* bhi = sm + O3_ST + s * STAGE_BYTES + kc * B_LBO + e_base * 16;
           uint8_t* blo = bhi + B_BYTES;
-          const bool rescale = hdr[6] != 0;
-          const float4 r0 = recs[e_base];
-          const uint8_t* arow = tb + T3_A + kc * 16 + (__float_as_int(r0.z) >> 16);
+          // the whole group's scalars in three 16-byte loads; B_j of the NEXT edge is fetched before the current one is
+          // processed (the compiler cannot hoist those loads over the operand stores itself: same address space)
+          const float4 dq = *reinterpret_cast<const float4*>(tb + P3_D + e_base * 4);
+          const float4 d0q = *reinterpret_cast<const float4*>(tb + P3_D0 + e_base * 4);
+          const int4 bo = *reinterpret_cast<const int4*>(tb + P3_BOFF + e_base * 4);
+          const uint8_t* arow = tb + P3_A + kc * 16 + reinterpret_cast<const int*>(tb + P3_GRP)[grp];
           const float4 a0 = *reinterpret_cast<const float4*>(arow), a1 = *reinterpret_cast<const float4*>(arow + 256);
           const float2 av[4] = {make_float2(a0.x, a0.y), make_float2(a0.z, a0.w), make_float2(a1.x, a1.y), make_float2(a1.z, a1.w)};
+          const float dq_[4] = {dq.x, dq.y, dq.z, dq.w}, d0q_[4] = {d0q.x, d0q.y, d0q.z, d0q.w};
+          const int bo_[4] = {bo.x, bo.y, bo.z, bo.w};
+          auto run_items = [&](auto rs_tag) {
+            constexpr bool RS = decltype(rs_tag)::value;
+            float4 b0 = *reinterpret_cast<const float4*>(panel + bo_[0]), b1 = *reinterpret_cast<const float4*>(panel + bo_[0] + 256);
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const int e = e_base + it;
-            const float4 rec = it == 0 ? r0 : recs[e];
-            const uint8_t* bp = panel + (__float_as_int(rec.z) & 0xffff);
-            const float4 b0 = *reinterpret_cast<const float4*>(bp), b1 = *reinterpret_cast<const float4*>(bp + 256);
-            const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
-            const float2 dd = make_float2(rec.x, rec.x), dd0 = make_float2(rec.y, rec.y);
-            float2 u[4], sv[4];
+            for (int it = 0; it < 4; ++it) {
+              float4 n0 = b0, n1 = b1;
+              if (it < 3) { n0 = *reinterpret_cast<const float4*>(panel + bo_[it + 1]); n1 = *reinterpret_cast<const float4*>(panel + bo_[it + 1] + 256); }
+              const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+              const float2 dd = make_float2(dq_[it], dq_[it]), dd0 = make_float2(d0q_[it], d0q_[it]);
+              float2 u[4], sv[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k)                       // egnn.py:49-50 in the log2 domain, two channels per instruction
-              u[k] = __ffma2_rn(dd0, w0r[k], __ffma2_rn(dd, wdr[k], __fadd2_rn(av[k], bv[k])));
-            usig4(u[0], u[1], sv[0], sv[1]);
-            usig4(u[2], u[3], sv[2], sv[3]);
-            if (rescale) {                                   // rare: diverging samples only (tile-uniform)
+              for (int k = 0; k < 4; ++k)                     // egnn.py:49-50 in the log2 domain, two channels per instruction
+                u[k] = __ffma2_rn(dd0, w0r[k], __ffma2_rn(dd, wdr[k], __fadd2_rn(av[k], bv[k])));
+              usig4(u[0], u[1], sv[0], sv[1]);
+              usig4(u[2], u[3], sv[2], sv[3]);
+              if (RS) {                                      // rare: diverging samples only (tile-uniform power of two)
+                const float sc = __int_as_float(dyn[3]);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) sv[k] = __fmul2_rn(sv[k], make_float2(rec.w, rec.w));
+                for (int k = 0; k < 4; ++k) sv[k] = __fmul2_rn(sv[k], make_float2(sc, sc));
+              }
+              uint4 hi, lo;
+              split2v(sv[0], hi.x, lo.x); split2v(sv[1], hi.y, lo.y);
+              split2v(sv[2], hi.z, lo.z); split2v(sv[3], hi.w, lo.w);
+              *reinterpret_cast<uint4*>(bhi + it * 16) = hi;
+              *reinterpret_cast<uint4*>(blo + it * 16) = lo;
+              b0 = n0; b1 = n1;
             }
-            uint4 hi, lo;
-            split2v(sv[0], hi.x, lo.x); split2v(sv[1], hi.y, lo.y);
-            split2v(sv[2], hi.z, lo.z); split2v(sv[3], hi.w, lo.w);
-            *reinterpret_cast<uint4*>(bhi + e * 16) = hi;
-            *reinterpret_cast<uint4*>(blo + e * 16) = lo;
-          }
+          };
+          if (dyn[2] != 0) run_items(std::true_type{}); else run_items(std::false_type{});
         }
         fence_proxy_async();
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(bars + B3_FULL + 8 * s);
+      if (lane == 0) { mbar_arrive(bars + B3_FULL + 8 * s); mbar_arrive(bars + B3_PFREE + 8 * ps); }
       if (Et <= 0) break;
     }
-    if (warp == W_PROD) prof_flush(4);
+    if (warp == W3_PROD) prof_flush(4);
   } else {
     // =================================== epilogue warps ====================================================================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(REGS3_EPI));   // first: the producers' increase waits for it
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RG::EPI));   // first: the producers' increase waits for it
     const int q = warp & 3;                                  // TMEM lane quarter
-    const int hw = warp >> 2;                                // prologue: 0 -> W2 hi, 1 -> W2 lo; main loop: row parity
+    const int g = (warp - W3_EPI) >> 2;                      // prologue: 0 -> W2 hi, 1 -> W2 lo; main loop: row phase
     const int c = q * 32 + lane;                             // output channel = TMEM lane
-    {
-      // W2 (this thread's output row, hi or lo half: 64 packed words) -> tensor memory columns [64 hw, 64 hw + 64)
-      const uint4* src = reinterpret_cast<const uint4*>(w2p + ((size_t)hw * H + c) * 64);
-      const uint32_t tw = tmem + ((uint32_t)(q * 32) << 16) + TM_W + hw * 64;
+    if (g < 2) {
+      // W2 (this thread's output row, hi or lo half: 64 packed words) -> tensor memory columns [64 g, 64 g + 64)
+      const uint4* src = reinterpret_cast<const uint4*>(w2p + ((size_t)g * H + c) * 64);
+      const uint32_t tw = tmem + ((uint32_t)(q * 32) << 16) + TM_W + g * 64;
 #pragma unroll 1
-      for (int g = 0; g < 4; ++g) {
+      for (int i4 = 0; i4 < 4; ++i4) {
         uint32_t r[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const uint4 v = __ldg(src + g * 4 + i);
+          const uint4 v = __ldg(src + i4 * 4 + i);
           r[4 * i] = v.x; r[4 * i + 1] = v.y; r[4 * i + 2] = v.z; r[4 * i + 3] = v.w;
         }
-        TMEM_ST_X16(tw + g * 16, r);
+        TMEM_ST_X16(tw + i4 * 16, r);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -352,74 +406,153 @@ __global__ void __launch_bounds__(EDGE_TC_THREADS, 1) k_edge_v3(Geom gm, EdgeArg
     }
     const float bias = b2s[c];
     const float2 bias2 = make_float2(bias, bias);
-    const float ds0 = a.w2_descale * -1.4426950408889634f;
-    int acc = 0, use = 0;
+    int acc = 0, use = 0, rot = g;                           // rot = (g + t) % NG: the warps of a lane quarter rotate over the rows
     for (int t = 0;; ++t) {
-      const int slot = t & (NSLOT3 - 1);
-      wait_on(bars + B3_TBL + 8 * slot, (t / NSLOT3) & 1, 0);
+      const int slot = t & (NES3 - 1);
+      wait_on(bars + B3_TBL + 8 * slot, (t / NES3) & 1, 0);
       wait_on(bars + B3_TFULL + 8 * acc, use & 1, 1);
       tc_fence_after();
-      const uint8_t* tb = sm + O3_TBL + slot * T3_BYTES;
-      const int* hdr = reinterpret_cast<const int*>(tb + T3_HDR);
+      const uint8_t* tb = sm + O3_ET + slot * E3_BYTES;
+      const int* hdr = reinterpret_cast<const int*>(tb + E3_HDR);
       const int Et = hdr[0];
       if (Et <= 0) break;
       const int nrt = hdr[1], ncc4 = hdr[2];
       const size_t gb = (size_t)hdr[3] * N;
-      const bool rescale = hdr[6] != 0;
-      const float* ews = reinterpret_cast<const float*>(tb + T3_EW);
-      const float* dss = reinterpret_cast<const float*>(tb + T3_DS);
-      const int* rownode = reinterpret_cast<const int*>(tb + T3_ROWNODE);
+      const float* ews = reinterpret_cast<const float*>(tb + E3_EW);
+      const int* rownode = reinterpret_cast<const int*>(tb + E3_ROWNODE);
+      const float ds0 = __int_as_float(reinterpret_cast<const int*>(tb + E3_DYN)[4]);   // tile-uniform descale * -log2 e
+      const float2 ds2 = make_float2(ds0, ds0);
       const uint32_t tacc = tmem + ((uint32_t)(q * 32) << 16) + TM_ACC + acc * TN;
-      // four edges of this thread's channel: u = -log2e (D descale + b2) (one packed FMA each pair), u * sigmoid, times the
-      // edge weight (which carries the -ln2), into two packed partial sums -- fixed order, deterministic.
-      auto quad = [&](const uint32_t* r, int col, float2& sa, float2& sb) {
-        const float4 ew = *reinterpret_cast<const float4*>(ews + col);
-        float2 d01 = make_float2(ds0, ds0), d23 = d01;
-        if (rescale) { const float4 dv = *reinterpret_cast<const float4*>(dss + col); d01 = make_float2(dv.x, dv.y); d23 = make_float2(dv.z, dv.w); }
-        const float2 u01 = __ffma2_rn(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), d01, bias2);
-        const float2 u23 = __ffma2_rn(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), d23, bias2);
-        float2 s01, s23;
-        usig4(u01, u23, s01, s23);
-        sa = __ffma2_rn(s01, make_float2(ew.x, ew.y), sa);
-        sb = __ffma2_rn(s23, make_float2(ew.z, ew.w), sb);
-      };
-      for (int rr = (hw + t) & 1; rr < nrt; rr += 2) {       // the two warp halves take alternate rows
+      // One row: this thread's channel over the row's columns. u = -log2e (D descale + b2) (packed FMA), u * sigmoid (usig4: four
+      // columns per reciprocal), times the edge weight (which carries the -ln2) into packed partial sums -- fixed order,
+      // deterministic.
+      auto do_row = [&](int rr) {
         const int col0 = rr * ncc4;
         const int n8 = ncc4 >> 3;
-        float2 sa = make_float2(0.f, 0.f), sb = sa;
-        uint32_t ra[8], rb[8];
-        if (n8 > 0) TMEM_LD_X8(tacc + col0, ra);
-        for (int k = 0; k < n8; k += 2) {                    // software-pipelined: the next 8 columns load while these are reduced
-          tmem_ld_wait();
-          if (k + 1 < n8) TMEM_LD_X8(tacc + col0 + (k + 1) * 8, rb);
-          quad(ra, col0 + k * 8, sa, sb);
-          quad(ra + 4, col0 + k * 8 + 4, sa, sb);
-          if (k + 1 < n8) {
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, s3 = s0;
+        auto quad = [&](const uint32_t* r, const float4 ew0, float2& sa, float2& sb) {
+          const float2 u0 = __ffma2_rn(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), ds2, bias2);
+          const float2 u1 = __ffma2_rn(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), ds2, bias2);
+          float2 g0, g1;
+          usig4(u0, u1, g0, g1);
+          sa = __ffma2_rn(g0, make_float2(ew0.x, ew0.y), sa);
+          sb = __ffma2_rn(g1, make_float2(ew0.z, ew0.w), sb);
+        };
+        if constexpr (NEPI == 12) {                          // 48 registers per thread: parallelism comes from the 12 warps
+          for (int k = 0; k < n8; ++k) {
+            uint32_t ra[8];
+            TMEM_LD_X8(tacc + col0 + k * 8, ra);
+            const float4 ew0 = lds128(ews + col0 + k * 8), ew1 = lds128(ews + col0 + k * 8 + 4);
             tmem_ld_wait();
-            if (k + 2 < n8) TMEM_LD_X8(tacc + col0 + (k + 2) * 8, ra);
-            quad(rb, col0 + (k + 1) * 8, sa, sb);
-            quad(rb + 4, col0 + (k + 1) * 8 + 4, sa, sb);
+            quad(ra, ew0, s0, s1);
+            quad(ra + 4, ew1, s2, s3);
+          }
+        } else {                                             // 8 warps, 64 registers: accumulator columns double-buffered
+          uint32_t ra[8], rb[8];
+          if (n8 > 0) TMEM_LD_X8(tacc + col0, ra);
+          for (int k = 0; k < n8; k += 2) {
+            const float4 ew0 = lds128(ews + col0 + k * 8), ew1 = lds128(ews + col0 + k * 8 + 4);
+            tmem_ld_wait();
+            if (k + 1 < n8) TMEM_LD_X8(tacc + col0 + (k + 1) * 8, rb);
+            quad(ra, ew0, s0, s1);
+            quad(ra + 4, ew1, s2, s3);
+            if (k + 1 < n8) {
+              const float4 ew2 = lds128(ews + col0 + k * 8 + 8), ew3 = lds128(ews + col0 + k * 8 + 12);
+              tmem_ld_wait();
+              if (k + 2 < n8) TMEM_LD_X8(tacc + col0 + (k + 2) * 8, ra);
+              quad(rb, ew2, s0, s1);
+              quad(rb + 4, ew3, s2, s3);
+            }
           }
         }
         if (ncc4 & 4) {
           uint32_t r4[4];
-          TMEM_LD_X4(tacc + col0 + n8 * 8, r4);
+          const int col = col0 + n8 * 8;
+          TMEM_LD_X4(tacc + col, r4);
+          const float4 ew0 = lds128(ews + col);
           tmem_ld_wait();
-          quad(r4, col0 + n8 * 8, sa, sb);
+          quad(r4, ew0, s0, s1);
         }
-        const float accv = (sa.x + sa.y) + (sb.x + sb.y);
+        const float accv = ((s0.x + s0.y) + (s1.x + s1.y)) + ((s2.x + s2.y) + (s3.x + s3.y));
         a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
-      }
+      };
+      for (int rr = rot; rr < nrt; rr += NG) do_row(rr);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(bars + B3_TEMPTY + 8 * acc); mbar_arrive(bars + B3_TFREE + 8 * slot); }
       if (++acc == NACC3) { acc = 0; ++use; }
+      if (++rot == NG) rot = 0;
     }
-    if (warp == W_EPI) prof_flush(12);
+    if (warp == W3_EPI) prof_flush(12);
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == W_MMA) tmem_dealloc(tmem, 512);
+  if (warp == W3_MMA) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tile tables (see TileTables): one CTA of TN threads per tile, thread = tile column (edge slot)
+// ---------------------------------------------------------------------------------------------------------
+// Static part, once per plan (masks are constant over a sampling chain): panel offsets, A-row offsets, the header, the
+// edge weights (caller's int8 edge_mask value, egnn.py:55-58, times -ln2; padding slots mirror a real edge with weight 0)
+// and the (row node, column node) pair of every slot for k_tiles_d.
+__global__ void __launch_bounds__(TN) k_tiles_static(int N, Plan p, const int8_t* __restrict__ edge_mask, uint8_t* __restrict__ ts,
+                                                    int2* __restrict__ tij) {
+  const int g = blockIdx.x, e = threadIdx.x;
+  if (g >= *p.n_items) return;
+  const int4 it = p.items[g];
+  const int b = it.x, r0 = it.y, nrt = it.z, nc = it.w, ncc4 = (nc + 3) & ~3;
+  const size_t gb = (size_t)b * N;
+  int rr = e / ncc4;
+  int jj = e - rr * ncc4;
+  const bool valid = rr < nrt && jj < nc;
+  rr = min(rr, nrt - 1); jj = min(jj, nc - 1);
+  const int i = p.rowidx[gb + r0 + rr], j = p.colidx[gb + jj];
+  uint8_t* rec = ts + (size_t)g * TS_BYTES;
+  reinterpret_cast<int*>(rec)[e] = j * (H * 4);
+  if (e < TN / 4) reinterpret_cast<int*>(rec + TN * 4)[e] = min((4 * e) / ncc4, nrt - 1) * (H * 4);
+  uint8_t* er = rec + TS_P_BYTES;
+  if (e < 16) {
+    reinterpret_cast<int*>(er + E3_HDR)[e] = e == 0 ? nrt * ncc4 : e == 1 ? nrt : e == 2 ? ncc4 : e == 3 ? b : 0;
+    reinterpret_cast<int*>(er + E3_ROWNODE)[e] = e < nrt ? p.rowidx[gb + r0 + e] : 0;
+  }
+  float ew = 0.f;
+  if (valid) ew = edge_mask ? (float)edge_mask[gb * N + (size_t)i * N + j] : 1.0f;
+  reinterpret_cast<float*>(er + E3_EW)[e] = ew * -0.6931471805599453f;
+  tij[(size_t)g * TN + e] = make_int2((int)(gb + i), (int)(gb + j));
+}
+
+// Squared distances of every tile slot from the coordinates `x4` (egnn.py:297-298; with the call's input coordinates also
+// egnn.py:220 -- at block 0 both coincide, so td0 is written by the same launch) and their per-tile maxima. Also carries
+// the x -> x_next copy that precedes a block's coordinate update (rows the update does not touch keep x).
+__global__ void __launch_bounds__(TN) k_tiles_d(const int* __restrict__ n_items, const int2* __restrict__ tij, const float4* __restrict__ x4,
+                                               float* __restrict__ td, float* __restrict__ tdmax, float* __restrict__ td0,
+                                               float* __restrict__ td0max, int n3, const float* __restrict__ xsrc, float* __restrict__ xdst,
+                                               const float4* __restrict__ x4src, float4* __restrict__ x4dst) {
+  __shared__ float red[TN / 32];
+  const int g = blockIdx.x, e = threadIdx.x;
+  if (xdst != nullptr) {
+    const int i = g * TN + e;
+    if (i < n3) xdst[i] = xsrc[i];
+    if (i * 3 < n3) x4dst[i] = x4src[i];
+  }
+  if (g >= *n_items) return;
+  const int2 ij = tij[(size_t)g * TN + e];
+  const float4 xi = x4[ij.x], xj = x4[ij.y];
+  const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+  const float d = dx * dx + dy * dy + dz * dz;
+  td[(size_t)g * TN + e] = d;
+  if (td0 != nullptr) td0[(size_t)g * TN + e] = d;
+  float m = d;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((e & 31) == 0) red[e >> 5] = m;
+  __syncthreads();
+  if (e == 0) {
+    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    tdmax[g] = m;
+    if (td0max != nullptr) td0max[g] = m;
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -480,20 +613,29 @@ inline dl_status make_panel_map(CUtensorMap* out, const float* AB, int B, int N)
 }
 
 inline dl_status configure3() {
-  const bool ok = cudaFuncSetAttribute(k_edge_v3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
+  const bool ok = cudaFuncSetAttribute(k_edge_v3<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
   return ok ? DL_OK : DL_ERR_CUDA;
 }
 
-inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, int num_sms, cudaStream_t st) {
-  k_edge_v3<false><<<num_sms, EDGE_TC_THREADS, SMEM3_BYTES, st>>>(gm, ea, reinterpret_cast<const uint32_t*>(w2_v3), tm, nullptr);
+inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt, int num_sms,
+                           cudaStream_t st) {
+  static const int nepi = getenv("DL_V3_NEPI") ? atoi(getenv("DL_V3_NEPI")) : 12;      // experiment switch: epilogue warps
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
+  if (nepi == 8) k_edge_v3<false, 8><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
+  else k_edge_v3<false, 12><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
 }
 
-inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, int num_sms, cudaStream_t st) {
+inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt, int num_sms,
+                                 cudaStream_t st) {
   unsigned long long* d = nullptr;
   if (cudaMalloc(&d, (size_t)num_sms * 16 * 8) != cudaSuccess) return DL_ERR_CUDA;
   cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
-  k_edge_v3<true><<<num_sms, EDGE_TC_THREADS, SMEM3_BYTES, st>>>(gm, ea, reinterpret_cast<const uint32_t*>(w2_v3), tm, d);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
+  if (getenv("DL_V3_NEPI") && atoi(getenv("DL_V3_NEPI")) == 8) k_edge_v3<true, 8><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
+  else k_edge_v3<true, 12><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
   if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
   std::vector<unsigned long long> h((size_t)num_sms * 16);
   cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
@@ -501,7 +643,7 @@ inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void*
   double avg[16] = {0};
   for (int b = 0; b < num_sms; ++b) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)b * 16 + i] / num_sms;
   fprintf(stderr, "[dl prof v3] cycles per CTA (avg over %d), tiles %.1f\n", num_sms, avg[10]);
-  fprintf(stderr, "[dl prof v3]  table   : wait tfree %.0f, wait pempty %.0f | total %.0f\n", avg[0], avg[1], avg[3]);
+  fprintf(stderr, "[dl prof v3]  table   : wait tfree %.0f, wait pempty %.0f, wait pfree %.0f | total %.0f\n", avg[0], avg[1], avg[2], avg[3]);
   fprintf(stderr, "[dl prof v3]  producer: wait tbl %.0f, wait empty %.0f, wait panel %.0f | total %.0f\n", avg[4], avg[5], avg[6], avg[7]);
   fprintf(stderr, "[dl prof v3]  mma     : wait full %.0f, wait tempty %.0f | total %.0f\n", avg[8], avg[9], avg[11]);
   fprintf(stderr, "[dl prof v3]  epilogue: wait tbl %.0f, wait tfull %.0f | total %.0f\n", avg[12], avg[13], avg[15]);
