@@ -108,6 +108,7 @@ struct EqW {
   const float* b1_u;   // log2-domain copies (see GclW)
   const float* wd_u;
   const float* w0_u;
+  const void* W2_v3;   // coord_mlp.2 in the v3 kernel's tensor-memory layout
 };
 
 // First-layer projection of an edge MLP applied per node: A = h W1a^T + b1, B = h W1b^T.

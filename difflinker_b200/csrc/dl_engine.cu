@@ -56,10 +56,12 @@ struct Workspace {
   void* tc_scratch = nullptr;
   // third-generation GCL kernel (kernels_edge_v3.cuh): FC graphs with N <= 64; tensor map of ABg's B halves
   bool v3 = false;
-  CUtensorMap tm_abg;
-  uint8_t* ts = nullptr;      // per-tile tables of the v3 kernel (tc3::TileTables)
-  int2* tij = nullptr;
-  float *td = nullptr, *td0 = nullptr, *tdmax = nullptr, *td0max = nullptr;
+  CUtensorMap tm_abg, tm_abc;
+  // per-tile tables of the v3 kernel (tc3::TileTables): set 0 = GCL tiles (plan.items), set 1 = COORD tiles (plan.xitems)
+  uint8_t* ts[2] = {nullptr, nullptr};
+  int2* tij[2] = {nullptr, nullptr};
+  float *td[2] = {nullptr, nullptr}, *td0[2] = {nullptr, nullptr}, *tdmax[2] = {nullptr, nullptr}, *td0max[2] = {nullptr, nullptr};
+  float* tcd = nullptr;
   std::vector<void*> allocs;
 };
 
@@ -91,6 +93,7 @@ struct dl_engine {
   HostStage stage;
   bool use_tc = false;
   bool allow_v3 = true;        // DL_EDGE_V3=0 keeps the second-generation kernel (A/B measurements)
+  bool allow_v3_coord = true;  // DL_EDGE_V3_COORD=0: coordinate update on the second-generation kernel
   // pointers of the most recent forward (for dl_time_edge_kernel)
   const int8_t* last_edge_mask = nullptr;
   const float* last_linker_mask = nullptr;
@@ -194,13 +197,16 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
   ws.B = B; ws.N = N;
   ws.v3 = false;
   if (e->use_tc && e->allow_v3 && tc3::supports(make_geom(e, B, N))) {
-    if (tc3::make_panel_map(&ws.tm_abg, ws.ABg, B, N) != DL_OK) { set_err("cuTensorMapEncodeTiled failed for the projection buffer"); return DL_ERR_CUDA; }
+    if (tc3::make_panel_map(&ws.tm_abg, ws.ABg, B, N) != DL_OK || tc3::make_panel_map(&ws.tm_abc, ws.ABc, B, N) != DL_OK) {
+      set_err("cuTensorMapEncodeTiled failed for the projection buffers"); return DL_ERR_CUDA;
+    }
     dl_status s2;
-    // at most one tile per live row
-    if ((s2 = dev_alloc(ws, &ws.ts, n * tc3::TS_BYTES)) != DL_OK || (s2 = dev_alloc(ws, &ws.tij, n * tc::TN)) != DL_OK ||
-        (s2 = dev_alloc(ws, &ws.td, n * tc::TN)) != DL_OK || (s2 = dev_alloc(ws, &ws.td0, n * tc::TN)) != DL_OK ||
-        (s2 = dev_alloc(ws, &ws.tdmax, n)) != DL_OK || (s2 = dev_alloc(ws, &ws.td0max, n)) != DL_OK)
-      return s2;
+    for (int k = 0; k < 2; ++k)                              // at most one tile per live row
+      if ((s2 = dev_alloc(ws, &ws.ts[k], n * tc3::TS_BYTES)) != DL_OK || (s2 = dev_alloc(ws, &ws.tij[k], n * tc::TN)) != DL_OK ||
+          (s2 = dev_alloc(ws, &ws.td[k], n * tc::TN)) != DL_OK || (s2 = dev_alloc(ws, &ws.td0[k], n * tc::TN)) != DL_OK ||
+          (s2 = dev_alloc(ws, &ws.tdmax[k], n)) != DL_OK || (s2 = dev_alloc(ws, &ws.td0max[k], n)) != DL_OK)
+        return s2;
+    if ((s2 = dev_alloc(ws, &ws.tcd, n * 3 * tc::TN)) != DL_OK) return s2;
     ws.v3 = true;
   }
   return DL_OK;
@@ -247,16 +253,21 @@ dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const 
   LAUNCH_CHECK();
   e->launches += 2;
   if (ws.v3) {
-    tc3::k_tiles_static<<<B * N, tc::TN, 0, st>>>(N, make_plan(ws), edge_mask, ws.ts, ws.tij);
+    tc3::k_tiles_static<<<B * N, tc::TN, 0, st>>>(N, ws.items, ws.n_items, ws.rowidx, ws.colidx, edge_mask, ws.ts[0], ws.tij[0]);
     LAUNCH_CHECK();
-    e->launches += 1;
+    tc3::k_tiles_static<<<B * N, tc::TN, 0, st>>>(N, ws.xitems, ws.n_xitems, ws.xrowidx, ws.colidx, edge_mask, ws.ts[1], ws.tij[1]);
+    LAUNCH_CHECK();
+    e->launches += 2;
   }
   return DL_OK;
 }
 
-tc3::TileTables make_tile_tables(const Workspace& ws) {
+tc3::TileTables make_tile_tables(const Workspace& ws, bool coord) {
   tc3::TileTables t;
-  t.ts = ws.ts; t.td = ws.td; t.td0 = ws.td0; t.tdmax = ws.tdmax; t.td0max = ws.td0max;
+  const int k = coord ? 1 : 0;
+  t.ts = ws.ts[k]; t.td = ws.td[k]; t.td0 = ws.td0[k]; t.tdmax = ws.tdmax[k]; t.td0max = ws.td0max[k];
+  t.tcd = coord ? ws.tcd : nullptr;
+  t.items = coord ? ws.xitems : ws.items; t.n_items = coord ? ws.n_xitems : ws.n_items; t.rowidx = coord ? ws.xrowidx : ws.rowidx;
   return t;
 }
 
@@ -277,8 +288,8 @@ ProjW proj_of(const EqW& w) { return ProjW{w.W1a_t, w.W1b_t, w.b1}; }
 
 dl_status launch_edge(dl_engine* e, const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_tc,
                       cudaStream_t st, const void* w2_v3 = nullptr) {
-  if (e->use_tc && !coord && e->ws.v3) {
-    tc3::launch_edge_v3(gm, ea, w2_v3, e->ws.tm_abg, make_tile_tables(e->ws), e->num_sms, st);
+  if (e->use_tc && e->ws.v3 && w2_v3 != nullptr) {
+    tc3::launch_edge_v3(gm, ea, coord, w2_v3, coord ? e->ws.tm_abc : e->ws.tm_abg, make_tile_tables(e->ws, coord), e->num_sms, st);
   } else if (e->use_tc) {
     dl_status s = tc::launch_edge_tc(gm, ea, coord, w2_tc, e->num_sms, st);
     if (s != DL_OK) return s;
@@ -349,8 +360,9 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     if (ws.v3) {
       // tile tables of this block (squared distances from the block's coordinates; block 0 also fills the input-distance
       // table: x == x0 there) + the x -> x_next copy that precedes the block's coordinate update
-      tc3::k_tiles_d<<<B * N, tc::TN, 0, st>>>(ws.n_items, ws.tij, xin4, ws.td, ws.tdmax, l == 0 ? ws.td0 : nullptr,
-                                               l == 0 ? ws.td0max : nullptr, n * 3, xin, xout, xin4, xout4);
+      tc3::TileDSet s0{ws.n_items, ws.tij[0], ws.td[0], ws.tdmax[0], ws.td0[0], ws.td0max[0], nullptr, nullptr};
+      tc3::TileDSet s1{ws.n_xitems, ws.tij[1], ws.td[1], ws.tdmax[1], ws.td0[1], ws.td0max[1], ws.ts[1], ws.tcd};
+      tc3::k_tiles_d<<<dim3(B * N, 2), tc::TN, 0, st>>>(s0, s1, xin4, l == 0 ? 1 : 0, gm.norm_constant, n * 3, xin, xout, xin4, xout4);
       LAUNCH_CHECK();
       e->launches += 1;
     }
@@ -420,7 +432,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
     ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = e->use_tc ? w.wd_u : w.wd; ea.w0 = e->use_tc ? w.w0_u : w.w0; ea.w5 = w.w5;
     ea.plan = plan; ea.agg = nullptr; ea.x_out = xout; ea.nbr = ws.nbr; ea.recs = ws.xrecs; ea.n_recs = ws.n_recs ? ws.n_recs + 1 : nullptr;
-    dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st);
+    dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st, e->allow_v3_coord ? w.W2_v3 : nullptr);
     if (st2 != DL_OK) return st2;
     std::swap(xin, xout);
     std::swap(xin4, xout4);
@@ -526,6 +538,7 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaFuncSetAttribute(k_edge_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * CUT_SMEM_PER_NODE));
   if (const char* v = getenv("DL_EDGE_V3")) e->allow_v3 = atoi(v) != 0;
+  if (const char* v = getenv("DL_EDGE_V3_COORD")) e->allow_v3_coord = atoi(v) != 0;
   dl_status s = tc::configure();
   if (s == DL_OK) s = tcn::configure_node();
   if (s == DL_OK) s = tc3::configure3();
@@ -637,6 +650,7 @@ dl_status dl_finalize_weights(dl_engine* e) {
     o.b2 = pk.add(R(p + "coord_mlp.2.bias"));
     o.w5 = pk.add(R(p + "coord_mlp.4.weight"));
     o.tc = tc::pack_w2(R(p + "coord_mlp.2.weight"), tcblob, &o.descale);
+    { float d3v = 0.f; o.v3 = tc3::pack_w2_v3(R(p + "coord_mlp.2.weight"), tcblob, &d3v); }
     o.tc1 = tcn::pack_blocks(scaled(W1), IN1, 2, tcblob, &o.d1);
     o.b1u = pk.add(scaled(R(p + "coord_mlp.0.bias")));
     o.wdu = pk.add(scaled(column(W1, H, IN1, 2 * H)));
@@ -665,7 +679,7 @@ dl_status dl_finalize_weights(dl_engine* e) {
     const GOff& o = eoff[l];
     e->eq[l] = EqW{base + o.W1a, base + o.W1b, base + o.b1, base + o.wd, base + o.w0,
                    base + o.W2,  base + o.b2,  base + o.w5, tbase + o.tc, o.descale, o.wdmax, o.w0max, tbase + o.tc1, o.d1,
-                   base + o.b1u, base + o.wdu, base + o.w0u};
+                   base + o.b1u, base + o.wdu, base + o.w0u, tbase + o.v3};
   }
   e->finalized = true;
   return DL_OK;
@@ -908,7 +922,7 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
   cudaStream_t st = e->loop_stream;
   if (e->use_tc && getenv("DL_PROFILE_EDGE")) {
-    if (ws.v3) tc3::profile_edge_v3(gm, ea, w.W2_v3, ws.tm_abg, make_tile_tables(ws), e->num_sms, st);
+    if (ws.v3) tc3::profile_edge_v3(gm, ea, w.W2_v3, ws.tm_abg, make_tile_tables(ws, false), e->num_sms, st);
     else tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
   }
   if (e->use_tc && getenv("DL_PROFILE_NODE")) {

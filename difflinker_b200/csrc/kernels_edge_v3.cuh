@@ -58,16 +58,22 @@ constexpr int E3_ROWNODE = E3_EW + TN * 4;                 // int[16]  node of e
 constexpr int TS_E_BYTES = E3_ROWNODE + 64;                // 640: static epilogue-side part of a tile in global memory
 constexpr int E3_DYN = TS_E_BYTES;                         // int[8]: first-of-molecule, q, rescale, f32 operand scale, f32 descale * -log2 e
 constexpr int E3_BYTES = E3_DYN + 32;
+constexpr int E3_CD = E3_BYTES;                            // COORD only: f32[3][TN] edge weight * normalised difference * -ln2 (bulk copy of tcd[tile])
+constexpr int E3C_BYTES = E3_CD + 3 * TN * 4;
+constexpr int NES3_COORD = 4;                              // COORD launches have few tiles per CTA and bigger slots
+constexpr int E3_REGION = (NES3 * E3_BYTES > NES3_COORD * E3C_BYTES) ? NES3 * E3_BYTES : NES3_COORD * E3C_BYTES;
 constexpr int TS_BYTES = TS_P_BYTES + TS_E_BYTES;          // per-tile static record in global memory: [P part | E part]
-constexpr int O3_B2 = O3_ET + NES3 * E3_BYTES;             // f32[128]: b2 * -log2 e
-constexpr int O3_BAR = O3_B2 + H * 4;
+constexpr int O3_B2 = O3_ET + E3_REGION;                   // f32[128]: b2 * -log2 e (COORD: b2, natural domain)
+constexpr int O3_W5 = O3_B2 + H * 4;                       // f32[128]: coord_mlp.4 weight (COORD)
+constexpr int O3_PART = O3_W5 + H * 4;                     // f32[3 groups][4 quarters][4]: per-row channel sums of the COORD epilogue
+constexpr int O3_BAR = O3_PART + 256;
 constexpr int B3_FULL = 0, B3_EMPTY = B3_FULL + 8 * N_STAGE, B3_TBL = B3_EMPTY + 8 * N_STAGE, B3_TFREE = B3_TBL + 8 * NES3,
               B3_PFREE = B3_TFREE + 8 * NES3, B3_TFULL = B3_PFREE + 8 * NPS3, B3_TEMPTY = B3_TFULL + 8 * NACC3,
               B3_PFULL = B3_TEMPTY + 8 * NACC3, B3_PEMPTY = B3_PFULL + 16, B3_W = B3_PEMPTY + 16, B3_TMEMSLOT = B3_W + 8;
 constexpr int SMEM3_BYTES = O3_BAR + B3_TMEMSLOT + 16 + 1024;
 static_assert(SMEM3_BYTES <= 232448, "k_edge_v3 exceeds the 227 KB of shared memory a CTA can opt into");
 static_assert(O3_PANEL % 128 == 0 && P3_A % 16 == 0 && P3_BYTES % 16 == 0 && O3_PT % 16 == 0 && O3_ET % 16 == 0 && E3_BYTES % 16 == 0 &&
-              TS_P_BYTES % 16 == 0 && TS_E_BYTES % 16 == 0, "TMA destinations need their alignment");
+              E3C_BYTES % 16 == 0 && TS_P_BYTES % 16 == 0 && TS_E_BYTES % 16 == 0, "TMA destinations need their alignment");
 
 // Per-tile tables in global memory (tile = GCL work item of the plan): see the header comment.
 struct TileTables {
@@ -76,6 +82,10 @@ struct TileTables {
   const float* td0;       // [tiles][TN] squared distances of the call's input coordinates
   const float* tdmax;     // [tiles] max of td over the tile
   const float* td0max;    // [tiles]
+  const float* tcd;       // COORD tiles: [tiles][3][TN] edge weight * normalised coordinate difference * -ln2 of the current block
+  const int4* items;      // the tile list these tables describe (GCL: plan.items over rowidx; COORD: plan.xitems over xrowidx)
+  const int* n_items;
+  const int* rowidx;
 };
 
 // Warp layout: producers 0..15, MMA issuer 16, table warps 17..19, epilogue 20..20+NEPI-1 (20 % 4 == 0: an epilogue warp's TMEM
@@ -107,10 +117,10 @@ struct TileIter3 {
   const int* rowlist;
   int N, wi_end, wi, rt, cache_base, lane;
   int4 cache;
-  __device__ TileIter3(const Plan& p, int N_) : N(N_), rt(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31) {
-    list = p.items;
-    rowlist = p.rowidx;
-    const int total = *p.n_items;
+  __device__ TileIter3(const TileTables& tt, int N_) : N(N_), rt(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31) {
+    list = tt.items;
+    rowlist = tt.rowidx;
+    const int total = *tt.n_items;
     const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
     wi = c * per + min(c, extra);
     wi_end = wi + per + (c < extra ? 1 : 0);
@@ -138,7 +148,12 @@ struct TileIter3 {
   }
 };
 
-template <bool PROF, int NEPI>
+// COORD = true: EquivariantUpdate (egnn.py:101-125) on the same pipeline. With phi_ij = w5 . silu(...) the update is
+//   x_i += sum_j cd_ij ew_ij phi_ij / norm = sum_c w5[c] * ( sum_j (cd_ij ew_ij) m_ij[c] ) / norm,
+// i.e. the GCL epilogue's per-channel segment sum with THREE edge weights (cd_x ew, cd_y ew, cd_z ew: tile table tcd) and one
+// reduction over the 128 channels per ROW (warp shuffles, then the four lane quarters meet in shared memory in a fixed order)
+// instead of one per edge.
+template <bool PROF, int NEPI, bool COORD>
 __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, EdgeArgs a, const uint32_t* __restrict__ w2p,
                                                                     const __grid_constant__ CUtensorMap tm_b, TileTables tt,
                                                                     unsigned long long* __restrict__ prof = nullptr) {
@@ -148,6 +163,8 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int N = gm.N;
   constexpr int NG = NEPI / 4;                             // epilogue warps per TMEM lane quarter: they take the tile rows round-robin
+  constexpr int NES = COORD ? NES3_COORD : NES3;           // epilogue-side ring depth
+  constexpr int EB = COORD ? E3C_BYTES : E3_BYTES;         // epilogue-side slot size
   using RG = Regs3<NEPI>;
   const uint32_t bars = sbase + O3_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + O3_BAR + B3_TMEMSLOT);
@@ -172,14 +189,17 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
 
   if (tid == 0) {
     for (int i = 0; i < N_STAGE; ++i) { mbar_init(bars + B3_FULL + 8 * i, N_PROD_WARPS); mbar_init(bars + B3_EMPTY + 8 * i, 1); }
-    for (int i = 0; i < NES3; ++i) { mbar_init(bars + B3_TBL + 8 * i, 1); mbar_init(bars + B3_TFREE + 8 * i, NEPI); }
+    for (int i = 0; i < NES; ++i) { mbar_init(bars + B3_TBL + 8 * i, 1); mbar_init(bars + B3_TFREE + 8 * i, NEPI); }
     for (int i = 0; i < NPS3; ++i) mbar_init(bars + B3_PFREE + 8 * i, N_PROD_WARPS);
     for (int i = 0; i < NACC3; ++i) { mbar_init(bars + B3_TFULL + 8 * i, 1); mbar_init(bars + B3_TEMPTY + 8 * i, NEPI); }
     for (int i = 0; i < 2; ++i) { mbar_init(bars + B3_PFULL + 8 * i, 1); mbar_init(bars + B3_PEMPTY + 8 * i, N_PROD_WARPS); }
     mbar_init(bars + B3_W, 8);
     fence_barrier_init();
   }
-  if (tid < H) b2s[tid] = a.b2[tid] * -1.4426950408889634f;
+  if (tid < H) {
+    b2s[tid] = a.b2[tid] * -1.4426950408889634f;
+    if (COORD) reinterpret_cast<float*>(sm + O3_W5)[tid] = a.w5[tid];
+  }
   if (warp == W3_MMA) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
   __syncthreads();
@@ -192,12 +212,12 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       // =================================== table warps =================================================================
       // Tile-parallel: table warp k serves tiles t = k, k+3, ...; all three walk the same tile sequence.
       const int tw = warp - W3_TBL;
-      TileIter3 iter(a.plan, N);
+      TileIter3 iter(tt, N);
       Tile3 cur;
       int q = -1, prev_b = -1, ps = 0, pu = 0;              // ps = t % NPS3, pu = t / NPS3
       float mol_bmax = 0.f;                                 // max |B_j| over the current molecule (range bound)
       for (int t = 0;; ++t, ps = (ps + 1 == NPS3 ? 0 : ps + 1), pu += (ps == 0)) {
-        const int slot = t & (NES3 - 1);
+        const int slot = t & (NES - 1);
         const bool more = iter.next(cur);
         bool first = false;
         if (more && cur.b != prev_b) { first = true; ++q; prev_b = cur.b; }
@@ -209,9 +229,9 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
           mol_bmax = m;
         }
         if (t % N_TBL_WARPS != tw) { if (!more) break; continue; }
-        if (t >= NES3) wait_relaxed(bars + B3_TFREE + 8 * slot, ((t - NES3) / NES3) & 1, 0);     // epilogue done with tile t - 8
+        if (t >= NES) wait_relaxed(bars + B3_TFREE + 8 * slot, ((t - NES) / NES) & 1, 0);        // epilogue done with tile t - NES
         if (pu > 0) wait_relaxed(bars + B3_PFREE + 8 * ps, (pu - 1) & 1, 2);                         // producers done with tile t - 3
-        uint8_t* tb = sm + O3_ET + slot * E3_BYTES;            // epilogue-side slot (+ headers)
+        uint8_t* tb = sm + O3_ET + slot * EB;                  // epilogue-side slot (+ headers)
         uint8_t* pb = sm + O3_PT + ps * P3_BYTES;              // producer-side slot
         const uint32_t bar = bars + B3_TBL + 8 * slot;
         if (more) {
@@ -224,7 +244,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
               tma_load_2d(sbase + O3_PANEL + buf * PANEL_BYTES, &tm_b, H, cur.b * N, bars + B3_PFULL + 8 * buf);
             }
           }
-          if (lane == 0) mbar_expect_tx_only(bar, (uint32_t)(cur.nrt * H * 4 + TS_BYTES + 2 * TN * 4));
+          if (lane == 0) mbar_expect_tx_only(bar, (uint32_t)(cur.nrt * H * 4 + TS_BYTES + 2 * TN * 4 + (COORD ? 3 * TN * 4 : 0)));
           __syncwarp();
           float amax = 0.f;
           if (lane < cur.nrt) {                              // A_i rows of the tile: 512-byte bulk copies into the slot
@@ -239,6 +259,8 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
             bulk_g2s(smem_u32(pb + P3_D), tt.td + (size_t)cur.gidx * TN, TN * 4, bar);
           } else if (lane == 11) {
             bulk_g2s(smem_u32(pb + P3_D0), tt.td0 + (size_t)cur.gidx * TN, TN * 4, bar);
+          } else if (COORD && lane == 12) {
+            bulk_g2s(smem_u32(tb + E3_CD), tt.tcd + (size_t)cur.gidx * 3 * TN, 3 * TN * 4, bar);
           }
 #pragma unroll
           for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));   // lanes 0..7 hold the rows
@@ -271,12 +293,12 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
         tc_fence_after();
         int acc = 0, use = 0;
         for (int t = 0;; ++t) {
-          const int s = t & (N_STAGE - 1), slot = t & (NES3 - 1);
+          const int s = t & (N_STAGE - 1), slot = t & (NES - 1);
           wait_relaxed(bars + B3_FULL + 8 * s, (t / N_STAGE) & 1, 0);
           // the epilogue drained this accumulator (also before the end marker: its plain arrive below must not land in the
           // phase a still-running commit of tile t-3 is about to complete)
           if (use > 0) wait_on(bars + B3_TEMPTY + 8 * acc, (use - 1) & 1, 1);
-          const int Et = reinterpret_cast<const int*>(sm + O3_ET + slot * E3_BYTES + E3_HDR)[0];
+          const int Et = reinterpret_cast<const int*>(sm + O3_ET + slot * EB + E3_HDR)[0];
           if (Et <= 0) { mbar_arrive(bars + B3_TFULL + 8 * acc); break; }
           tc_fence_after();
           const uint32_t bhi = sbase + O3_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
@@ -315,11 +337,11 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
     const int e_base = 4 * grp;
     int ps = 0;
     for (int t = 0;; ++t, ps = (ps + 1 == NPS3 ? 0 : ps + 1)) {
-      const int s = t & (N_STAGE - 1), slot = t & (NES3 - 1);
-      wait_on(bars + B3_TBL + 8 * slot, (t / NES3) & 1, 0);
+      const int s = t & (N_STAGE - 1), slot = t & (NES - 1);
+      wait_on(bars + B3_TBL + 8 * slot, (t / NES) & 1, 0);
       const uint8_t* tb = sm + O3_PT + ps * P3_BYTES;        // producer-side slot
-      const int* hdr = reinterpret_cast<const int*>(sm + O3_ET + slot * E3_BYTES + E3_HDR);
-      const int* dyn = reinterpret_cast<const int*>(sm + O3_ET + slot * E3_BYTES + E3_DYN);
+      const int* hdr = reinterpret_cast<const int*>(sm + O3_ET + slot * EB + E3_HDR);
+      const int* dyn = reinterpret_cast<const int*>(sm + O3_ET + slot * EB + E3_DYN);
       const int Et = hdr[0];
       if (Et > 0 && dyn[0]) {                                // first tile of a molecule: switch panel buffers
         const int q = dyn[1], buf = q & 1;
@@ -408,11 +430,11 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
     const float2 bias2 = make_float2(bias, bias);
     int acc = 0, use = 0, rot = g;                           // rot = (g + t) % NG: the warps of a lane quarter rotate over the rows
     for (int t = 0;; ++t) {
-      const int slot = t & (NES3 - 1);
-      wait_on(bars + B3_TBL + 8 * slot, (t / NES3) & 1, 0);
+      const int slot = t & (NES - 1);
+      wait_on(bars + B3_TBL + 8 * slot, (t / NES) & 1, 0);
       wait_on(bars + B3_TFULL + 8 * acc, use & 1, 1);
       tc_fence_after();
-      const uint8_t* tb = sm + O3_ET + slot * E3_BYTES;
+      const uint8_t* tb = sm + O3_ET + slot * EB;
       const int* hdr = reinterpret_cast<const int*>(tb + E3_HDR);
       const int Et = hdr[0];
       if (Et <= 0) break;
@@ -476,7 +498,46 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
         const float accv = ((s0.x + s0.y) + (s1.x + s1.y)) + ((s2.x + s2.y) + (s3.x + s3.y));
         a.agg[(gb + rownode[rr]) * H + c] = accv / gm.normalization_factor;   // egnn.py:312-313
       };
-      for (int rr = rot; rr < nrt; rr += NG) do_row(rr);
+      // COORD: three weighted segment sums per channel, then one reduction over the channels per row (see the kernel comment)
+      auto do_row_coord = [&](int rr) {
+        const int col0 = rr * ncc4;
+        const float* wx = reinterpret_cast<const float*>(tb + E3_CD);
+        float2 ax = make_float2(0.f, 0.f), ay = ax, az = ax;
+        for (int k = 0; k < ncc4; k += 4) {
+          uint32_t r[4];
+          TMEM_LD_X4(tacc + col0 + k, r);
+          const float4 w0 = lds128(wx + col0 + k), w1 = lds128(wx + TN + col0 + k), w2 = lds128(wx + 2 * TN + col0 + k);
+          tmem_ld_wait();
+          const float2 u0 = __ffma2_rn(make_float2(__uint_as_float(r[0]), __uint_as_float(r[1])), ds2, bias2);
+          const float2 u1 = __ffma2_rn(make_float2(__uint_as_float(r[2]), __uint_as_float(r[3])), ds2, bias2);
+          float2 g0, g1;
+          usig4(u0, u1, g0, g1);
+          ax = __ffma2_rn(g0, make_float2(w0.x, w0.y), ax); ax = __ffma2_rn(g1, make_float2(w0.z, w0.w), ax);
+          ay = __ffma2_rn(g0, make_float2(w1.x, w1.y), ay); ay = __ffma2_rn(g1, make_float2(w1.z, w1.w), ay);
+          az = __ffma2_rn(g0, make_float2(w2.x, w2.y), az); az = __ffma2_rn(g1, make_float2(w2.z, w2.w), az);
+        }
+        const float w5c = reinterpret_cast<const float*>(sm + O3_W5)[c];
+        float vx = (ax.x + ax.y) * w5c, vy = (ay.x + ay.y) * w5c, vz = (az.x + az.y) * w5c;   // coord_mlp.4 (egnn.py:96-97, no bias)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          vx += __shfl_xor_sync(0xffffffffu, vx, o); vy += __shfl_xor_sync(0xffffffffu, vy, o); vz += __shfl_xor_sync(0xffffffffu, vz, o);
+        }
+        float* part = reinterpret_cast<float*>(sm + O3_PART) + g * 16;
+        named_sync(1 + g, 128);                              // the group's previous row has been read
+        if (lane == 0) { part[q * 4 + 0] = vx; part[q * 4 + 1] = vy; part[q * 4 + 2] = vz; }
+        named_sync(1 + g, 128);                              // the four lane quarters of this group meet (fixed order below: deterministic)
+        if (q == 0 && lane < 3) {
+          const float sacc = ((part[lane] + part[4 + lane]) + part[8 + lane]) + part[12 + lane];
+          const int i = rownode[rr];
+          const float lm = a.linker_mask ? a.linker_mask[gb + i] : 1.f;
+          const float xv = a.x[(gb + i) * 3 + lane];
+          const float xn = (xv + (sacc / gm.normalization_factor) * lm) * a.nm[gb + i];   // egnn.py:110-124
+          a.x_out[(gb + i) * 3 + lane] = xn;
+          reinterpret_cast<float*>(a.x4_out + gb + i)[lane] = xn;
+        }
+      };
+      if constexpr (COORD) { for (int rr = rot; rr < nrt; rr += NG) do_row_coord(rr); }
+      else { for (int rr = rot; rr < nrt; rr += NG) do_row(rr); }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(bars + B3_TEMPTY + 8 * acc); mbar_arrive(bars + B3_TFREE + 8 * slot); }
@@ -496,25 +557,26 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
 // Static part, once per plan (masks are constant over a sampling chain): panel offsets, A-row offsets, the header, the
 // edge weights (caller's int8 edge_mask value, egnn.py:55-58, times -ln2; padding slots mirror a real edge with weight 0)
 // and the (row node, column node) pair of every slot for k_tiles_d.
-__global__ void __launch_bounds__(TN) k_tiles_static(int N, Plan p, const int8_t* __restrict__ edge_mask, uint8_t* __restrict__ ts,
-                                                    int2* __restrict__ tij) {
+__global__ void __launch_bounds__(TN) k_tiles_static(int N, const int4* __restrict__ items, const int* __restrict__ n_items,
+                                                    const int* __restrict__ rowidx, const int* __restrict__ colidx,
+                                                    const int8_t* __restrict__ edge_mask, uint8_t* __restrict__ ts, int2* __restrict__ tij) {
   const int g = blockIdx.x, e = threadIdx.x;
-  if (g >= *p.n_items) return;
-  const int4 it = p.items[g];
+  if (g >= *n_items) return;
+  const int4 it = items[g];
   const int b = it.x, r0 = it.y, nrt = it.z, nc = it.w, ncc4 = (nc + 3) & ~3;
   const size_t gb = (size_t)b * N;
   int rr = e / ncc4;
   int jj = e - rr * ncc4;
   const bool valid = rr < nrt && jj < nc;
   rr = min(rr, nrt - 1); jj = min(jj, nc - 1);
-  const int i = p.rowidx[gb + r0 + rr], j = p.colidx[gb + jj];
+  const int i = rowidx[gb + r0 + rr], j = colidx[gb + jj];
   uint8_t* rec = ts + (size_t)g * TS_BYTES;
   reinterpret_cast<int*>(rec)[e] = j * (H * 4);
   if (e < TN / 4) reinterpret_cast<int*>(rec + TN * 4)[e] = min((4 * e) / ncc4, nrt - 1) * (H * 4);
   uint8_t* er = rec + TS_P_BYTES;
   if (e < 16) {
     reinterpret_cast<int*>(er + E3_HDR)[e] = e == 0 ? nrt * ncc4 : e == 1 ? nrt : e == 2 ? ncc4 : e == 3 ? b : 0;
-    reinterpret_cast<int*>(er + E3_ROWNODE)[e] = e < nrt ? p.rowidx[gb + r0 + e] : 0;
+    reinterpret_cast<int*>(er + E3_ROWNODE)[e] = e < nrt ? rowidx[gb + r0 + e] : 0;
   }
   float ew = 0.f;
   if (valid) ew = edge_mask ? (float)edge_mask[gb * N + (size_t)i * N + j] : 1.0f;
@@ -523,26 +585,38 @@ __global__ void __launch_bounds__(TN) k_tiles_static(int N, Plan p, const int8_t
 }
 
 // Squared distances of every tile slot from the coordinates `x4` (egnn.py:297-298; with the call's input coordinates also
-// egnn.py:220 -- at block 0 both coincide, so td0 is written by the same launch) and their per-tile maxima. Also carries
-// the x -> x_next copy that precedes a block's coordinate update (rows the update does not touch keep x).
-__global__ void __launch_bounds__(TN) k_tiles_d(const int* __restrict__ n_items, const int2* __restrict__ tij, const float4* __restrict__ x4,
-                                               float* __restrict__ td, float* __restrict__ tdmax, float* __restrict__ td0,
-                                               float* __restrict__ td0max, int n3, const float* __restrict__ xsrc, float* __restrict__ xdst,
+// egnn.py:220 -- at block 0 both coincide, so td0 is written by the same launch) and their per-tile maxima, for the GCL tile
+// set (blockIdx.y = 0) and the COORD tile set (blockIdx.y = 1); the latter also gets its three weighted edge-weight arrays
+// ew * (x_i - x_j) / (sqrt(d + 1e-8) + norm_constant) (egnn.py:299-300, 107-109; ew already carries the -ln2). The y = 0 CTAs
+// also carry the x -> x_next copy that precedes a block's coordinate update (rows the update does not touch keep x).
+struct TileDSet {
+  const int* n_items; const int2* tij; float* td; float* tdmax; float* td0; float* td0max;
+  const uint8_t* ts; float* tcd;   // COORD set only (else null)
+};
+__global__ void __launch_bounds__(TN) k_tiles_d(TileDSet s0, TileDSet s1, const float4* __restrict__ x4, int write_d0, float norm_constant,
+                                               int n3, const float* __restrict__ xsrc, float* __restrict__ xdst,
                                                const float4* __restrict__ x4src, float4* __restrict__ x4dst) {
   __shared__ float red[TN / 32];
   const int g = blockIdx.x, e = threadIdx.x;
-  if (xdst != nullptr) {
+  const TileDSet& s = blockIdx.y == 0 ? s0 : s1;
+  if (blockIdx.y == 0 && xdst != nullptr) {
     const int i = g * TN + e;
     if (i < n3) xdst[i] = xsrc[i];
     if (i * 3 < n3) x4dst[i] = x4src[i];
   }
-  if (g >= *n_items) return;
-  const int2 ij = tij[(size_t)g * TN + e];
+  if (s.n_items == nullptr || g >= *s.n_items) return;
+  const int2 ij = s.tij[(size_t)g * TN + e];
   const float4 xi = x4[ij.x], xj = x4[ij.y];
   const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
   const float d = dx * dx + dy * dy + dz * dz;
-  td[(size_t)g * TN + e] = d;
-  if (td0 != nullptr) td0[(size_t)g * TN + e] = d;
+  s.td[(size_t)g * TN + e] = d;
+  if (write_d0) s.td0[(size_t)g * TN + e] = d;
+  if (s.tcd != nullptr) {
+    const float ew = reinterpret_cast<const float*>(s.ts + (size_t)g * TS_BYTES + TS_P_BYTES + E3_EW)[e];
+    const float inv = ew / (sqrtf(d + 1e-8f) + norm_constant);
+    float* o = s.tcd + (size_t)g * 3 * TN;
+    o[e] = dx * inv; o[TN + e] = dy * inv; o[2 * TN + e] = dz * inv;
+  }
   float m = d;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
@@ -550,8 +624,8 @@ __global__ void __launch_bounds__(TN) k_tiles_d(const int* __restrict__ n_items,
   __syncthreads();
   if (e == 0) {
     m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
-    tdmax[g] = m;
-    if (td0max != nullptr) td0max[g] = m;
+    s.tdmax[g] = m;
+    if (write_d0) s.td0max[g] = m;
   }
 }
 
@@ -613,19 +687,21 @@ inline dl_status make_panel_map(CUtensorMap* out, const float* AB, int B, int N)
 }
 
 inline dl_status configure3() {
-  const bool ok = cudaFuncSetAttribute(k_edge_v3<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<false, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<true, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
+  const bool ok = cudaFuncSetAttribute(k_edge_v3<false, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<true, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<false, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<true, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<false, 12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
   return ok ? DL_OK : DL_ERR_CUDA;
 }
 
-inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt, int num_sms,
-                           cudaStream_t st) {
+inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt,
+                           int num_sms, cudaStream_t st) {
   static const int nepi = getenv("DL_V3_NEPI") ? atoi(getenv("DL_V3_NEPI")) : 12;      // experiment switch: epilogue warps
   const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
-  if (nepi == 8) k_edge_v3<false, 8><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
-  else k_edge_v3<false, 12><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
+  if (coord) k_edge_v3<false, 12, true><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
+  else if (nepi == 8) k_edge_v3<false, 8, false><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
+  else k_edge_v3<false, 12, false><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
 }
 
 inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt, int num_sms,
@@ -634,8 +710,8 @@ inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void*
   if (cudaMalloc(&d, (size_t)num_sms * 16 * 8) != cudaSuccess) return DL_ERR_CUDA;
   cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
   const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
-  if (getenv("DL_V3_NEPI") && atoi(getenv("DL_V3_NEPI")) == 8) k_edge_v3<true, 8><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
-  else k_edge_v3<true, 12><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
+  if (getenv("DL_V3_NEPI") && atoi(getenv("DL_V3_NEPI")) == 8) k_edge_v3<true, 8, false><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
+  else k_edge_v3<true, 12, false><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
   if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
   std::vector<unsigned long long> h((size_t)num_sms * 16);
   cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);

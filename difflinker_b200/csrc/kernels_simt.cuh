@@ -75,8 +75,15 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, int col_pad, i
     }
     if (nxr[b] > 0 && c > 0) {
       xmols[xc++] = b;
-      int per = c >= tile_edges ? 1 : tile_edges / c;
-      if (per > max_rows) per = max_rows;
+      int per;
+      if (col_pad > 1) {                                     // v3 kernel: same rows-per-tile rule as its GCL tiles
+        const int cp = (c + col_pad - 1) / col_pad * col_pad;
+        per = cp >= tile_edges ? 1 : tile_edges / cp;
+        if (per > max_rows_gcl) per = max_rows_gcl;
+      } else {
+        per = c >= tile_edges ? 1 : tile_edges / c;
+        if (per > max_rows) per = max_rows;
+      }
       for (int r0 = 0; r0 < nxr[b]; r0 += per) xitems[xi++] = make_int4(b, r0, min(per, nxr[b] - r0), c);
     }
   }
