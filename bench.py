@@ -36,6 +36,9 @@ def parse_args():
     ap.add_argument("--coord-gain", type=float, default=None,
                     help="scale of coord_mlp.4 on top of the default init; default 100 (SURVEY 8c) for N <= 64, 1 above: "
                          "with 100 and hundreds of neighbours the random-weight dynamics blow up to |x| ~ 5e3 within steps")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: every rank samples its own batches (default); strong: ONE batch per step is split across the "
+                         "ranks (distributed.sample_chain_sharded: same result as on one GPU)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -100,13 +103,12 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_reference_step(oracle, sd, ocfg, sample):
-    """One bounded sample of the reference algorithm on the CPU: a single Dynamics.forward (edge-list formulation,
-    egnn.py:374-447) over `sample['B']` molecules of the workload."""
+def cpu_reference_step(fwd, sample):
+    """One bounded sample of the reference algorithm on the CPU: a single Dynamics.forward (egnn.py:374-447) over
+    `sample['B']` molecules of the workload."""
     t0 = time.perf_counter()
     with torch.no_grad():
-        oracle.dynamics_forward(sd, ocfg, sample["t"], sample["z"], sample["node_mask"], sample["linker_mask"],
-                                sample["edge_mask"], sample["context"])
+        fwd(sample["t"], sample["z"], sample["node_mask"], sample["linker_mask"], sample["edge_mask"], sample["context"])
     return time.perf_counter() - t0
 
 
@@ -128,30 +130,61 @@ def build_cpu_sample(spec, hp, nb):
                     linker_mask=batch['linker_mask'], edge_mask=batch['edge_mask'], context=batch['fragment_mask'])
 
 
+def staged_reference_dynamics(hp, sd):
+    """The UNMODIFIED reference `src.egnn.Dynamics` (staged by oracle/build_ref.py under oracle/_ref/), carrying the same
+    weights as the oracle port's sample. None when the staging directory is absent."""
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "oracle", "_ref")
+    if not os.path.isfile(os.path.join(root, "src", "egnn.py")):
+        return None
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import importlib
+    egnn = importlib.import_module("src.egnn")
+    dyn = egnn.Dynamics(in_node_nf=hp['in_node_nf'], n_dims=3, context_node_nf=hp['context_node_nf'], hidden_nf=128,
+                        n_layers=hp['n_layers'], norm_constant=hp['norm_constant'], inv_sublayers=hp['inv_sublayers'],
+                        normalization_factor=hp['normalization_factor'])
+    dyn.load_state_dict(sd, strict=True)
+    return dyn.eval()
+
+
 def cpu_reference_measure(spec, hp, steps, warmup):
-    """Times the oracle port of Dynamics.forward on the host. torch's intra-op pool is slower with all 100+ hardware
-    threads on these small ops than with a few dozen, so a quick sweep on a small sample picks the thread count the
-    reference would be best run with; the measurement then uses it. Returns (s_per_forward, nb, threads, ocfg)."""
+    """Times Dynamics.forward on the host cores: the reference's own module when oracle/_ref/ is staged (kind "reference";
+    its FC edge list is cached by the warm-up call, egnn.py:449-467), else the oracle port (kind "port"). torch's intra-op
+    pool is slower with all 100+ hardware threads on these small ops than with a few dozen, so a quick sweep on a small
+    sample picks the thread count the reference is best run with. Returns (s_per_forward, nb, threads, kind, s_port)."""
     from oracle import difflinker_oracle as orc
     cores = os.cpu_count() or 1
     ocfg = orc.OracleConfig(in_node_nf=hp['in_node_nf'], context_node_nf=hp['context_node_nf'], n_layers=hp['n_layers'],
                             inv_sublayers=hp['inv_sublayers'], norm_constant=hp['norm_constant'],
                             normalization_factor=hp['normalization_factor'])
+
+    def port_fwd(sd):
+        return lambda t, z, nm, lm, em, ctx: orc.dynamics_forward(sd, ocfg, t, z, nm, lm, em, ctx)
+
     sd_small, small = build_cpu_sample(spec, hp, min(spec.B, 8))
+    ref_small = staged_reference_dynamics(hp, sd_small)
+    fwd_small = ref_small.forward if ref_small is not None else port_fwd(sd_small)
     best_t, best = cores, None
     for th in sorted({min(cores, c) for c in (8, 16, 32, 64, cores)}):
         torch.set_num_threads(th)
-        cpu_reference_step(orc, sd_small, ocfg, small)
-        dt = cpu_reference_step(orc, sd_small, ocfg, small)
+        cpu_reference_step(fwd_small, small)
+        dt = cpu_reference_step(fwd_small, small)
         if best is None or dt < best:
             best, best_t = dt, th
     torch.set_num_threads(best_t)
     nb = min(spec.B, 64)
     sd, sample = build_cpu_sample(spec, hp, nb)
-    for _ in range(warmup):
-        cpu_reference_step(orc, sd, ocfg, sample)
-    ts = [cpu_reference_step(orc, sd, ocfg, sample) for _ in range(steps)]
-    return sum(ts) / len(ts), nb, best_t
+    ref = staged_reference_dynamics(hp, sd)
+    kind = "reference" if ref is not None else "port"
+    fwd = ref.forward if ref is not None else port_fwd(sd)
+    for _ in range(max(warmup, 1)):
+        cpu_reference_step(fwd, sample)
+    ts = [cpu_reference_step(fwd, sample) for _ in range(steps)]
+    s_port = None
+    if ref is not None:                                      # the port beside it, one call (for the record)
+        cpu_reference_step(port_fwd(sd), sample)
+        s_port = cpu_reference_step(port_fwd(sd), sample)
+    return sum(ts) / len(ts), nb, best_t, kind, s_port
 
 
 def run_reference_arm(args, spec, hp, rank, world):
@@ -159,7 +192,7 @@ def run_reference_arm(args, spec, hp, rank, world):
     molecules/s is extrapolated as B_sample / ((T+1) * s_per_forward)."""
     if rank != 0:
         return
-    s_fwd, nb, cores = cpu_reference_measure(spec, hp, args.steps, args.warmup)
+    s_fwd, nb, cores, kind, s_port = cpu_reference_measure(spec, hp, args.steps, args.warmup)
     T = args.T or spec.T
     value = nb / ((T + 1) * s_fwd)
     sample_desc = f"{args.steps} Dynamics.forward calls over {nb} of {spec.B} molecules (N={spec.N}, L={spec.L}); x(T+1)={T + 1} extrapolated"
@@ -168,7 +201,8 @@ def run_reference_arm(args, spec, hp, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * s_fwd,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": spec.name, "B": spec.B, "N": spec.N, "n_layers": spec.L, "T": T, "hidden_nf": 128},
-        "cpu_baseline": {"value": value, "unit": "molecules/s", "cores": cores, "kind": "port", "sample": sample_desc},
+        "cpu_baseline": {"value": value, "unit": "molecules/s", "cores": cores, "kind": kind, "sample": sample_desc,
+                         "port_value": (nb / ((T + 1) * s_port)) if s_port else None},
         "e2e": {"value": value, "unit": "molecules/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -245,7 +279,20 @@ def main():
         return float(t.item())
 
     # ---------------- kernel-resident arm: inputs in HBM, CUDA events --------------------------------------
-    resident = [resident_inputs(b) for b in host_batches]
+    strong = args.scaling == "strong" and world > 1
+    if strong:
+        # every rank holds the SAME batches (seed without the rank term) and samples its slice of each
+        from difflinker_b200.distributed import shard_range, slice_sampler_inputs
+        host_batches = []
+        for i in range(n_batches):
+            data = collate(synthetic.make_items(spec, seed_offset=1 + i))
+            host_batches.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()})
+        lo, hi = shard_range(spec.B, rank, world)
+        resident = [slice_sampler_inputs(resident_inputs(b), lo, hi) for b in host_batches]
+        for kw in resident:
+            kw["batch_slice"] = (lo, spec.B)
+    else:
+        resident = [resident_inputs(b) for b in host_batches]
     torch.cuda.synchronize(dev)
     for i in range(args.warmup):
         edm.sample_chain(**resident[i], keep_frames=1)
@@ -257,7 +304,9 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     loop_ms = []
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for i in range(args.steps):
+        l2_flush.zero_()                                                 # larger than the 126 MB L2
         chain = edm.sample_chain(**resident[args.warmup + i], keep_frames=1)
         loop_ms.append(edm.last_loop_ms)
     ev1.record()
@@ -265,7 +314,7 @@ def main():
     clocks = sampler.stop()
     launches = lib.dl_launch_count(eng) - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    mols = world * spec.B * args.steps
+    mols = (1 if strong else world) * spec.B * args.steps
     value = mols / (ms_total * 1e-3)
     assert torch.isfinite(chain).all()
 
@@ -274,7 +323,11 @@ def main():
     if not args.no_e2e:
         def e2e_step(data):
             d = to_device(data)                                          # H2D of this step's inputs
-            ch, nm = ddpm.sample_chain(d, keep_frames=1)                 # the call generate.py makes (generate.py:156)
+            if strong:
+                from difflinker_b200.distributed import sample_chain_sharded
+                ch, nm = sample_chain_sharded(ddpm, d, keep_frames=1)    # slices + one all_gather of the final frames
+            else:
+                ch, nm = ddpm.sample_chain(d, keep_frames=1)             # the call generate.py makes (generate.py:156)
             return ch.cpu(), nm.cpu()                                    # D2H of the step's result
         e2e_step(host_batches[0])
         barrier()
@@ -282,6 +335,7 @@ def main():
         wall0 = time.perf_counter()
         t0.record()
         for i in range(args.steps):
+            l2_flush.zero_()
             ch, nm = e2e_step(host_batches[args.warmup + i])
         t1.record()
         barrier()
@@ -333,26 +387,55 @@ def main():
                "compute_frac": flops_fwd / (fwd_ms * 1e-3) / 1e12 / peaks["bf16_tflops_sustained"],
                "hbm_frac": bytes_fwd / (fwd_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]}
 
+    # ---------------- parity of the benchmarked launch: one Dynamics.forward at the timed shape vs the oracle -------------
+    parity = None
+    if rank == 0:
+        from oracle import difflinker_oracle as orc
+        k = min(4, spec.B)
+        hbp = host_batches[args.warmup]
+        dbp = to_device(hbp)
+        from difflinker_b200.ddpm import sampler_inputs
+        kwp = sampler_inputs(ddpm, dbp)
+        gp = torch.Generator().manual_seed(17)
+        zp = torch.cat([kwp['x'].cpu(), kwp['h'].cpu() / 4], dim=2)
+        zp = zp * kwp['fragment_mask'].cpu() + torch.randn(zp.shape, generator=gp) * kwp['linker_mask'].cpu()
+        tp = torch.full((spec.B, 1), 0.4)
+        with torch.no_grad():
+            got = edm.dynamics(tp.to(dev), zp.to(dev), kwp['node_mask'], kwp['linker_mask'], kwp['edge_mask'], kwp['context']).cpu()
+            ocfg = orc.OracleConfig(in_node_nf=hp['in_node_nf'], context_node_nf=hp['context_node_nf'], n_layers=hp['n_layers'],
+                                    inv_sublayers=hp['inv_sublayers'], norm_constant=hp['norm_constant'],
+                                    normalization_factor=hp['normalization_factor'], graph_type=hp['graph_type'])
+            N = spec.N if not hasattr(kwp['x'], 'shape') else kwp['x'].shape[1]
+            em = kwp['edge_mask'].cpu()
+            em_k = em[:k * (em.shape[0] // spec.B)]
+            sdp = {n: v.detach().cpu() for n, v in edm.dynamics.state_dict().items()}
+            want = orc.dynamics_forward(sdp, ocfg, tp[:k], zp[:k], kwp['node_mask'].cpu()[:k], kwp['linker_mask'].cpu()[:k], em_k,
+                                        kwp['context'].cpu()[:k])
+        err = (got[:k] - want).abs().max().item() / max(want.abs().max().item(), 1e-30)
+        parity = {"rel_err": err, "molecules": k, "of_batch": spec.B,
+                  "what": "Dynamics.forward of the benchmarked (B,N,L) launch vs the oracle on the first molecules; tolerance 1e-4"}
+
     # ---------------- CPU baseline (oracle port of the reference algorithm), rank 0 at N=1 only -------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        s_fwd, nb, cores = cpu_reference_measure(spec, hp, 3, 1)
-        cpu = {"value": nb / ((T + 1) * s_fwd), "unit": "molecules/s", "cores": cores, "kind": "port",
+        s_fwd, nb, cores, kind, s_port = cpu_reference_measure(spec, hp, 3, 1)
+        cpu = {"value": nb / ((T + 1) * s_fwd), "unit": "molecules/s", "cores": cores, "kind": kind,
                "sample": f"3 Dynamics.forward calls over {nb} of {spec.B} molecules ({cores} torch threads, best of a sweep), extrapolated x{T + 1}",
-               "s_per_forward": s_fwd}
+               "s_per_forward": s_fwd, "port_value": (nb / ((T + 1) * s_port)) if s_port else None}
 
     if rank == 0:
         line = {
             "metric": "molecules/sec (T=%d denoising)" % T, "value": value, "unit": "molecules/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": spec.name, "B": spec.B, "N": spec.N, "n_layers": spec.L, "T": T, "hidden_nf": 128,
                        "edge_impl": args.edge_impl, "coord_gain": coord_gain,
+                       "noise": "drawn inside the kernels in the reference's torch.randn order (Philox4x32-10, dl_sample_chain_rng)",
                        "edges_per_launch": int(sum(e for e, _ in e_b)), "cut_graph_device_stats": cut_stats,
-                       "l2": "inputs larger than L2: every timed step consumes a fresh %.0f MB noise tensor"
-                             % ((T + 2) * spec.B * spec.N * (3 + spec.F) * 4 / 1e6)},
+                       "l2": "flushed: a 256 MB buffer is written before every timed step (inside the timed region, ~0.05 ms); "
+                             "every step also samples a fresh batch"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "forward": forward,
-            "cpu_baseline": cpu, "loop_ms_device": loop_ms,
+            "cpu_baseline": cpu, "loop_ms_device": loop_ms, "parity": parity,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -76,6 +76,8 @@ struct dl_engine {
   dl_config cfg{};
   int D = 0;
   int num_sms = 0;
+  int max_threads_per_sm = 2048;
+  int slice_B_full = 0, slice_b0 = 0;   // dl_set_noise_slice: this engine samples rows [b0, b0 + B) of a B_full batch
   bool finalized = false;
   std::map<std::string, std::vector<float>> raw;
   float* wblob = nullptr;      // packed fp32 weights
@@ -280,6 +282,7 @@ struct FwdIO {
   // sampler mode
   bool sampler = false; bool inpaint = false; const float* xh0 = nullptr; const float* upd_linker_mask = nullptr;
   const float* fragment_mask = nullptr; const float* noise = nullptr; float* chain = nullptr;
+  NoiseRng rng{};
   int T = 0; float norm0 = 1.f, norm1 = 1.f, bias1 = 0.f;
 };
 
@@ -444,7 +447,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   const bool fused_update = io.sampler && !io.inpaint;
   fa.out = fused_update ? nullptr : (io.sampler ? ws.eps : io.out);
   if (fused_update) {
-    fa.z = ws.z; fa.fragment_mask = io.fragment_mask; fa.linker_mask = io.linker_mask; fa.noise = io.noise;
+    fa.z = ws.z; fa.fragment_mask = io.fragment_mask; fa.linker_mask = io.linker_mask; fa.noise = io.noise; fa.rng = io.rng;
     fa.coef = e->coef_dev; fa.step_fin = e->step_ctr + 1; fa.step_prep = e->step_ctr; fa.T = io.T;
     fa.norm0 = io.norm0; fa.norm1 = io.norm1; fa.bias1 = io.bias1; fa.chain = io.chain;
   } else if (io.sampler) {
@@ -526,6 +529,7 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   e->cfg = *cfg;
   e->D = D;
   e->num_sms = prop.multiProcessorCount;
+  e->max_threads_per_sm = prop.maxThreadsPerMultiProcessor;
   e->use_tc = tc::AVAILABLE && cfg->edge_impl != DL_EDGE_SIMT;
   CK(cudaStreamCreateWithFlags(&e->loop_stream, cudaStreamNonBlocking));
   CK(cudaEventCreateWithFlags(&e->ev_in, cudaEventDisableTiming));
@@ -742,17 +746,89 @@ dl_status dl_dynamics_forward_host(dl_engine* e, int32_t B, int32_t N, const flo
   return any ? DL_NAN_DETECTED : DL_OK;
 }
 
+// torch's launch geometry for randn(numel) on this device (see NoiseRng)
+static void randn_geometry(const dl_engine* e, long long numel, int* S, unsigned long long* consumed) {
+  long long grid = (numel + 255) / 256;
+  grid = std::min<long long>(grid, (long long)e->num_sms * (e->max_threads_per_sm / 256));
+  grid = std::max<long long>(grid, 1);
+  *S = (int)(256 * grid);
+  *consumed = (unsigned long long)(((numel - 1) / (4LL * *S) + 1) * 4);
+}
+static NoiseRng make_rng(const dl_engine* e, int B, int N, uint64_t seed, uint64_t offset) {
+  NoiseRng q{};
+  const int F = e->cfg.in_node_nf;
+  unsigned long long cx = 0, ch = 0;
+  const int B_full = e->slice_B_full > 0 ? e->slice_B_full : B;   // geometry of the FULL batch's randn calls
+  randn_geometry(e, (long long)B_full * N * 3, &q.Sx, &cx);
+  randn_geometry(e, (long long)B_full * N * F, &q.Sh, &ch);
+  q.seed = seed; q.offset = offset; q.cx = cx; q.per_draw = cx + ch; q.F = F; q.on = 1;
+  q.g0 = e->slice_B_full > 0 ? e->slice_b0 * N : 0;
+  return q;
+}
+
+static dl_status sample_chain_impl(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                                   const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                                   const float* linker_mask, const int8_t* edge_mask, const float* context,
+                                   const float* noise, const NoiseRng* rng, const dl_step_coef* coef, const float* norm,
+                                   float* chain, int32_t* nan_flags, void* stream);
+
 dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
                           const float* xh, const int8_t* node_mask, const float* fragment_mask,
                           const float* linker_mask, const int8_t* edge_mask, const float* context,
                           const float* noise, const dl_step_coef* coef, const float* norm, float* chain,
                           int32_t* nan_flags, void* stream) {
+  if (!noise) { set_err("null argument (noise): use dl_sample_chain_rng to draw on the device"); return DL_ERR_INVALID; }
+  return sample_chain_impl(e, sampler, B, N, T, keep_frames, xh, node_mask, fragment_mask, linker_mask, edge_mask, context, noise,
+                           nullptr, coef, norm, chain, nan_flags, stream);
+}
+
+dl_status dl_sample_chain_rng(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                              const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                              const float* linker_mask, const int8_t* edge_mask, const float* context, uint64_t seed,
+                              uint64_t offset, uint64_t* offset_consumed, const dl_step_coef* coef, const float* norm,
+                              float* chain, int32_t* nan_flags, void* stream) {
+  dl_status s = check_shapes(e, B, N);
+  if (s != DL_OK) return s;
+  if (e->slice_B_full > 0 && e->slice_b0 + B > e->slice_B_full) { set_err("batch slice [%d, %d) exceeds the full batch %d", e->slice_b0, e->slice_b0 + B, e->slice_B_full); return DL_ERR_INVALID; }
+  if (sampler != DL_SAMPLER_LINKER) { set_err("device-side noise is implemented for the linker sampler (the inpainting sampler takes prepared slabs)"); return DL_ERR_UNSUPPORTED; }
+  if (offset % 4 != 0) { set_err("philox offset must be a multiple of 4 (torch.Generator.get_offset())"); return DL_ERR_INVALID; }
+  const NoiseRng q = make_rng(e, B, N, seed, offset);
+  if (offset_consumed) *offset_consumed = (uint64_t)(T + 2) * q.per_draw;
+  return sample_chain_impl(e, sampler, B, N, T, keep_frames, xh, node_mask, fragment_mask, linker_mask, edge_mask, context, nullptr,
+                           &q, coef, norm, chain, nan_flags, stream);
+}
+
+dl_status dl_set_noise_slice(dl_engine* e, int32_t B_full, int32_t b0) {
+  if (!e) { set_err("null engine"); return DL_ERR_INVALID; }
+  if (B_full < 0 || b0 < 0 || (B_full > 0 && b0 >= B_full)) { set_err("bad batch slice (%d of %d)", b0, B_full); return DL_ERR_INVALID; }
+  e->slice_B_full = B_full; e->slice_b0 = B_full > 0 ? b0 : 0;
+  return DL_OK;
+}
+
+dl_status dl_noise_fill(dl_engine* e, int32_t n_draws, int32_t B, int32_t N, uint64_t seed, uint64_t offset, float* out,
+                        uint64_t* offset_consumed, void* stream) {
+  dl_status s = check_shapes(e, B, N);
+  if (s != DL_OK) return s;
+  if (!out || n_draws < 1) { set_err("null argument"); return DL_ERR_INVALID; }
+  CK(cudaSetDevice(e->cfg.device));
+  const NoiseRng q = make_rng(e, B, N, seed, offset);
+  if (offset_consumed) *offset_consumed = (uint64_t)n_draws * q.per_draw;
+  k_noise_fill<<<e->num_sms * 4, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(n_draws, B * N, 3 + e->cfg.in_node_nf, q, out);
+  LAUNCH_CHECK();
+  return DL_OK;
+}
+
+static dl_status sample_chain_impl(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                                   const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                                   const float* linker_mask, const int8_t* edge_mask, const float* context,
+                                   const float* noise, const NoiseRng* rng, const dl_step_coef* coef, const float* norm,
+                                   float* chain, int32_t* nan_flags, void* stream) {
   dl_status s = check_shapes(e, B, N);
   if (s != DL_OK) return s;
   if (sampler != DL_SAMPLER_LINKER && sampler != DL_SAMPLER_INPAINT) { set_err("unknown sampler %d", sampler); return DL_ERR_INVALID; }
   const bool inpaint = sampler == DL_SAMPLER_INPAINT;
   if (inpaint != (e->cfg.centering != 0)) { set_err("the inpainting sampler needs a model built with centering=1 (and vice versa)"); return DL_ERR_INVALID; }
-  if (!xh || !node_mask || !fragment_mask || !linker_mask || !noise || !coef || !norm || !chain) {
+  if (!xh || !node_mask || !fragment_mask || !linker_mask || (!noise && !rng) || !coef || !norm || !chain) {
     set_err("null argument"); return DL_ERR_INVALID;
   }
   if (T < 1 || keep_frames < 1 || keep_frames > T) { set_err("need 1 <= keep_frames <= T"); return DL_ERR_INVALID; }
@@ -783,7 +859,7 @@ dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, i
     // z_T = COM-free masked noise on every atom (edm.py:565); the caller's slab 0 is already masked and projected
     CK(cudaMemcpyAsync(e->ws.z, noise, (size_t)n * xd * sizeof(float), cudaMemcpyDeviceToDevice, st));
   } else {
-    k_init_z<<<(n * xd + 255) / 256, 256, 0, st>>>(n, xd, xh, fragment_mask, linker_mask, noise, e->ws.z);
+    k_init_z<<<(n * xd + 255) / 256, 256, 0, st>>>(n, xd, xh, fragment_mask, linker_mask, noise, rng ? *rng : NoiseRng{}, e->ws.z);
     LAUNCH_CHECK();
     e->launches += 1;
   }
@@ -794,6 +870,7 @@ dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, i
   io.sampler = true; io.inpaint = inpaint; io.xh0 = xh; io.upd_linker_mask = linker_mask;
   io.node_mask = node_mask; io.linker_mask = inpaint ? nullptr : linker_mask; io.edge_mask = edge_mask;
   io.context = context; io.nan_flags = nan_flags; io.fragment_mask = fragment_mask; io.noise = noise;
+  if (rng) io.rng = *rng;
   io.chain = chain; io.T = T; io.norm0 = norm[0]; io.norm1 = norm[1]; io.bias1 = norm[2];
 
   // capture ONE reverse step; the step index lives on the device, so the same graph serves all T+1 steps
@@ -806,25 +883,28 @@ dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, i
   if (s != DL_OK) { if (graph) cudaGraphDestroy(graph); return s; }
   if (ce != cudaSuccess) { set_err("cudaStreamEndCapture -> %s", cudaGetErrorString(ce)); return DL_ERR_CUDA; }
   const int64_t per_step = e->launches - before;
-  CK(cudaGraphInstantiate(&exec, graph, 0));
-  CK(cudaEventRecord(e->ev_t0, st));
-  for (int r = 0; r <= T; ++r) {
-    cudaError_t le = cudaGraphLaunch(exec, st);
-    if (le != cudaSuccess) {
-      set_err("cudaGraphLaunch step %d -> %s", r, cudaGetErrorString(le));
-      cudaGraphExecDestroy(exec); cudaGraphDestroy(graph);
-      return DL_ERR_CUDA;
-    }
+  // every exit below releases the captured graph and its executable (destruction is deferred by the runtime until the
+  // launched work has finished)
+  cudaError_t ge = cudaGraphInstantiate(&exec, graph, 0);
+  if (ge == cudaSuccess) ge = cudaEventRecord(e->ev_t0, st);
+  int failed_step = -1;
+  for (int r = 0; ge == cudaSuccess && r <= T; ++r) {
+    ge = cudaGraphLaunch(exec, st);
+    if (ge != cudaSuccess) failed_step = r;
   }
-  CK(cudaEventRecord(e->ev_t1, st));
+  if (ge == cudaSuccess) ge = cudaEventRecord(e->ev_t1, st);
+  if (ge == cudaSuccess && user != st) {
+    ge = cudaEventRecord(e->ev_out, st);
+    if (ge == cudaSuccess) ge = cudaStreamWaitEvent(user, e->ev_out, 0);
+  }
+  if (exec) cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  if (ge != cudaSuccess) {
+    if (failed_step >= 0) set_err("cudaGraphLaunch step %d -> %s", failed_step, cudaGetErrorString(ge));
+    else set_err("%s:%d reverse-loop graph -> %s", __FILE__, __LINE__, cudaGetErrorString(ge));
+    return DL_ERR_CUDA;
+  }
   e->launches = before + per_step * (T + 1);
-  if (user != st) {
-    CK(cudaEventRecord(e->ev_out, st));
-    CK(cudaStreamWaitEvent(user, e->ev_out, 0));
-  }
-  // exec/graph destruction is deferred by the runtime until the launched work has finished
-  CK(cudaGraphExecDestroy(exec));
-  CK(cudaGraphDestroy(graph));
   return DL_OK;
 }
 

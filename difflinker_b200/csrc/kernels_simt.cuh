@@ -2,6 +2,8 @@
 // output/z-update.  The tcgen05 edge kernel (kernels_tc.cuh) replaces k_edge_simt on the product path;
 // k_edge_simt stays as the on-device cross-check (dl_selftest_tc, DL_EDGE_SIMT).
 #pragma once
+#include <curand_kernel.h>
+
 #include "common.cuh"
 
 namespace dl {
@@ -750,6 +752,45 @@ __global__ void k_copy_x(int n3, const float* __restrict__ src, float* __restric
 // and -- in sampler mode -- the reverse-diffusion update of z fused in (edm.py:196-206 / 225-233).
 // 16 threads per node (one per output column), 16 nodes per CTA.
 // ------------------------------------------------------------------------------------------------
+// ------------------------------------------------------------------------------------------------
+// Device-side noise in the reference's stream order. The reference draws, per noise sample, torch.randn(B,N,3) then
+// torch.randn(B,N,F) (edm.py:328-340, utils.py:189-192). On a CUDA device torch serves each call with Philox4x32-10:
+//   grid = min(SMs * (maxThreadsPerSM / 256), ceil(numel / 256)) blocks of 256 threads, thread idx = subsequence idx,
+//   element e is component (e mod 4S) / S of the (e / 4S)-th curand_normal4 of thread e mod S (S = 256 * grid), and the
+//   call advances the generator's offset by ((numel - 1) / (4S) + 1) * 4
+// (ATen/native/cuda/DistributionTemplates.h: calc_execution_policy, distribution_elementwise_grid_stride_kernel,
+// normal_and_transform). Reproducing that mapping with the same cuRAND device functions gives the SAME numbers the
+// reference would draw on this GPU for the same seed and offset -- without the (T+2) x 2 randn launches, the
+// (T+2,B,N,3+F) slab and its interleaving copy.
+// ------------------------------------------------------------------------------------------------
+struct NoiseRng {
+  unsigned long long seed, offset;   // torch CUDA generator state when EDM.sample_chain was entered
+  unsigned long long per_draw;       // offset consumed by one draw (x call + h call)
+  unsigned long long cx;             // ... by the x call alone
+  int Sx, Sh;                        // 256 * grid of the x / h call
+  int F;
+  int on;                            // 0: read the caller's noise tensor instead
+  int g0;                            // first node row of this engine's slice inside the full batch (strong scaling: the slice
+                                     // consumes exactly the rows of the full-batch draw, so results do not depend on the split)
+};
+__device__ __forceinline__ float philox_normal_elem(unsigned long long seed, unsigned long long offset, int S, long long e) {
+  const long long per_round = 4LL * S;
+  const long long rr = e / per_round;
+  const int rem = (int)(e - rr * per_round);
+  const int ii = rem / S, idx = rem - ii * S;
+  curandStatePhilox4_32_10_t st;
+  curand_init(seed, (unsigned long long)idx, offset + 4ULL * (unsigned long long)rr, &st);
+  const float4 v = curand_normal4(&st);
+  return ii == 0 ? v.x : ii == 1 ? v.y : ii == 2 ? v.z : v.w;
+}
+// element d of node g (of n_total) of noise draw r
+__device__ __forceinline__ float noise_draw(const NoiseRng& q, int r, int g, int d) {
+  const unsigned long long base = q.offset + (unsigned long long)r * q.per_draw;
+  const long long gg = (long long)g + q.g0;
+  if (d < 3) return philox_normal_elem(q.seed, base, q.Sx, gg * 3 + d);
+  return philox_normal_elem(q.seed, base + q.cx, q.Sh, gg * q.F + (d - 3));
+}
+
 struct FinishArgs {
   const float* h;        // (B*N,128) final hidden state
   const float* x;        // (B*N,3) final coordinates
@@ -762,7 +803,8 @@ struct FinishArgs {
   // sampler mode
   float* z;              // (B*N,3+F) in/out, null when not sampling
   const float* fragment_mask; const float* linker_mask;
-  const float* noise;    // (T+2,B*N,3+F)
+  const float* noise;    // (T+2,B*N,3+F), or null with rng.on
+  NoiseRng rng;
   const float* coef;     // device table, 8 floats per row
   const int* step_fin; int* step_prep;
   int T;
@@ -824,7 +866,8 @@ __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
     lm = a.linker_mask[g]; fm = a.fragment_mask[g];
     const float zt = a.z[(size_t)g * xd + d];
     const float eps = e * lm;                                                 // edm.py:196 / 225
-    const float nz = a.noise[((size_t)(step + 1) * n_total + g) * xd + d] * lm;  // utils.py:189-192
+    const float nz = (a.rng.on ? noise_draw(a.rng, step + 1, g, d)
+                               : a.noise[((size_t)(step + 1) * n_total + g) * xd + d]) * lm;  // utils.py:189-192
     if (step < a.T) {
       float mu = zt / ca - cb * eps;                                          // edm.py:199
       float zs = mu + cc * nz;                                                // edm.py:205, 342-345
@@ -982,12 +1025,23 @@ __global__ void __launch_bounds__(256) k_inpaint(Geom gm, InpaintArgs a) {
 
 // z0 = xh*fragment_mask + (noise[0]*linker_mask)*linker_mask   (edm.py:136-137)
 __global__ void k_init_z(int n_total, int xd, const float* __restrict__ xh, const float* __restrict__ fm,
-                         const float* __restrict__ lm, const float* __restrict__ noise, float* __restrict__ z) {
+                         const float* __restrict__ lm, const float* __restrict__ noise, NoiseRng rng, float* __restrict__ z) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_total * xd) return;
   int g = idx / xd;
   float l = lm[g];
-  z[idx] = xh[idx] * fm[g] + (noise[idx] * l) * l;
+  const float nz = rng.on ? noise_draw(rng, 0, g, idx - g * xd) : noise[idx];
+  z[idx] = xh[idx] * fm[g] + (nz * l) * l;
+}
+
+// Debug / test helper: the (n_draws, n_total, 3+F) tensor the device-side stream stands for.
+__global__ void k_noise_fill(int n_draws, int n_total, int xd, NoiseRng rng, float* __restrict__ out) {
+  const long long total = (long long)n_draws * n_total * xd;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(i % xd);
+    const long long gi = i / xd;
+    out[i] = noise_draw(rng, (int)(gi / n_total), (int)(gi % n_total), d);
+  }
 }
 
 // SizeGNN head (linker_size.py:88-91 + linker_size_lightning.py:110): out[b] = mean over ALL N padded rows of

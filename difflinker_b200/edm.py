@@ -41,7 +41,12 @@ class EDM(torch.nn.Module):
         self.T = timesteps
         self.norm_values = norm_values
         self.norm_biases = norm_biases
-        self.noise_mode = 'reference_stream'   # or 'bulk': one randn call for the whole chain
+        # 'reference_stream' (default): the reference's torch.randn call order, so seeds line up with the reference run on
+        #   the same kind of device. On CUDA the numbers are regenerated INSIDE the kernels that consume them from the torch
+        #   generator's (seed, offset) -- same values as the randn calls, no tensor, no launches (dl_sample_chain_rng).
+        # 'reference_tensor': the same stream materialised with torch.randn (two launches per draw).
+        # 'bulk': one randn call for the whole chain (a different stream).
+        self.noise_mode = 'reference_stream'
         self.last_loop_ms = None               # device time of the last reverse loop (CUDA events)
 
     def forward(self, *args, **kwargs):
@@ -123,9 +128,11 @@ class EDM(torch.nn.Module):
 
     @torch.no_grad()
     def sample_chain(self, x, h, node_mask, fragment_mask, linker_mask, edge_mask, context, keep_frames=None,
-                     noise=None):
+                     noise=None, batch_slice=None):
         """Same contract as the reference (edm.py:126-176): returns (keep_frames, B, N, 3+F); chain[0] holds the
-        final coordinates and one-hot atom types. `noise` optionally injects the (T+2,B,N,3+F) draws (tests)."""
+        final coordinates and one-hot atom types. `noise` optionally injects the (T+2,B,N,3+F) draws (tests).
+        `batch_slice=(b0, B_full)`: the inputs are rows [b0, b0+B) of a batch of B_full molecules (strong scaling,
+        distributed.sample_chain_sharded); the device-side noise is then those rows of the full batch's draws."""
         lib = _native.load_library()
         n_samples, n_nodes = x.size(0), x.size(1)
         dev = x.device
@@ -137,10 +144,16 @@ class EDM(torch.nn.Module):
         d = self.n_dims + self.in_node_nf
         xn, hn = self.normalize(x, h)
         xh = torch.cat([xn, hn], dim=2).to(torch.float32).contiguous()
-        if noise is None:
-            noise = self.draw_noise(T + 2, n_samples, n_nodes, dev)
-        noise = noise.to(device=dev, dtype=torch.float32).contiguous()
-        assert noise.shape == (T + 2, n_samples, n_nodes, d), noise.shape
+        # device-side stream unless a tensor is injected (tests), draw_noise is overridden on the instance, or another mode is set
+        on_device = (noise is None and dev.type == 'cuda' and self.noise_mode == 'reference_stream'
+                     and 'draw_noise' not in self.__dict__)
+        if batch_slice is not None and not on_device:
+            raise ValueError("batch_slice needs the device-side noise stream (CUDA tensors, noise_mode='reference_stream')")
+        if not on_device:
+            if noise is None:
+                noise = self.draw_noise(T + 2, n_samples, n_nodes, dev)
+            noise = noise.to(device=dev, dtype=torch.float32).contiguous()
+            assert noise.shape == (T + 2, n_samples, n_nodes, d), noise.shape
 
         eng = self.dynamics.engine(self.dynamics._device_index(x))
         self.dynamics._check_graph_type()
@@ -162,10 +175,24 @@ class EDM(torch.nn.Module):
         if dev.type == 'cuda':
             with torch.cuda.device(dev):
                 stream = torch.cuda.current_stream(dev).cuda_stream
-                st = lib.dl_sample_chain(eng, _native.SAMPLER_LINKER, n_samples, n_nodes, T, keep_frames, ptr(xh),
-                                         ptr(nm), ptr(fm), ptr(lm), ptr(em), ptr(ctx), ptr(noise), coef, norm,
-                                         ptr(chain), ptr(flags), stream)
-                _native.check(st, "dl_sample_chain")
+                if on_device:
+                    gen = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()]
+                    seed, offset = gen.initial_seed() & 0xFFFFFFFFFFFFFFFF, gen.get_offset()
+                    used = C.c_uint64(0)
+                    if batch_slice is not None:
+                        _native.check(lib.dl_set_noise_slice(eng, int(batch_slice[1]), int(batch_slice[0])), "dl_set_noise_slice")
+                    st = lib.dl_sample_chain_rng(eng, _native.SAMPLER_LINKER, n_samples, n_nodes, T, keep_frames, ptr(xh),
+                                                 ptr(nm), ptr(fm), ptr(lm), ptr(em), ptr(ctx), seed, offset, C.byref(used),
+                                                 coef, norm, ptr(chain), ptr(flags), stream)
+                    if batch_slice is not None:
+                        lib.dl_set_noise_slice(eng, 0, 0)
+                    _native.check(st, "dl_sample_chain_rng")
+                    gen.set_offset(offset + used.value)          # as if the reference's (T+2) x 2 randn calls had run
+                else:
+                    st = lib.dl_sample_chain(eng, _native.SAMPLER_LINKER, n_samples, n_nodes, T, keep_frames, ptr(xh),
+                                             ptr(nm), ptr(fm), ptr(lm), ptr(em), ptr(ctx), ptr(noise), coef, norm,
+                                             ptr(chain), ptr(flags), stream)
+                    _native.check(st, "dl_sample_chain")
                 bad = bool(flags.any().item())   # one sync per chain instead of one per step (egnn.py:441)
         else:
             st = lib.dl_sample_chain_host(eng, _native.SAMPLER_LINKER, n_samples, n_nodes, T, keep_frames, ptr(xh),

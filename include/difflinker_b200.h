@@ -149,6 +149,31 @@ dl_status dl_sample_chain(dl_engine* e, int32_t sampler, int32_t B, int32_t N, i
 
 /* HOST-buffer variant (pinned or pageable): H2D of all inputs incl. noise, loop, D2H of chain and flags,
  * synchronises. Returns DL_NAN_DETECTED if any flag is set. */
+/*
+ * Same loop with the noise drawn ON THE DEVICE in the reference's stream order (edm.py:328-345, utils.py:189-192): per draw
+ * torch.randn(B,N,3) then torch.randn(B,N,F). For a CUDA generator in state (seed, offset) those calls are Philox4x32-10
+ * streams with a fixed thread -> element mapping (ATen DistributionTemplates.h); the kernels that consume the noise
+ * regenerate exactly those numbers, so the result equals what `dl_sample_chain` returns for the tensor torch would have
+ * drawn -- without the tensor ((T+2) B N (3+F) floats: 226 MB for B=256, N=40, T=500), its 2(T+2) launches and its
+ * interleaving copy. A plain C caller can sample with nothing but a seed.
+ *   seed, offset      the generator state on entry (torch.Generator.initial_seed() / get_offset(); offset % 4 == 0)
+ *   offset_consumed   HOST out (may be NULL): what the (T+2) draws consumed -- advance the generator by it
+ * DL_SAMPLER_LINKER only (the inpainting sampler needs centre-of-mass projected draws: pass prepared slabs).
+ */
+dl_status dl_sample_chain_rng(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
+                              const float* xh, const int8_t* node_mask, const float* fragment_mask,
+                              const float* linker_mask, const int8_t* edge_mask, const float* context, uint64_t seed,
+                              uint64_t offset, uint64_t* offset_consumed, const dl_step_coef* coef, const float* norm,
+                              float* chain, int32_t* nan_flags, void* stream);
+/* Strong scaling: this engine samples molecules [b0, b0 + B) of a batch of B_full. The device-side noise of
+ * the following dl_sample_chain_rng / dl_noise_fill calls is then the slice's ROWS of the full-batch draws (and
+ * offset_consumed is the full batch's), so the gathered result is bit-identical to the single-GPU run whatever the split.
+ * B_full = 0 switches it off. */
+dl_status dl_set_noise_slice(dl_engine* e, int32_t B_full, int32_t b0);
+/* The (n_draws,B,N,3+F) tensor the device-side stream of dl_sample_chain_rng stands for (tests, debugging). DEVICE out. */
+dl_status dl_noise_fill(dl_engine* e, int32_t n_draws, int32_t B, int32_t N, uint64_t seed, uint64_t offset, float* out,
+                        uint64_t* offset_consumed, void* stream);
+
 dl_status dl_sample_chain_host(dl_engine* e, int32_t sampler, int32_t B, int32_t N, int32_t T, int32_t keep_frames,
                                const float* xh, const int8_t* node_mask, const float* fragment_mask,
                                const float* linker_mask, const int8_t* edge_mask, const float* context,

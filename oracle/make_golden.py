@@ -127,7 +127,7 @@ def golden_dynamics(ns, name, spec, nb, seed, pocket=False, t_scalar=False):
          edge_mask=batch['edge_mask'], context=ctx, out=out)
 
 
-def golden_chain(ns, name, spec, nb, seed, keep_frames, n_steps=None):
+def golden_chain(ns, name, spec, nb, seed, keep_frames, n_steps=None, moad_val_dataset=False):
     hp = synthetic.model_hparams(spec)
     torch.manual_seed(seed)
     ddpm = ns.lightning.DDPM(**hp, data_path=None, batch_size=nb, lr=1e-4, torch_device='cpu', test_epochs=1,
@@ -137,6 +137,8 @@ def golden_chain(ns, name, spec, nb, seed, keep_frames, n_steps=None):
     if n_steps is not None:
         ddpm.edm.T = n_steps                                       # generate.py:103-104
     T = ddpm.edm.T
+    if moad_val_dataset:                                           # generate_with_pocket.py:249-250
+        ddpm.val_dataset = ns.datasets.MOADDataset(data=synthetic.make_items(spec, batch=nb))
     data = ns.datasets.collate(synthetic.make_items(spec, batch=nb))
     noise_seed = seed + 1000
     draw = seeded_noise(noise_seed)
@@ -190,7 +192,7 @@ def golden_chain(ns, name, spec, nb, seed, keep_frames, n_steps=None):
     assert np.array_equal(coef[T], np.array([rows[T].t, rows[T].a, rows[T].b, rows[T].c], dtype=np.float32))
     meta = dict(kind="chain", spec=spec.name, batch=nb, seed=seed, noise_seed=noise_seed, keep_frames=keep_frames,
                 T=T, table_timesteps=hp['diffusion_steps'], sha=state_sha(ddpm.edm.dynamics.state_dict()),
-                oracle_max_abs_err=err)
+                oracle_max_abs_err=err, moad_val_dataset=bool(moad_val_dataset))
     save(name, meta, chain=chain, node_mask=node_mask, coef=coef)
 
 

@@ -87,6 +87,97 @@ def test_sample_chain_matches_reference_golden(name, impl):
     assert torch.equal(chain[0][..., :3] * fm, x * fm)
 
 
+class MOADDataset(list):
+    """Stand-in with the reference class's NAME: lightning.py:441 switches the centre-of-mass mask on
+    `isinstance(self.val_dataset, MOADDataset)`, which generate_with_pocket.py:249-250 sets before sampling."""
+
+
+PUBLIC_CHAINS = ["chain_cfg1", "chain_small_pocket_FC-10A-4A", "chain_small_pocket_FC-4A", "chain_small_pocket_4A",
+                 "chain_cfg2_zinc_T500", "chain_cfg2_zinc_L8_T500", "chain_cfg3_geom_T500"]
+
+
+@pytest.mark.parametrize("name", PUBLIC_CHAINS)
+def test_public_ddpm_sample_chain_matches_reference_golden(name):
+    """The call generate.py:156 / generate_with_pocket.py:265 make -- `DDPM.sample_chain(data, keep_frames)` -- against chains
+    the live reference produced through the SAME entry point (oracle/make_golden*.py), with the reference's noise draws
+    injected through `EDM.draw_noise`. Covers the benchmarked shapes (configs 2 and 3 non-ragged, T=500, L=6 and the real
+    ZINC depth L=8; 8-molecule slices) and pocket-conditioned sampling (MOAD prefix, val_dataset set, all three cut-off
+    graph types: the graph is rebuilt from the current coordinates at every one of the T+1 calls)."""
+    meta, a = helpers.load_golden(name)
+    spec = helpers.spec_by_name(meta["spec"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"], diffusion_steps=meta["table_timesteps"])
+    assert helpers.state_sha(ddpm.edm.dynamics.state_dict()) == meta["sha"]
+    ddpm.edm.T = meta["T"]
+    items = synthetic.make_items(spec, batch=meta["batch"])
+    if meta.get("moad_val_dataset"):
+        ddpm.val_dataset = MOADDataset(items)
+    d = dev()
+    ddpm = ddpm.to(d)
+    data = collate(items)
+    sizes = data['linker_mask'].sum(1).view(-1).int()
+    tpl = create_templates_for_linker_generation(data, sizes)
+    B, N = tpl['positions'].shape[:2]
+    noise = helpers.noise_tensor(meta["noise_seed"], meta["T"], B, N, spec.F)
+    calls = []
+
+    def injected(n_draws, n_samples, n_nodes, device, generator=None):
+        calls.append((n_draws, n_samples, n_nodes))
+        assert (n_draws, n_samples, n_nodes) == (meta["T"] + 2, B, N)
+        return noise.to(device)
+    ddpm.edm.draw_noise = injected
+    data_dev = {k: (v.to(d) if torch.is_tensor(v) else v) for k, v in data.items()}
+    chain, node_mask = ddpm.sample_chain(data_dev, keep_frames=meta["keep_frames"])
+    assert len(calls) == 1
+    chain, node_mask = chain.cpu(), node_mask.cpu()
+    want = a["chain"]
+    assert chain.shape == want.shape and torch.equal(node_mask, a["node_mask"])
+    assert torch.equal(chain[0][..., 3:], want[0][..., 3:]), "atom types differ"
+    lm = tpl['linker_mask']
+    assert rel_err(chain[0][..., :3] * lm, want[0][..., :3] * lm) <= REL_TOL
+    assert rel_err(chain[0][..., :3], want[0][..., :3]) <= REL_TOL
+    for f in range(1, meta["keep_frames"]):
+        assert rel_err(chain[f], want[f]) <= REL_TOL, f
+
+
+@pytest.mark.parametrize("N,nb", [(32, 4), (64, 3), (256, 2)])
+def test_forward_padded_n_sweep_l6_vs_oracle(N, nb):
+    """BASELINE configs[4] (padded-N sweep) at its real depth L=6: N=32 and N=64 run the third-generation edge kernels
+    (TMA-staged panels), N=256 the column-chunked second-generation ones."""
+    spec = synthetic.SPECS[f"cfg5_sweep_N{N}"]
+    dyn, hp = helpers.build_dynamics(spec, 0)
+    assert hp['n_layers'] == 6
+    batch = collate(synthetic.make_items(spec, batch=nb))
+    z, t = helpers.random_latent(batch, 7)
+    ctx = helpers.context_of(batch, spec)
+    with torch.no_grad():
+        want = orc.dynamics_forward(dyn.state_dict(), helpers.oracle_cfg(hp), t, z, batch['atom_mask'],
+                                    batch['linker_mask'], batch['edge_mask'], ctx)
+    got = run_dyn(dyn, t, z, batch['atom_mask'], batch['linker_mask'], batch['edge_mask'], ctx, dev())
+    assert rel_err(got[..., :3], want[..., :3]) <= REL_TOL
+    assert rel_err(got[..., 3:], want[..., 3:]) <= REL_TOL
+
+
+@pytest.mark.parametrize("spec_name,nb", [("cfg2_zinc_ragged", 16), ("cfg3_geom_ragged", 8), ("small_pocket_FC-10A-4A", 2)])
+def test_device_side_collate_and_templates_match_oracle(spec_name, nb):
+    """datasets.collate / create_templates_for_linker_generation (datasets.py:332-375, 483-512) run as torch ops on the
+    batch's device: every tensor of the result equals the oracle's per-molecule formulation bit for bit, with the
+    reference's dtypes (int8 masks incl. the -1/-2 edge mask, or the batch-id vector for pockets)."""
+    spec = helpers.spec_by_name(spec_name)
+    items = synthetic.make_items(spec, batch=nb)
+    want_c = orc.collate_molecules(items)
+    g = torch.Generator().manual_seed(3)
+    sizes = torch.randint(1, 12, (nb,), generator=g).int()
+    want_t = orc.linker_templates(want_c, sizes)
+    d = dev()
+    items_dev = [{k: (v.to(d) if torch.is_tensor(v) else v) for k, v in it.items()} for it in items]
+    got_c = collate(items_dev)
+    got_t = create_templates_for_linker_generation(got_c, sizes.to(d))
+    for want, got in ((want_c, got_c), (want_t, got_t)):
+        for k, v in want.items():
+            if torch.is_tensor(v):
+                assert got[k].is_cuda and got[k].dtype == v.dtype and torch.equal(got[k].cpu(), v), k
+
+
 @pytest.mark.parametrize("impl", IMPLS)
 def test_inpainting_sample_chain_matches_reference_golden(impl):
     """InpaintingEDM (edm.py:549-727) through DDPM(inpainting=True): centring dynamics, all atoms move, fragments are
@@ -532,3 +623,74 @@ def test_draw_noise_on_cuda_equals_the_reference_call_sequence():
     for r in range(5):
         assert torch.equal(got[r, :, :, :3], torch.randn((4, 30, 3), device=d, generator=g2))
         assert torch.equal(got[r, :, :, 3:], torch.randn((4, 30, spec.F), device=d, generator=g2))
+
+
+def test_device_side_noise_stream_equals_torch_cuda_randn_sequence():
+    """dl_noise_fill / dl_sample_chain_rng regenerate, from (seed, offset) alone, the numbers torch's CUDA generator hands to
+    the reference's call sequence randn(B,N,3), randn(B,N,F), ... (utils.py:189-192): bit-identical, for shapes below and
+    above one grid of 256-thread blocks per call, and from a non-zero starting offset."""
+    import ctypes as C
+    from difflinker_b200 import _native
+    lib = _native.load_library()
+    d = dev()
+    for spec_name, B, N, n_draws, warm in (("cfg1_plumbing", 4, 30, 5, 0), ("cfg2_zinc", 256, 40, 3, 3), ("cfg3_geom", 512, 300, 2, 1)):
+        spec = synthetic.SPECS[spec_name]
+        dyn, hp = helpers.build_dynamics(spec, 0)
+        eng = dyn.engine(d.index or 0)
+        torch.manual_seed(1234 + B)
+        for _ in range(warm):
+            torch.randn((7, 13), device=d)                       # the stream does not start at offset 0
+        gen = torch.cuda.default_generators[d.index or 0]
+        seed, offset = gen.initial_seed(), gen.get_offset()
+        out = torch.empty((n_draws, B, N, 3 + spec.F), device=d)
+        used = C.c_uint64(0)
+        with torch.cuda.device(d):
+            _native.check(lib.dl_noise_fill(eng, n_draws, B, N, seed, offset, out.data_ptr(), C.byref(used),
+                                            torch.cuda.current_stream(d).cuda_stream), "dl_noise_fill")
+        for r in range(n_draws):
+            assert torch.equal(out[r, :, :, :3], torch.randn((B, N, 3), device=d)), (spec_name, r)
+            assert torch.equal(out[r, :, :, 3:], torch.randn((B, N, spec.F), device=d)), (spec_name, r)
+        assert gen.get_offset() == offset + used.value
+
+
+def test_sampler_with_device_side_noise_equals_sampler_fed_the_torch_tensor():
+    """EDM.sample_chain on CUDA draws inside its kernels (no noise tensor); the chain equals, bit for bit, the one the same
+    engine produces from the tensor torch.randn would have drawn for the same seed, and the generator ends at the same offset."""
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    ddpm, hp = helpers.build_ddpm(spec, 0)
+    d = dev()
+    ddpm = ddpm.to(d)
+    data = {k: (v.to(d) if torch.is_tensor(v) else v) for k, v in collate(synthetic.make_items(spec)).items()}
+    torch.manual_seed(99)
+    chain_dev, _ = ddpm.sample_chain(data, keep_frames=3)
+    end_dev = torch.cuda.default_generators[d.index or 0].get_offset()
+    torch.manual_seed(99)
+    ddpm.edm.noise_mode = 'reference_tensor'
+    chain_ten, _ = ddpm.sample_chain(data, keep_frames=3)
+    assert torch.cuda.default_generators[d.index or 0].get_offset() == end_dev
+    assert torch.equal(chain_dev, chain_ten)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_batch_slices_reproduce_the_single_gpu_chain(world):
+    """Strong scaling, emulated on one GPU: the ranks' slices of a batch, each sampled with
+    `batch_slice=(lo, B)` from the same generator state, concatenate to exactly the chain of the unsplit batch (the
+    slice consumes the slice's rows of the full-batch noise; molecules never interact)."""
+    from difflinker_b200.ddpm import sampler_inputs
+    from difflinker_b200.distributed import shard_range, slice_sampler_inputs
+    spec = synthetic.SPECS["cfg2_zinc_ragged"]
+    ddpm, hp = helpers.build_ddpm(spec, 0)
+    ddpm.edm.T = 12
+    d = dev()
+    ddpm = ddpm.to(d)
+    data = {k: (v.to(d) if torch.is_tensor(v) else v) for k, v in collate(synthetic.make_items(spec, batch=7)).items()}
+    torch.manual_seed(5)
+    full, _ = ddpm.sample_chain(data, keep_frames=2)
+    kw = sampler_inputs(ddpm, data)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_range(7, r, world)
+        torch.manual_seed(5)
+        parts.append(ddpm.edm.sample_chain(**slice_sampler_inputs(kw, lo, hi), keep_frames=2, batch_slice=(lo, 7)))
+    assert torch.equal(torch.cat(parts, dim=1), full)
+

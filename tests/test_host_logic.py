@@ -161,6 +161,48 @@ print("rank", rank, "ok")
     assert res.stdout.count("ok") == 2
 
 
+def test_sharded_sampling_gathers_the_full_batch_world_size_2_gloo(tmp_path):
+    """distributed.sample_chain_sharded under gloo, world size 2 (uneven split 3 + 2): every rank builds the same template
+    batch, samples its slice (stand-in EDM: a deterministic function of the slice, no GPU here) and the all_gather
+    reassembles the batch order."""
+    script = tmp_path / "sharded.py"
+    script.write_text(f"""
+import os, sys, types, torch, torch.distributed as dist
+sys.path.insert(0, {str(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))!r})
+from difflinker_b200 import synthetic
+from difflinker_b200.batching import collate
+from difflinker_b200.distributed import sample_chain_sharded, shard_range
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[1], rank=int(sys.argv[2]), world_size=2)
+spec = synthetic.SPECS["cfg1_plumbing"]
+data = collate(synthetic.make_items(spec, batch=5))
+seen = dict()
+class FakeEDM:
+    def sample_chain(self, x, h, node_mask, fragment_mask, linker_mask, edge_mask, context, keep_frames=None, batch_slice=None):
+        seen["slice"] = batch_slice; seen["B"] = x.shape[0]
+        assert edge_mask.shape[0] == x.shape[0] * x.shape[1] * x.shape[1]
+        return torch.stack([torch.cat([x, h], dim=2) * (f + 1) for f in range(keep_frames)])
+model = types.SimpleNamespace(inpainting=False, anchors_context=False, train_data_prefix="zinc_train", center_of_mass="fragments",
+                              val_dataset=None, edm=FakeEDM())
+chain, node_mask = sample_chain_sharded(model, data, keep_frames=2)
+lo, hi = shard_range(5, dist.get_rank(), 2)
+assert seen["slice"] == (lo, 5) and seen["B"] == hi - lo, seen
+dist.destroy_process_group()
+single = types.SimpleNamespace(**{{**model.__dict__}})
+full, nm = sample_chain_sharded(single, data, keep_frames=2)           # world size 1 path
+assert torch.equal(chain, full) and torch.equal(node_mask, nm) and chain.shape[1] == 5
+print("ok")
+""")
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    procs = [subprocess.Popen([sys.executable, str(script), str(port), str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                              text=True) for r in range(2)]
+    for pr in procs:
+        out, err = pr.communicate(timeout=240)
+        assert pr.returncode == 0 and "ok" in out, out + err
+
+
 def test_accelerate_swaps_reference_edm():
     """Whole-loop drop-in: a *reference* DDPM (live reference, build container only) gets the native EDM with
     the same weights; strict state_dict load proves the key layout."""

@@ -27,20 +27,24 @@ def test_oracle_dynamics_matches_reference_golden(name):
     assert torch.equal(out * (1 - a["node_mask"].float()), torch.zeros_like(out))  # utils.py:99-101
 
 
-@pytest.mark.parametrize("name", ["chain_cfg1", "chain_cfg1_nsteps20"])
+@pytest.mark.parametrize("name", ["chain_cfg1", "chain_cfg1_nsteps20", "chain_small_pocket_FC-10A-4A",
+                                  "chain_small_pocket_FC-4A", "chain_small_pocket_4A"])
 def test_oracle_chain_matches_reference_golden(name):
+    """(The T=500 chains at the benchmarked shapes -- chain_cfg2_zinc_T500 etc. -- were pinned against the oracle when they
+    were generated, oracle/make_golden_r2.py; replaying them takes minutes of CPU, so here they only serve the GPU tests.)"""
     meta, a = helpers.load_golden(name)
     spec = helpers.spec_by_name(meta["spec"])
-    ddpm, hp = helpers.build_ddpm(spec, meta["seed"])
+    ddpm, hp = helpers.build_ddpm(spec, meta["seed"], diffusion_steps=meta["table_timesteps"])
     assert helpers.state_sha(ddpm.edm.dynamics.state_dict()) == meta["sha"]
     data = orc.collate_molecules(synthetic.make_items(spec, batch=meta["batch"]))
     tpl = orc.linker_templates(data, data['linker_mask'].sum(1).view(-1).int())
-    x = orc.remove_partial_mean(tpl['positions'], tpl['atom_mask'], tpl['fragment_mask'])
+    com = tpl['fragment_only_mask'] if spec.pocket else tpl['fragment_mask']   # lightning.py:441-444 (MOAD val_dataset)
+    x = orc.remove_partial_mean(tpl['positions'], tpl['atom_mask'], com)
     gam = orc.gamma_table(hp['diffusion_noise_schedule'], hp['diffusion_steps'], hp['diffusion_noise_precision'])
     with torch.no_grad():
         chain = orc.edm_sample_chain(ddpm.edm.dynamics.state_dict(), helpers.oracle_cfg(hp), gam, meta["T"], x,
                                      tpl['one_hot'], tpl['atom_mask'], tpl['fragment_mask'], tpl['linker_mask'],
-                                     tpl['edge_mask'], tpl['fragment_mask'], keep_frames=meta["keep_frames"],
+                                     tpl['edge_mask'], helpers.context_of(tpl, spec), keep_frames=meta["keep_frames"],
                                      norm_values=tuple(hp['normalize_factors']),
                                      noise_fn=helpers.seeded_noise(meta["noise_seed"]))
     assert chain.shape == a["chain"].shape                              # (keep_frames,B,N,3+F)
