@@ -25,19 +25,20 @@ namespace tcn {
 using namespace dl::tc;
 
 constexpr int TM = 128;                        // nodes per tile = UMMA N
-constexpr int X_LBO = TM * 16 + 16;            // 2064 B: padded slab pitch of the node operand tiles
-constexpr int X_BYTES = KC * X_LBO;            // 33,024 B per fp16 copy
+constexpr int X_LBO_MAX = TM * 16 + 16;        // 2064 B: padded slab pitch of a 128-node operand tile (run time: n_pad * 16 + 16)
+constexpr int X_BYTES_MAX = KC * X_LBO_MAX;    // 33,024 B per fp16 copy
 constexpr int HALF_BYTES = 8 * W_LBO;          // 16 KB: kc 0..7 of one fp16 copy of a 128x128 block
 constexpr int STAGE_BYTES = 2 * HALF_BYTES;    // hi | lo
 constexpr int BLOCK_BYTES = 2 * W_BYTES;       // one packed 128x128 block: [hi 32 KB | lo 32 KB]
-constexpr int N_RING = 2;
-
-constexpr int N_OFF_XA = 0;                    // hi | lo
-constexpr int N_OFF_XB = N_OFF_XA + 2 * X_BYTES;
-constexpr int N_OFF_WS = N_OFF_XB + 2 * X_BYTES;
-constexpr int N_OFF_MISC = N_OFF_WS + N_RING * STAGE_BYTES;   // nm[128] f32, nodemax[2][128] i32, tilemax i32
-constexpr int N_OFF_BAR = N_OFF_MISC + 128 * 4 * 3 + 16;      // full[2], empty[2], acc[4]; tmem slot
+constexpr int N_RING = 4;                      // ring slots that have barriers; how many are USED depends on the tile width:
+                                               // the operand tiles are sized for the run-time tile (72 nodes on cfg 2: 83 KB
+                                               // instead of 132 KB), and the space goes to the weight ring (4 x 32 KB in flight
+                                               // instead of 2: the next GEMM's weights land while the current epilogue runs)
+constexpr int N_OFF_XA = 0;                    // hi | lo, then XB hi | lo, then the weight ring (run-time offsets)
+constexpr int N_OFF_MISC = 226304;             // nm[128] f32, nodemax[2][128] i32, tilemax i32
+constexpr int N_OFF_BAR = N_OFF_MISC + 128 * 4 * 3 + 16;      // full[4], empty[4], acc[4]; tmem slot
 constexpr int N_SMEM_BYTES = N_OFF_BAR + 128 + 1024;
+static_assert(N_SMEM_BYTES <= 232448 && 4 * X_BYTES_MAX + 2 * STAGE_BYTES <= N_OFF_MISC, "k_node_tc shared memory");
 constexpr int NW = 16;                         // worker warps: warp w serves TMEM lane quarter w % 4 and node columns
 constexpr int NPART = NW / 4;                  //   [part*CW, (part+1)*CW) with part = w / 4 -- 4 warps per scheduler
 constexpr int CW = TM / NPART;                 //   hide each other's TMEM / shared / global latencies
@@ -73,10 +74,10 @@ __device__ __forceinline__ float pow2_scale_for(float bound) {
 __device__ __forceinline__ void workers_sync() { asm volatile("bar.sync 1, %0;" ::"n"(32 * NW) : "memory"); }
 
 // one value of channel c, node n -> fp16 hi/lo operand tile
-__device__ __forceinline__ void store_elem(uint8_t* xhi, uint8_t* xlo, int c, int n, float v) {
+__device__ __forceinline__ void store_elem(uint8_t* xhi, uint8_t* xlo, int x_lbo, int c, int n, float v) {
   const __half hi = __float2half_rn(v);
   const __half lo = __float2half_rn(v - __half2float(hi));
-  const int off = (c >> 3) * X_LBO + n * 16 + (c & 7) * 2;
+  const int off = (c >> 3) * x_lbo + n * 16 + (c & 7) * 2;
   *reinterpret_cast<__half*>(xhi + off) = hi;
   *reinterpret_cast<__half*>(xlo + off) = lo;
 }
@@ -94,10 +95,14 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   const int n_live = min(tile, n_total - g0);
   const int n_pad = (tile + 15) & ~15;                     // UMMA N: operand rows [0, n_pad) are read by the tensor core
 
+  const int X_LBO = n_pad * 16 + 16;                       // operand slab pitch of THIS tile width (+16 B: conflict-free stores)
+  const int X_BYTES = KC * X_LBO;
+  const int off_ws = 4 * X_BYTES;                          // weight ring starts after XA hi|lo, XB hi|lo
+  const int n_ring = min(N_RING, (N_OFF_MISC - off_ws) / STAGE_BYTES);
   const uint32_t bar_full = sbase + N_OFF_BAR, bar_empty = bar_full + 8 * N_RING, bar_acc = bar_empty + 8 * N_RING;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + N_OFF_BAR + 8 * (2 * N_RING + 4));
   uint8_t* xa_hi = sm + N_OFF_XA; uint8_t* xa_lo = xa_hi + X_BYTES;
-  uint8_t* xb_hi = sm + N_OFF_XB; uint8_t* xb_lo = xb_hi + X_BYTES;
+  uint8_t* xb_hi = sm + 2 * X_BYTES; uint8_t* xb_lo = xb_hi + X_BYTES;
   float* nms = reinterpret_cast<float*>(sm + N_OFF_MISC);
   int* tilemax = reinterpret_cast<int*>(sm + N_OFF_MISC + 512 * 3);
 
@@ -123,13 +128,13 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   if (warp == NW) {
     if (lane == 0) {
       for (int i = 0; i < n_half; ++i) {
-        const int s = i % N_RING, blk = (i >> 1) + blk0, hf = i & 1;
-        if (i >= N_RING) mbar_wait(bar_empty + 8 * s, ((i - N_RING) / N_RING) & 1);
+        const int s = i % n_ring, blk = (i >> 1) + blk0, hf = i & 1;
+        if (i >= n_ring) mbar_wait(bar_empty + 8 * s, ((i - n_ring) / n_ring) & 1);
         const __half* base = blk < 2 ? a.w3 + (size_t)blk * (BLOCK_BYTES / 2)
                              : blk == 2 ? a.w4
                                         : a.pw[(blk - 3) >> 1] + (size_t)((blk - 3) & 1) * (BLOCK_BYTES / 2);
         const uint8_t* src = reinterpret_cast<const uint8_t*>(base);
-        const uint32_t dst = sbase + N_OFF_WS + s * STAGE_BYTES;
+        const uint32_t dst = sbase + off_ws + s * STAGE_BYTES;
         mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
         bulk_g2s(dst, src + hf * HALF_BYTES, HALF_BYTES, bar_full + 8 * s);                      // hi, kc 8hf..8hf+7
         bulk_g2s(dst + HALF_BYTES, src + W_BYTES + hf * HALF_BYTES, HALF_BYTES, bar_full + 8 * s);  // lo
@@ -202,11 +207,11 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     // xhi_of[j]: node-operand hi base for half-block j of this GEMM (lo = hi + X_BYTES); kc offset = 8*(j&1)
     tc_fence_after();
     for (int j = 0; j < nh; ++j) {
-      const int i = i0 + j, s = i % N_RING;
-      mbar_wait(bar_full + 8 * s, (i / N_RING) & 1);
+      const int i = i0 + j, s = i % n_ring;
+      mbar_wait(bar_full + 8 * s, (i / n_ring) & 1);
       tc_fence_after();
       const uint32_t xh = smem_u32(xhi_of[j]) + (8 * (j & 1)) * X_LBO, xl = xh + X_BYTES;
-      const uint32_t wh = sbase + N_OFF_WS + s * STAGE_BYTES, wl = wh + HALF_BYTES;
+      const uint32_t wh = sbase + off_ws + s * STAGE_BYTES, wl = wh + HALF_BYTES;
 #pragma unroll
       for (int ks = 0; ks < 4; ++ks) {
         const uint64_t a_hi = umma_desc(wh + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(wl + ks * 2 * W_LBO, W_LBO, SBO);
@@ -247,7 +252,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
             for (int u = 0; u < 8; ++u) {
               const float v = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
               mx = fmaxf(mx, fabsf(v));                  // |silu(v)| <= |v|
-              store_elem(xb_hi, xb_lo, c, ncol0 + k * 8 + u, silu_f(v) * scale);
+              store_elem(xb_hi, xb_lo, X_LBO, c, ncol0 + k * 8 + u, silu_f(v) * scale);
             }
           }
         }
@@ -299,13 +304,13 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
             const float o = (hv[k & 1][u] + fmaf(__uint_as_float(r[k & 1][u]), ds, bias)) * nms[n];     // egnn.py:71,78-79
             if (n < n_live) hcol[(size_t)n * H] = o;
             mx = fmaxf(mx, fabsf(o));
-            store_elem(xa_hi, xa_lo, c, n, o);
+            store_elem(xa_hi, xa_lo, X_LBO, c, n, o);
           }
         }
       }
       s3 = pow2_scale_for(tile_max(mx));
       if (s3 != 1.0f) {                                  // rare: rewrite h' scaled (own global writes, program order)
-        for (int n = ncol0; n < ncol0 + 8 * ng; ++n) store_elem(xa_hi, xa_lo, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
+        for (int n = ncol0; n < ncol0 + 8 * ng; ++n) store_elem(xa_hi, xa_lo, X_LBO, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
       }
     }
     fence_proxy_async();
@@ -399,8 +404,10 @@ inline int pick_tile_nodes(int n, int num_sms) {
 }
 
 // Debug: one timed launch; prints the phase boundaries (cycles from kernel entry, thread 0, averaged over CTAs).
-inline void profile_node(int n, const NodeTcArgs& ta, cudaStream_t st) {
-  const int grid = (n + TM - 1) / TM;
+inline void profile_node(int n, const NodeTcArgs& ta_in, cudaStream_t st, int num_sms = 148) {
+  NodeTcArgs ta = ta_in;
+  ta.tile_nodes = pick_tile_nodes(n, num_sms);             // the configuration the forward actually launches
+  const int grid = (n + ta.tile_nodes - 1) / ta.tile_nodes;
   long long* d = nullptr;
   if (cudaMalloc(&d, (size_t)grid * 8 * 8) != cudaSuccess) return;
   cudaMemsetAsync(d, 0, (size_t)grid * 64, st);
@@ -411,8 +418,8 @@ inline void profile_node(int n, const NodeTcArgs& ta, cudaStream_t st) {
   cudaFree(d);
   double avg[8] = {0};
   for (int b = 0; b < grid; ++b) for (int i = 0; i < 8; ++i) avg[i] += (double)h[(size_t)b * 8 + i] / grid;
-  fprintf(stderr, "[dl prof node] grid %d, n_proj %d: rows %.0f | G1 ready %.0f | epi1 %.0f | G2 ready %.0f | epi2 %.0f | proj done %.0f\n",
-          grid, ta.n_proj, avg[0], avg[1], avg[2], avg[3], avg[4], avg[6]);
+  fprintf(stderr, "[dl prof node] tile %d, grid %d, n_proj %d: rows %.0f | G1 ready %.0f | epi1 %.0f | G2 ready %.0f | epi2 %.0f | proj done %.0f\n",
+          ta.tile_nodes, grid, ta.n_proj, avg[0], avg[1], avg[2], avg[3], avg[4], avg[6]);
 }
 
 inline dl_status configure_node() {
