@@ -349,8 +349,9 @@ def test_header_is_plain_c_and_a_c_program_links_against_the_library(tmp_path):
 
 
 def test_bench_reference_arm_contract_on_cpu():
-    """`bench.py --impl reference` (the reference's CPU path = the oracle port) prints ONE JSON line with the contract's keys;
-    it needs no GPU, so the arm itself is checked here on the plumbing config."""
+    """`bench.py --impl reference` (the reference's CPU path: its own staged `src.egnn.Dynamics.forward` when oracle/_ref/ exists
+    -- oracle/build_ref.py -- else the oracle port) prints ONE JSON line with the contract's keys; it needs no GPU, so the
+    arm itself is checked here on the plumbing config."""
     import json
     res = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "cfg1_plumbing",
                           "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=600)
@@ -362,7 +363,10 @@ def test_bench_reference_arm_contract_on_cpu():
               "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["unit"] == "molecules/s" and d["value"] > 0 and d["higher_is_better"] is True
-    assert d["config"]["workload"] == "cfg1_plumbing" and d["cpu_baseline"]["kind"] == "port"
+    staged = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "src", "egnn.py"))
+    assert d["config"]["workload"] == "cfg1_plumbing" and d["cpu_baseline"]["kind"] == ("reference" if staged else "port")
+    if staged:
+        assert d["cpu_baseline"]["port_value"] > 0
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
