@@ -104,6 +104,52 @@ struct dl_engine {
 
 namespace {
 
+// DL_TIME_KERNELS=1: CUDA-event time of every launch of a (non-captured) forward, accumulated per kernel label and printed
+// when the engine is destroyed -- the live (warm-cache, back-to-back) counterpart of the ncu launch list.
+struct KernelTimes {
+  bool on = false;
+  struct Rec { const char* label; cudaEvent_t a, b; };
+  std::vector<Rec> pending;
+  std::map<std::string, std::pair<double, long>> acc;
+  void begin(cudaStream_t st, const char* label) {
+    if (!on) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return;
+    Rec r{label, nullptr, nullptr};
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, st);
+    pending.push_back(r);
+  }
+  void end(cudaStream_t st) {
+    if (!on || pending.empty() || pending.back().b == nullptr) return;
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    if (cap != cudaStreamCaptureStatusNone) return;
+    cudaEventRecord(pending.back().b, st);
+  }
+  void collect(cudaStream_t st) {
+    if (!on || pending.empty()) return;
+    cudaStreamSynchronize(st);
+    for (auto& r : pending) {
+      float ms = 0.f;
+      if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { auto& a = acc[r.label]; a.first += ms; a.second += 1; }
+      cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+    }
+    pending.clear();
+  }
+  void report() {
+    if (!on || acc.empty()) return;
+    double tot = 0;
+    for (auto& kv : acc) tot += kv.second.first;
+    for (auto& kv : acc)
+      fprintf(stderr, "[dl times] %-22s %6ld launches  avg %8.2f us  share %5.1f%%\n", kv.first.c_str(), kv.second.second,
+              1e3 * kv.second.first / kv.second.second, 100.0 * kv.second.first / tot);
+  }
+};
+KernelTimes g_times;
+#define TIMED(label, stream, stmt) do { g_times.begin(stream, label); stmt; g_times.end(stream); } while (0)
+
 struct ExpectedParam {
   std::string name;
   int64_t numel;
@@ -324,7 +370,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   pa.coef = io.sampler ? e->coef_dev : nullptr;
   pa.step_prep = io.sampler ? e->step_ctr : nullptr;
   pa.step_fin = io.sampler ? e->step_ctr + 1 : nullptr;
-  k_prep<<<node_blocks, 256, 0, st>>>(gm, pa);
+  TIMED("k_prep", st, (k_prep<<<node_blocks, 256, 0, st>>>(gm, pa)));
   LAUNCH_CHECK();
   e->launches += 1;
   if (e->use_tc) {
@@ -337,7 +383,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(w0.W1_tc); ta.pb1[0] = w0.b1_u;
     ta.p_descale[0] = w0.w1_descale; ta.AB[0] = ws.ABg; ta.ABmax[0] = ws.ABgmax;
     ta.tile_nodes = tcn::pick_tile_nodes(n, e->num_sms);
-    tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
+    TIMED("k_node_tc(proj only)", st, (tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr)));
     LAUNCH_CHECK();
     e->launches += 1;
   }
@@ -365,7 +411,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       // table: x == x0 there) + the x -> x_next copy that precedes the block's coordinate update
       tc3::TileDSet s0{ws.n_items, ws.tij[0], ws.td[0], ws.tdmax[0], ws.td0[0], ws.td0max[0], nullptr, nullptr};
       tc3::TileDSet s1{ws.n_xitems, ws.tij[1], ws.td[1], ws.tdmax[1], ws.td0[1], ws.td0max[1], ws.ts[1], ws.tcd};
-      tc3::k_tiles_d<<<dim3(B * N, 2), tc::TN, 0, st>>>(s0, s1, xin4, l == 0 ? 1 : 0, gm.norm_constant, n * 3, xin, xout, xin4, xout4);
+      TIMED("k_tiles_d", st, (tc3::k_tiles_d<<<dim3(e->num_sms * 8, 2), tc::TN, 0, st>>>(s0, s1, xin4, l == 0 ? 1 : 0, gm.norm_constant, n * 3, xin, xout, xin4, xout4)));
       LAUNCH_CHECK();
       e->launches += 1;
     }
@@ -377,7 +423,9 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
       ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = e->use_tc ? w.wd_u : w.wd; ea.w0 = e->use_tc ? w.w0_u : w.w0; ea.w5 = nullptr;
       ea.plan = plan; ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
+      g_times.begin(st, "edge GCL");
       dl_status st2 = launch_edge(e, gm, ea, false, w.W2_tc, st, w.W2_v3);
+      g_times.end(st);
       if (st2 != DL_OK) return st2;
 
       const bool last_sub = s + 1 >= S;
@@ -406,7 +454,8 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
         if (node_prof_left > 0 && cap == cudaStreamCaptureStatusNone) { --node_prof_left; tcn::profile_node(n, ta, st); }
         else {
           ta.tile_nodes = tcn::pick_tile_nodes(n, e->num_sms);
-          tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr);
+          TIMED(ta.n_proj == 2 ? "k_node_tc(2 proj)" : "k_node_tc(1 proj)", st,
+                (tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr)));
         }
       } else {
         NodeArgs na{};
@@ -435,7 +484,9 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ea.edge_mask = io.edge_mask; ea.cls = ws.cls; ea.nm = ws.nm;
     ea.linker_mask = io.linker_mask; ea.W2_t = w.W2_t; ea.b2 = w.b2; ea.wd = e->use_tc ? w.wd_u : w.wd; ea.w0 = e->use_tc ? w.w0_u : w.w0; ea.w5 = w.w5;
     ea.plan = plan; ea.agg = nullptr; ea.x_out = xout; ea.nbr = ws.nbr; ea.recs = ws.xrecs; ea.n_recs = ws.n_recs ? ws.n_recs + 1 : nullptr;
+    g_times.begin(st, "edge COORD");
     dl_status st2 = launch_edge(e, gm, ea, true, w.W2_tc, st, e->allow_v3_coord ? w.W2_v3 : nullptr);
+    g_times.end(st);
     if (st2 != DL_OK) return st2;
     std::swap(xin, xout);
     std::swap(xin4, xout4);
@@ -453,7 +504,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   } else if (io.sampler) {
     fa.tag_step = e->step_ctr + 1;
   }
-  k_finish<<<(n + 15) / 16, 256, 0, st>>>(gm, fa);
+  TIMED("k_finish", st, (k_finish<<<(n + 15) / 16, 256, 0, st>>>(gm, fa)));
   LAUNCH_CHECK();
   e->launches += 1;
   if (e->cfg.centering || io.inpaint) {
@@ -541,6 +592,7 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaFuncSetAttribute(k_edge_simt<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_edge_simt<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)EDGE_SIMT_SMEM));
   CK(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * CUT_SMEM_PER_NODE));
+  if (getenv("DL_TIME_KERNELS")) g_times.on = true;
   if (const char* v = getenv("DL_EDGE_V3")) e->allow_v3 = atoi(v) != 0;
   if (const char* v = getenv("DL_EDGE_V3_COORD")) e->allow_v3_coord = atoi(v) != 0;
   dl_status s = tc::configure();
@@ -553,6 +605,8 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
 
 dl_status dl_destroy(dl_engine* e) {
   if (!e) return DL_OK;
+  g_times.report();
+  g_times.acc.clear();
   cudaSetDevice(e->cfg.device);
   cudaDeviceSynchronize();
   free_workspace(e->ws);
@@ -708,6 +762,7 @@ dl_status dl_dynamics_forward(dl_engine* e, int32_t B, int32_t N, const float* t
   io.edge_mask = edge_mask; io.context = context; io.nan_flags = nan_flags;
   if ((s = enqueue_forward(e, B, N, io, st)) != DL_OK) return s;
   CK(cudaEventRecord(e->ev_t1, st));
+  g_times.collect(st);
   return DL_OK;
 }
 

@@ -596,15 +596,19 @@ struct TileDSet {
 __global__ void __launch_bounds__(TN) k_tiles_d(TileDSet s0, TileDSet s1, const float4* __restrict__ x4, int write_d0, float norm_constant,
                                                int n3, const float* __restrict__ xsrc, float* __restrict__ xdst,
                                                const float4* __restrict__ x4src, float4* __restrict__ x4dst) {
-  __shared__ float red[TN / 32];
-  const int g = blockIdx.x, e = threadIdx.x;
+  __shared__ float red[2][TN / 32];
+  const int e = threadIdx.x;
   const TileDSet& s = blockIdx.y == 0 ? s0 : s1;
-  if (blockIdx.y == 0 && xdst != nullptr) {
-    const int i = g * TN + e;
-    if (i < n3) xdst[i] = xsrc[i];
-    if (i * 3 < n3) x4dst[i] = x4src[i];
+  if (blockIdx.y == 0 && xdst != nullptr) {                // grid-stride copy (the grid is a few CTAs per SM, not one per tile)
+    for (int i = blockIdx.x * TN + e; i < n3; i += gridDim.x * TN) {
+      xdst[i] = xsrc[i];
+      if (i * 3 < n3) x4dst[i] = x4src[i];
+    }
   }
-  if (s.n_items == nullptr || g >= *s.n_items) return;
+  if (s.n_items == nullptr) return;
+  const int n_tiles = *s.n_items;
+  int par = 0;
+  for (int g = blockIdx.x; g < n_tiles; g += gridDim.x, par ^= 1) {
   const int2 ij = s.tij[(size_t)g * TN + e];
   const float4 xi = x4[ij.x], xj = x4[ij.y];
   const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
@@ -620,12 +624,13 @@ __global__ void __launch_bounds__(TN) k_tiles_d(TileDSet s0, TileDSet s1, const 
   float m = d;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((e & 31) == 0) red[e >> 5] = m;
+  if ((e & 31) == 0) red[par][e >> 5] = m;                 // double-buffered: one barrier per tile
   __syncthreads();
   if (e == 0) {
-    m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+    m = fmaxf(fmaxf(red[par][0], red[par][1]), fmaxf(red[par][2], red[par][3]));
     s.tdmax[g] = m;
     if (write_d0) s.td0max[g] = m;
+  }
   }
 }
 

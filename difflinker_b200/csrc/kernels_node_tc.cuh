@@ -104,14 +104,14 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   uint8_t* xa_hi = sm + N_OFF_XA; uint8_t* xa_lo = xa_hi + X_BYTES;
   uint8_t* xb_hi = sm + 2 * X_BYTES; uint8_t* xb_lo = xb_hi + X_BYTES;
   float* nms = reinterpret_cast<float*>(sm + N_OFF_MISC);
-  int* tilemax = reinterpret_cast<int*>(sm + N_OFF_MISC + 512 * 3);
+  int* tilemax = reinterpret_cast<int*>(sm + N_OFF_MISC + 512);   // [16] one pre-zeroed slot per tile_max() call
 
   if (tid == 0) {
     for (int i = 0; i < N_RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 4; ++i) mbar_init(bar_acc + 8 * i, 1);
     fence_barrier_init();
-    *tilemax = 0;
   }
+  if (tid < 16) tilemax[tid] = 0;
   if (tid < TM) nms[tid] = tid < n_live ? a.nm[g0 + tid] : 0.f;   // (tid < TM are workers of part 0)
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
   tc_fence_before();
@@ -182,20 +182,26 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
     }
     return mx;
   };
-  // block-wide maximum of a non-negative float (int compare is order-preserving); all 128 workers call it
+  // block-wide maximum of a non-negative float (int compare is order-preserving); all workers call it, in the same order:
+  // the k-th call uses the k-th pre-zeroed slot, so one barrier per call suffices
+  int tm_calls = 0;
   auto tile_max = [&](float mx) -> float {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    workers_sync();                                    // previous users of *tilemax are done
-    if (tid == 0) *tilemax = 0;
+    int* slot = tilemax + (tm_calls++ & 15);
+    if (lane == 0) atomicMax(slot, __float_as_int(mx));
     workers_sync();
-    if (lane == 0) atomicMax(tilemax, __float_as_int(mx));
-    workers_sync();
-    return __int_as_float(*tilemax);
+    return __int_as_float(*slot);
   };
 
-  float s1 = pow2_scale_for(tile_max(load_rows(1.0f)));
-  if (s1 != 1.0f) load_rows(s1);                       // rare (diverging samples): rewrite the operands scaled
+  float s1 = 1.0f;
+#pragma unroll 1
+  for (int pass = 0; pass < 2; ++pass) {               // second pass: rare (diverging samples), rewrites the operands scaled
+    const float mx = load_rows(s1);
+    if (pass == 1) break;
+    s1 = pow2_scale_for(tile_max(mx));
+    if (s1 == 1.0f) break;
+  }
   fence_proxy_async();
   tc_fence_before();
   workers_sync();
@@ -258,8 +264,14 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
         }
         return mx;
       };
-      s2 = pow2_scale_for(tile_max(epi1(1.0f)));
-      if (s2 != 1.0f) epi1(s2);
+      s2 = 1.0f;
+#pragma unroll 1
+      for (int pass = 0; pass < 2; ++pass) {
+        const float mx = epi1(s2);
+        if (pass == 1) break;
+        s2 = pow2_scale_for(tile_max(mx));
+        if (s2 == 1.0f) break;
+      }
     }
     fence_proxy_async();
     tc_fence_before();

@@ -827,22 +827,36 @@ __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
     step = *a.tag_step;
   }
   const bool act = g < n_total && d < xd;
+  // embedding_out operands staged in shared memory: the 16 nodes' h rows (coalesced loads) and Wo transposed to [k][j], so
+  // the 16 lanes of a node read 16 consecutive floats per k (the direct form -- every lane streaming its own 512-byte
+  // Wo row -- was bound by L1 wavefronts: 23 us for 14 MFLOP)
+  __shared__ __align__(16) float hs[16][H + 4];
+  __shared__ float ws[H][16];
+  for (int idx = tid; idx < 16 * (H / 4); idx += 256) {
+    const int rr = idx / (H / 4), k4 = idx - rr * (H / 4);
+    const int gg = blockIdx.x * 16 + rr;
+    const float4 v = gg < n_total ? *reinterpret_cast<const float4*>(a.h + (size_t)gg * H + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    *reinterpret_cast<float4*>(&hs[rr][k4 * 4]) = v;
+  }
+  for (int idx = tid; idx < 16 * H; idx += 256) {
+    const int j = idx / H, k = idx - j * H;
+    ws[k][j] = j < gm.F ? __ldg(a.Wo + (size_t)j * H + k) : 0.f;
+  }
+  __syncthreads();
   float e = 0.f;
   if (act) {
     float m = a.nm[g];
     if (d < 3) {
       e = (a.x[(size_t)g * 3 + d] - a.x0[(size_t)g * 3 + d]) * m;
     } else {
-      const float* hr = a.h + (size_t)g * H;
-      const float* wr = a.Wo + (size_t)(d - 3) * H;
-      float s = 0.f;
+      const int j = d - 3;
+      float s = 0.f;                                          // same summation order as before: k ascending
 #pragma unroll 8
       for (int k = 0; k < H; k += 4) {
-        float4 hv = *reinterpret_cast<const float4*>(hr + k);
-        float4 wv = __ldg(reinterpret_cast<const float4*>(wr + k));
-        s = fmaf(hv.x, wv.x, s); s = fmaf(hv.y, wv.y, s); s = fmaf(hv.z, wv.z, s); s = fmaf(hv.w, wv.w, s);
+        const float4 hv = *reinterpret_cast<const float4*>(&hs[r][k]);
+        s = fmaf(hv.x, ws[k][j], s); s = fmaf(hv.y, ws[k + 1][j], s); s = fmaf(hv.z, ws[k + 2][j], s); s = fmaf(hv.w, ws[k + 3][j], s);
       }
-      e = (s + a.bo[d - 3]) * m;
+      e = (s + a.bo[j]) * m;
     }
     if (e != e && a.nan_flags != nullptr) {
       // bit0: NaN in vel, bit1: NaN in h (utils.py:274-282); bits 8.. = 1 + index of the first failing

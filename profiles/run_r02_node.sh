@@ -9,3 +9,4 @@ import json
 d=json.loads(open("gpurun_out/node_prof.json").read().strip().splitlines()[-1])
 print("value", round(d["value"],1), "fwd_ms", round(d["forward"]["ms"],4), "gcl_ms", d["roofline"]["kernel_ms"])
 PY
+DL_TIME_KERNELS=1 python profiles/time_kernels.py cfg2_zinc 20 2>&1 | grep "dl times"
