@@ -62,6 +62,7 @@ struct Workspace {
   int2* tij[2] = {nullptr, nullptr};
   float *td[2] = {nullptr, nullptr}, *td0[2] = {nullptr, nullptr}, *tdmax[2] = {nullptr, nullptr}, *td0max[2] = {nullptr, nullptr};
   float* tcd = nullptr;
+  int* cta_begin[2] = {nullptr, nullptr};   // cost-balanced slices of the two tile lists over the v3 kernels' CTAs
   std::vector<void*> allocs;
 };
 
@@ -255,6 +256,7 @@ dl_status ensure_workspace(dl_engine* e, int B, int N) {
           (s2 = dev_alloc(ws, &ws.tdmax[k], n)) != DL_OK || (s2 = dev_alloc(ws, &ws.td0max[k], n)) != DL_OK)
         return s2;
     if ((s2 = dev_alloc(ws, &ws.tcd, n * 3 * tc::TN)) != DL_OK) return s2;
+    if ((s2 = dev_alloc(ws, &ws.cta_begin[0], (size_t)e->num_sms + 1)) != DL_OK || (s2 = dev_alloc(ws, &ws.cta_begin[1], (size_t)e->num_sms + 1)) != DL_OK) return s2;
     ws.v3 = true;
   }
   return DL_OK;
@@ -297,7 +299,8 @@ dl_status build_plan(dl_engine* e, int B, int N, const int8_t* node_mask, const 
   const int max_rows = e->use_tc ? tc::MAXR : MAXR;
   // GCL items of the v3 kernel: rows padded to a multiple of four columns, at most MAXR3 rows per tile
   k_plan_items<<<1, 1, 0, st>>>(B, tile_edges, max_rows, ws.v3 ? 4 : 1, ws.v3 ? tc3::MAXR3 : max_rows, ws.nr, ws.nc, ws.nxr,
-                                ws.items, ws.n_items, ws.xmols, ws.n_xmols, ws.xitems, ws.n_xitems);
+                                ws.items, ws.n_items, ws.xmols, ws.n_xmols, ws.xitems, ws.n_xitems, ws.v3 ? e->num_sms : 0,
+                                ws.cta_begin[0], ws.cta_begin[1]);
   LAUNCH_CHECK();
   e->launches += 2;
   if (ws.v3) {
@@ -316,6 +319,7 @@ tc3::TileTables make_tile_tables(const Workspace& ws, bool coord) {
   t.ts = ws.ts[k]; t.td = ws.td[k]; t.td0 = ws.td0[k]; t.tdmax = ws.tdmax[k]; t.td0max = ws.td0max[k];
   t.tcd = coord ? ws.tcd : nullptr;
   t.items = coord ? ws.xitems : ws.items; t.n_items = coord ? ws.n_xitems : ws.n_items; t.rowidx = coord ? ws.xrowidx : ws.rowidx;
+  t.cta_begin = ws.cta_begin[k];
   return t;
 }
 

@@ -86,6 +86,7 @@ struct TileTables {
   const int4* items;      // the tile list these tables describe (GCL: plan.items over rowidx; COORD: plan.xitems over xrowidx)
   const int* n_items;
   const int* rowidx;
+  const int* cta_begin;   // [gridDim.x + 1] cost-balanced contiguous slices of the tile list (k_plan_items)
 };
 
 // Warp layout: producers 0..15, MMA issuer 16, table warps 17..19, epilogue 20..20+NEPI-1 (20 % 4 == 0: an epilogue warp's TMEM
@@ -120,10 +121,8 @@ struct TileIter3 {
   __device__ TileIter3(const TileTables& tt, int N_) : N(N_), rt(0), cache_base(-(1 << 30)), lane(threadIdx.x & 31) {
     list = tt.items;
     rowlist = tt.rowidx;
-    const int total = *tt.n_items;
-    const int per = total / (int)gridDim.x, extra = total % (int)gridDim.x, c = (int)blockIdx.x;
-    wi = c * per + min(c, extra);
-    wi_end = wi + per + (c < extra ? 1 : 0);
+    wi = tt.cta_begin[blockIdx.x];
+    wi_end = tt.cta_begin[blockIdx.x + 1];
     cache = make_int4(0, 0, 0, 0);
   }
   __device__ bool next(Tile3& t) {
@@ -215,18 +214,21 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       TileIter3 iter(tt, N);
       Tile3 cur;
       int q = -1, prev_b = -1, ps = 0, pu = 0;              // ps = t % NPS3, pu = t / NPS3
-      float mol_bmax = 0.f;                                 // max |B_j| over the current molecule (range bound)
+      float mol_abmax = 0.f;                                // max |A_i| + max |B_j| over the current molecule (range bound)
       for (int t = 0;; ++t, ps = (ps + 1 == NPS3 ? 0 : ps + 1), pu += (ps == 0)) {
         const int slot = t & (NES - 1);
         const bool more = iter.next(cur);
         bool first = false;
         if (more && cur.b != prev_b) { first = true; ++q; prev_b = cur.b; }
         if (more && first) {                                 // every table warp tracks the molecule bound (cheap, keeps them in step)
-          float m = 0.f;
-          for (int j = lane; j < N; j += 32) m = fmaxf(m, a.ABmax[((size_t)cur.b * N + j) * 2 + 1]);
+          float ma = 0.f, mb = 0.f;
+          for (int j = lane; j < N; j += 32) {
+            const float2 v = *reinterpret_cast<const float2*>(a.ABmax + ((size_t)cur.b * N + j) * 2);
+            ma = fmaxf(ma, v.x); mb = fmaxf(mb, v.y);
+          }
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-          mol_bmax = m;
+          for (int o = 16; o > 0; o >>= 1) { ma = fmaxf(ma, __shfl_xor_sync(0xffffffffu, ma, o)); mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, o)); }
+          mol_abmax = ma + mb;
         }
         if (t % N_TBL_WARPS != tw) { if (!more) break; continue; }
         if (t >= NES) wait_relaxed(bars + B3_TFREE + 8 * slot, ((t - NES) / NES) & 1, 0);        // epilogue done with tile t - NES
@@ -246,11 +248,9 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
           }
           if (lane == 0) mbar_expect_tx_only(bar, (uint32_t)(cur.nrt * H * 4 + TS_BYTES + 2 * TN * 4 + (COORD ? 3 * TN * 4 : 0)));
           __syncwarp();
-          float amax = 0.f;
           if (lane < cur.nrt) {                              // A_i rows of the tile: 512-byte bulk copies into the slot
             const int node_r = cur.rows[cur.slot0 + lane];
             bulk_g2s(smem_u32(pb + P3_A) + lane * (H * 4), a.AB + (gb + node_r) * 2 * H, H * 4, bar);
-            amax = a.ABmax[(gb + node_r) * 2];
           } else if (lane == 8) {
             bulk_g2s(smem_u32(pb + P3_BOFF), tt.ts + (size_t)cur.gidx * TS_BYTES, TS_P_BYTES, bar);
           } else if (lane == 9) {
@@ -262,12 +262,10 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
           } else if (COORD && lane == 12) {
             bulk_g2s(smem_u32(tb + E3_CD), tt.tcd + (size_t)cur.gidx * 3 * TN, 3 * TN * 4, bar);
           }
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));   // lanes 0..7 hold the rows
           if (lane == 0) {
-            // |u| <= max|A_i| + max|B_j| + d max|wd| + d0 max|w0| over the tile: ONE exact power-of-two scale per tile keeps
-            // the fp16 hi/lo operands below 2^14 (only ever != 1 for diverging samples)
-            const float bound = amax + mol_bmax + tt.tdmax[cur.gidx] * a.wdmax + tt.td0max[cur.gidx] * a.w0max;
+            // |u| <= max|A_i| + max|B_j| (over the molecule) + d max|wd| + d0 max|w0| (over the tile): ONE exact power-of-two
+            // scale per tile keeps the fp16 hi/lo operands below 2^14 (only ever != 1 for diverging samples)
+            const float bound = mol_abmax + tt.tdmax[cur.gidx] * a.wdmax + tt.td0max[cur.gidx] * a.w0max;
             float sc = 1.0f;
             if (!(bound <= F16_TARGET)) {
               const int ex2 = ((__float_as_int(bound) >> 23) & 0xff) - 127;

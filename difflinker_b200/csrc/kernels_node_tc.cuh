@@ -39,9 +39,13 @@ constexpr int N_OFF_MISC = 226304;             // nm[128] f32, nodemax[2][128] i
 constexpr int N_OFF_BAR = N_OFF_MISC + 128 * 4 * 3 + 16;      // full[4], empty[4], acc[4]; tmem slot
 constexpr int N_SMEM_BYTES = N_OFF_BAR + 128 + 1024;
 static_assert(N_SMEM_BYTES <= 232448 && 4 * X_BYTES_MAX + 2 * STAGE_BYTES <= N_OFF_MISC, "k_node_tc shared memory");
-constexpr int NW = 16;                         // worker warps: warp w serves TMEM lane quarter w % 4 and node columns
-constexpr int NPART = NW / 4;                  //   [part*CW, (part+1)*CW) with part = w / 4 -- 4 warps per scheduler
-constexpr int CW = TM / NPART;                 //   hide each other's TMEM / shared / global latencies
+#ifndef DL_NODE_WORKER_WARPS
+#define DL_NODE_WORKER_WARPS 24
+#endif
+constexpr int NW = DL_NODE_WORKER_WARPS;       // worker warps: warp w serves TMEM lane quarter w % 4 and node columns
+constexpr int NPART = NW / 4;                  //   [part*cw, (part+1)*cw) with part = w / 4 -- 6 warps per scheduler hide each
+constexpr int CW = ((TM + NPART - 1) / NPART + 7) & ~7;   // other's TMEM / shared / global latencies (the epilogues of this kernel
+                                               //   are dependency-latency bound: 24 instead of 16 warps shorten every phase)
 constexpr int NODE_TC_THREADS = 32 * (NW + 1); // + 1 weight-loader warp
 
 struct NodeTcArgs {
@@ -155,7 +159,7 @@ __global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, Nod
   auto load_rows = [&](float scale) -> float {
     float mx = 0.f;
 #pragma unroll 1
-    for (int rb = 0; rb < TM / NW; rb += 4) {            // 4 rows per warp per batch: 8 x 16-byte loads in flight per lane
+    for (int rb = 0; warp + NW * rb < n_pad; rb += 4) {  // 4 rows per warp per batch: 8 x 16-byte loads in flight per lane
       float4 hv[4], av[4];
 #pragma unroll
       for (int j = 0; j < 4; ++j) {

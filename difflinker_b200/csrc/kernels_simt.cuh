@@ -64,7 +64,8 @@ __global__ void k_plan_mol(int N, int graph_type, const int8_t* __restrict__ edg
 __global__ void k_plan_items(int B, int tile_edges, int max_rows, int col_pad, int max_rows_gcl, const int* __restrict__ nr,
                              const int* __restrict__ nc, const int* __restrict__ nxr, int4* __restrict__ items,
                              int* __restrict__ n_items, int* __restrict__ xmols, int* __restrict__ n_xmols,
-                             int4* __restrict__ xitems, int* __restrict__ n_xitems) {
+                             int4* __restrict__ xitems, int* __restrict__ n_xitems, int n_cta = 0,
+                             int* __restrict__ cta_begin = nullptr, int* __restrict__ xcta_begin = nullptr) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   int cnt = 0, xc = 0, xi = 0;
   for (int b = 0; b < B; ++b) {
@@ -92,6 +93,27 @@ __global__ void k_plan_items(int B, int tile_edges, int max_rows, int col_pad, i
   *n_items = cnt;
   *n_xmols = xc;
   *n_xitems = xi;
+  // v3 kernels: contiguous slices of the tile lists per CTA, balanced by cost (padded edges + a per-tile constant) instead of
+  // by tile count -- single-row tiles at the end of a molecule cost a third of a full tile
+  if (n_cta > 0 && cta_begin != nullptr) {
+    for (int pass = 0; pass < 2; ++pass) {
+      const int4* list = pass == 0 ? items : xitems;
+      const int total = pass == 0 ? cnt : xi;
+      int* out = pass == 0 ? cta_begin : xcta_begin;
+      if (out == nullptr) continue;
+      long long sum = 0;
+      for (int k = 0; k < total; ++k) sum += (long long)list[k].z * ((list[k].w + col_pad - 1) / col_pad * col_pad) + 32;
+      long long run = 0;
+      int c = 0;
+      out[0] = 0;
+      for (int k = 0; k < total; ++k) {
+        // CTA c ends before item k once its share is reached
+        while (c + 1 < n_cta && run * n_cta >= (long long)(c + 1) * sum) out[++c] = k;
+        run += (long long)list[k].z * ((list[k].w + col_pad - 1) / col_pad * col_pad) + 32;
+      }
+      while (c < n_cta) out[++c] = total;
+    }
+  }
 }
 
 // Activation of the fp32 SIMT kernels: SiLU for the denoiser (egnn.py:325), ReLU for SizeGNN (linker_size.py:60).
