@@ -387,7 +387,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
     ta.n_proj = 1; ta.pw[0] = reinterpret_cast<const __half*>(w0.W1_tc); ta.pb1[0] = w0.b1_u;
     ta.p_descale[0] = w0.w1_descale; ta.AB[0] = ws.ABg; ta.ABmax[0] = ws.ABgmax;
     ta.tile_nodes = tcn::pick_tile_nodes(n, e->num_sms);
-    TIMED("k_node_tc(proj only)", st, (tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr)));
+    TIMED("k_node_tc(proj only)", st, (tcn::launch_node(n, ta, st, nullptr)));
     LAUNCH_CHECK();
     e->launches += 1;
   }
@@ -459,7 +459,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
         else {
           ta.tile_nodes = tcn::pick_tile_nodes(n, e->num_sms);
           TIMED(ta.n_proj == 2 ? "k_node_tc(2 proj)" : "k_node_tc(1 proj)", st,
-                (tcn::k_node_tc<<<(n + ta.tile_nodes - 1) / ta.tile_nodes, tcn::NODE_TC_THREADS, tcn::N_SMEM_BYTES, st>>>(n, ta, nullptr)));
+                (tcn::launch_node(n, ta, st, nullptr)));
         }
       } else {
         NodeArgs na{};

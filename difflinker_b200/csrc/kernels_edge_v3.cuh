@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       if (warp == W3_TBL) prof_flush(0);
     } else {
       // =================================== MMA issuer ===================================================================
-      if (lane == 0) {
+      // warp-convergent: all lanes walk the loop with uniform values, one elected lane issues each tcgen05 instruction
+      {
         mbar_wait(bars + B3_W, 0);                           // W2 hi | lo are in tensor memory
         tc_fence_after();
         int acc = 0, use = 0;
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
           // phase a still-running commit of tile t-3 is about to complete)
           if (use > 0) wait_on(bars + B3_TEMPTY + 8 * acc, (use - 1) & 1, 1);
           const int Et = reinterpret_cast<const int*>(sm + O3_ET + slot * EB + E3_HDR)[0];
-          if (Et <= 0) { mbar_arrive(bars + B3_TFULL + 8 * acc); break; }
+          if (Et <= 0) { if (lane == 0) mbar_arrive(bars + B3_TFULL + 8 * acc); break; }
           tc_fence_after();
           const uint32_t bhi = sbase + O3_ST + s * STAGE_BYTES, blo = bhi + B_BYTES;
           const uint32_t dcol = tmem + TM_ACC + acc * TN;
@@ -306,12 +307,12 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
           for (int ks = 0; ks < 8; ++ks) {
             const uint64_t b_hi = umma_desc(bhi + ks * 2 * B_LBO, B_LBO, SBO), b_lo = umma_desc(blo + ks * 2 * B_LBO, B_LBO, SBO);
             const uint32_t a_hi = tmem + TM_W + ks * 8, a_lo = tmem + TM_W + 64 + ks * 8;
-            umma_f16_ts(dcol, a_lo, b_hi, idesc, ks > 0);
-            umma_f16_ts(dcol, a_hi, b_lo, idesc, 1);
-            umma_f16_ts(dcol, a_hi, b_hi, idesc, 1);
+            umma_f16_ts_elect(dcol, a_lo, b_hi, idesc, ks > 0);
+            umma_f16_ts_elect(dcol, a_hi, b_lo, idesc, 1);
+            umma_f16_ts_elect(dcol, a_hi, b_hi, idesc, 1);
           }
-          umma_commit(bars + B3_EMPTY + 8 * s);
-          umma_commit(bars + B3_TFULL + 8 * acc);
+          umma_commit_elect(bars + B3_EMPTY + 8 * s);
+          umma_commit_elect(bars + B3_TFULL + 8 * acc);
           pc[2] += 1;
           if (++acc == NACC3) { acc = 0; ++use; }
         }
