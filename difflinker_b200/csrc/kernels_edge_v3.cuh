@@ -89,13 +89,12 @@ struct TileTables {
   const int* cta_begin;   // [gridDim.x + 1] cost-balanced contiguous slices of the tile list (k_plan_items)
 };
 
-// Warp layout: producers 0..15, MMA issuer 16, table warps 17..19, epilogue 20..20+NEPI-1 (20 % 4 == 0: an epilogue warp's TMEM
-// lane quarter is warp % 4). NEPI = 8: 896 threads (72 registers at launch); NEPI = 12: 1024 threads (64 at launch).
-// Registers after setmaxnreg: 16 x 32 x PROD + 4 x 32 x CTRL + NEPI x 32 x EPI <= 65,536.
-constexpr int W3_PROD = 0, W3_MMA = 16, W3_TBL = 17, W3_EPI = 20;
-template <int NEPI> struct Regs3;
-template <> struct Regs3<8> { static constexpr int EPI = 64, CTRL = 56, PROD = 80; };    // 16,384 + 7,168 + 40,960 = 64,512
-template <> struct Regs3<12> { static constexpr int EPI = 48, CTRL = 48, PROD = 80; };   // 18,432 + 6,144 + 40,960 = 65,536
+// Warp layout: producers 0..15, MMA issuer 16, table warps 17..19, epilogue 20..31 (20 % 4 == 0: an epilogue warp's TMEM lane
+// quarter is warp % 4): 1024 threads, 64 registers at launch. Registers after setmaxnreg:
+// 16 x 32 x 80 (producers) + 4 x 32 x 48 (control) + 12 x 32 x 48 (epilogue) = 65,536.
+// (8 epilogue warps at 64 registers with double-buffered accumulator loads were measured 35 % slower: 102 vs 76 us.)
+constexpr int W3_PROD = 0, W3_MMA = 16, W3_TBL = 17, W3_EPI = 20, NEPI = 12;
+struct Regs3 { static constexpr int EPI = 48, CTRL = 48, PROD = 80; };
 
 // operand position p (0..127) -> channel (see "K permutation" above)
 __host__ __device__ constexpr int chan_of_pos(int p) { return (p & 4) ? 64 + 4 * (p >> 3) + (p & 3) : 4 * (p >> 3) + (p & 3); }
@@ -152,7 +151,7 @@ struct TileIter3 {
 // i.e. the GCL epilogue's per-channel segment sum with THREE edge weights (cd_x ew, cd_y ew, cd_z ew: tile table tcd) and one
 // reduction over the 128 channels per ROW (warp shuffles, then the four lane quarters meet in shared memory in a fixed order)
 // instead of one per edge.
-template <bool PROF, int NEPI, bool COORD>
+template <bool PROF, bool COORD>
 __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, EdgeArgs a, const uint32_t* __restrict__ w2p,
                                                                     const __grid_constant__ CUtensorMap tm_b, TileTables tt,
                                                                     unsigned long long* __restrict__ prof = nullptr) {
@@ -164,7 +163,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
   constexpr int NG = NEPI / 4;                             // epilogue warps per TMEM lane quarter: they take the tile rows round-robin
   constexpr int NES = COORD ? NES3_COORD : NES3;           // epilogue-side ring depth
   constexpr int EB = COORD ? E3C_BYTES : E3_BYTES;         // epilogue-side slot size
-  using RG = Regs3<NEPI>;
+  using RG = Regs3;
   const uint32_t bars = sbase + O3_BAR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + O3_BAR + B3_TMEMSLOT);
   float* b2s = reinterpret_cast<float*>(sm + O3_B2);
@@ -459,32 +458,13 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
           sa = __ffma2_rn(g0, make_float2(ew0.x, ew0.y), sa);
           sb = __ffma2_rn(g1, make_float2(ew0.z, ew0.w), sb);
         };
-        if constexpr (NEPI == 12) {                          // 48 registers per thread: parallelism comes from the 12 warps
-          for (int k = 0; k < n8; ++k) {
-            uint32_t ra[8];
-            TMEM_LD_X8(tacc + col0 + k * 8, ra);
-            const float4 ew0 = lds128(ews + col0 + k * 8), ew1 = lds128(ews + col0 + k * 8 + 4);
-            tmem_ld_wait();
-            quad(ra, ew0, s0, s1);
-            quad(ra + 4, ew1, s2, s3);
-          }
-        } else {                                             // 8 warps, 64 registers: accumulator columns double-buffered
-          uint32_t ra[8], rb[8];
-          if (n8 > 0) TMEM_LD_X8(tacc + col0, ra);
-          for (int k = 0; k < n8; k += 2) {
-            const float4 ew0 = lds128(ews + col0 + k * 8), ew1 = lds128(ews + col0 + k * 8 + 4);
-            tmem_ld_wait();
-            if (k + 1 < n8) TMEM_LD_X8(tacc + col0 + (k + 1) * 8, rb);
-            quad(ra, ew0, s0, s1);
-            quad(ra + 4, ew1, s2, s3);
-            if (k + 1 < n8) {
-              const float4 ew2 = lds128(ews + col0 + k * 8 + 8), ew3 = lds128(ews + col0 + k * 8 + 12);
-              tmem_ld_wait();
-              if (k + 2 < n8) TMEM_LD_X8(tacc + col0 + (k + 2) * 8, ra);
-              quad(rb, ew2, s0, s1);
-              quad(rb + 4, ew3, s2, s3);
-            }
-          }
+        for (int k = 0; k < n8; ++k) {                       // 48 registers per thread: parallelism comes from the 12 warps
+          uint32_t ra[8];
+          TMEM_LD_X8(tacc + col0 + k * 8, ra);
+          const float4 ew0 = lds128(ews + col0 + k * 8), ew1 = lds128(ews + col0 + k * 8 + 4);
+          tmem_ld_wait();
+          quad(ra, ew0, s0, s1);
+          quad(ra + 4, ew1, s2, s3);
         }
         if (ncc4 & 4) {
           uint32_t r4[4];
@@ -691,31 +671,26 @@ inline dl_status make_panel_map(CUtensorMap* out, const float* AB, int B, int N)
 }
 
 inline dl_status configure3() {
-  const bool ok = cudaFuncSetAttribute(k_edge_v3<false, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<true, 8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<false, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<true, 12, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
-                  cudaFuncSetAttribute(k_edge_v3<false, 12, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
+  const bool ok = cudaFuncSetAttribute(k_edge_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
   return ok ? DL_OK : DL_ERR_CUDA;
 }
 
 inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt,
                            int num_sms, cudaStream_t st) {
-  static const int nepi = getenv("DL_V3_NEPI") ? atoi(getenv("DL_V3_NEPI")) : 12;      // experiment switch: epilogue warps
   const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
-  if (coord) k_edge_v3<false, 12, true><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
-  else if (nepi == 8) k_edge_v3<false, 8, false><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
-  else k_edge_v3<false, 12, false><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
+  if (coord) k_edge_v3<false, true><<<num_sms, 32 * (W3_EPI + NEPI), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
+  else k_edge_v3<false, false><<<num_sms, 32 * (W3_EPI + NEPI), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
 }
 
+// Debug: one profiled GCL launch (clock64 accounting per role: wait vs total cycles), averaged over the CTAs, to stderr.
 inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt, int num_sms,
                                  cudaStream_t st) {
   unsigned long long* d = nullptr;
   if (cudaMalloc(&d, (size_t)num_sms * 16 * 8) != cudaSuccess) return DL_ERR_CUDA;
   cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
-  const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
-  if (getenv("DL_V3_NEPI") && atoi(getenv("DL_V3_NEPI")) == 8) k_edge_v3<true, 8, false><<<num_sms, 32 * (W3_EPI + 8), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
-  else k_edge_v3<true, 12, false><<<num_sms, 32 * (W3_EPI + 12), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, d);
+  k_edge_v3<true, false><<<num_sms, 32 * (W3_EPI + NEPI), SMEM3_BYTES, st>>>(gm, ea, reinterpret_cast<const uint32_t*>(w2_v3), tm, tt, d);
   if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
   std::vector<unsigned long long> h((size_t)num_sms * 16);
   cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);

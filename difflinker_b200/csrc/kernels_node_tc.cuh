@@ -86,313 +86,13 @@ __device__ __forceinline__ void store_elem(uint8_t* xhi, uint8_t* xlo, int x_lbo
   *reinterpret_cast<__half*>(xlo + off) = lo;
 }
 
-__global__ void __launch_bounds__(NODE_TC_THREADS, 1) k_node_tc(int n_total, NodeTcArgs a, long long* __restrict__ prof = nullptr) {
-  extern __shared__ uint8_t smem_raw[];
-  // keep the pointer derived from the __shared__ array (no integer round trip) so accesses compile to LDS/STS
-  uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const uint32_t sbase = smem_u32(sm);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const long long t0 = prof ? clock64() : 0;
-  auto mark = [&](int i) { if (prof && tid == 0) prof[(size_t)blockIdx.x * 8 + i] = clock64() - t0; };
-  const int tile = a.tile_nodes > 0 ? a.tile_nodes : TM;   // nodes of this CTA's tile (<= TM)
-  const int g0 = blockIdx.x * tile;
-  const int n_live = min(tile, n_total - g0);
-  const int n_pad = (tile + 15) & ~15;                     // UMMA N: operand rows [0, n_pad) are read by the tensor core
-
-  const int X_LBO = n_pad * 16 + 16;                       // operand slab pitch of THIS tile width (+16 B: conflict-free stores)
-  const int X_BYTES = KC * X_LBO;
-  const int off_ws = 4 * X_BYTES;                          // weight ring starts after XA hi|lo, XB hi|lo
-  const int n_ring = min(N_RING, (N_OFF_MISC - off_ws) / STAGE_BYTES);
-  const uint32_t bar_full = sbase + N_OFF_BAR, bar_empty = bar_full + 8 * N_RING, bar_acc = bar_empty + 8 * N_RING;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sm + N_OFF_BAR + 8 * (2 * N_RING + 4));
-  uint8_t* xa_hi = sm + N_OFF_XA; uint8_t* xa_lo = xa_hi + X_BYTES;
-  uint8_t* xb_hi = sm + 2 * X_BYTES; uint8_t* xb_lo = xb_hi + X_BYTES;
-  float* nms = reinterpret_cast<float*>(sm + N_OFF_MISC);
-  int* tilemax = reinterpret_cast<int*>(sm + N_OFF_MISC + 512);   // [16] one pre-zeroed slot per tile_max() call
-
-  if (tid == 0) {
-    for (int i = 0; i < N_RING; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 4; ++i) mbar_init(bar_acc + 8 * i, 1);
-    fence_barrier_init();
-  }
-  if (tid < 16) tilemax[tid] = 0;
-  if (tid < TM) nms[tid] = tid < n_live ? a.nm[g0 + tid] : 0.f;   // (tid < TM are workers of part 0)
-  if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-
-  const int blk0 = a.proj_only ? 3 : 0;           // proj_only: the W3 / W4 blocks are not streamed
-  const int n_blocks = 3 + 2 * a.n_proj - blk0;   // 128x128 weight blocks consumed by this tile, in order
-  const int n_half = 2 * n_blocks;
-
-  // ---- weight loader: a dedicated warp streams the half-blocks through the ring; it never joins the workers'
-  //      barriers (the ring's empty barriers are released by MMA completion, which needs the workers) ---------------
-  if (warp == NW) {
-    if (lane == 0) {
-      for (int i = 0; i < n_half; ++i) {
-        const int s = i % n_ring, blk = (i >> 1) + blk0, hf = i & 1;
-        if (i >= n_ring) mbar_wait(bar_empty + 8 * s, ((i - n_ring) / n_ring) & 1);
-        const __half* base = blk < 2 ? a.w3 + (size_t)blk * (BLOCK_BYTES / 2)
-                             : blk == 2 ? a.w4
-                                        : a.pw[(blk - 3) >> 1] + (size_t)((blk - 3) & 1) * (BLOCK_BYTES / 2);
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(base);
-        const uint32_t dst = sbase + off_ws + s * STAGE_BYTES;
-        mbar_expect_tx(bar_full + 8 * s, STAGE_BYTES);
-        bulk_g2s(dst, src + hf * HALF_BYTES, HALF_BYTES, bar_full + 8 * s);                      // hi, kc 8hf..8hf+7
-        bulk_g2s(dst + HALF_BYTES, src + W_BYTES + hf * HALF_BYTES, HALF_BYTES, bar_full + 8 * s);  // lo
-      }
-    }
-    return;
-  }
-
-  const int c = tid & (TM - 1);                        // this thread's output channel = TMEM lane
-  const int part = tid >> 7;                           // which slice of the node columns this thread serves
-  const int cw = (((tile + NPART - 1) / NPART) + 7) & ~7;  // slice width: a multiple of 8 (TMEM loads are 8 columns wide)
-  const int ncol0 = part * cw;
-  const int ncols = max(0, min(cw, tile - ncol0));     // this slice's columns (warp-uniform; 0 = idle slice)
-  const int ng = (ncols + 7) >> 3;                     // 8-column groups, <= CW / 8
-  const uint32_t trow = tmem + ((uint32_t)((warp & 3) * 32) << 16) + ncol0;
-
-  // ---- operand rows: h -> XA, agg -> XB; coalesced row loads (one row per warp iteration) -----------------------------
-  auto load_rows = [&](float scale) -> float {
-    float mx = 0.f;
-#pragma unroll 1
-    for (int rb = 0; warp + NW * rb < n_pad; rb += 4) {  // 4 rows per warp per batch: 8 x 16-byte loads in flight per lane
-      float4 hv[4], av[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = warp + NW * (rb + j);
-        hv[j] = make_float4(0, 0, 0, 0); av[j] = hv[j];
-        if (r < n_live) {
-          hv[j] = *reinterpret_cast<const float4*>(a.h + (size_t)(g0 + r) * H + lane * 4);
-          if (!a.proj_only) av[j] = __ldg(reinterpret_cast<const float4*>(a.agg + (size_t)(g0 + r) * H + lane * 4));
-        }
-      }
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = warp + NW * (rb + j);
-        if (r >= n_pad) continue;                        // (warp-uniform) rows beyond the UMMA N extent are never read
-        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(hv[j].x), fabsf(hv[j].y)), fmaxf(fabsf(hv[j].z), fabsf(hv[j].w))));
-        mx = fmaxf(mx, fmaxf(fmaxf(fabsf(av[j].x), fabsf(av[j].y)), fmaxf(fabsf(av[j].z), fabsf(av[j].w))));
-        const int off = (lane >> 1) * X_LBO + r * 16 + (lane & 1) * 8;     // channels 4*lane..4*lane+3 of row r
-        uint2 hi, lo;
-        split2(hv[j].x * scale, hv[j].y * scale, hi.x, lo.x); split2(hv[j].z * scale, hv[j].w * scale, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(xa_hi + off) = hi; *reinterpret_cast<uint2*>(xa_lo + off) = lo;
-        split2(av[j].x * scale, av[j].y * scale, hi.x, lo.x); split2(av[j].z * scale, av[j].w * scale, hi.y, lo.y);
-        *reinterpret_cast<uint2*>(xb_hi + off) = hi; *reinterpret_cast<uint2*>(xb_lo + off) = lo;
-      }
-    }
-    return mx;
-  };
-  // block-wide maximum of a non-negative float (int compare is order-preserving); all workers call it, in the same order:
-  // the k-th call uses the k-th pre-zeroed slot, so one barrier per call suffices
-  int tm_calls = 0;
-  auto tile_max = [&](float mx) -> float {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    int* slot = tilemax + (tm_calls++ & 15);
-    if (lane == 0) atomicMax(slot, __float_as_int(mx));
-    workers_sync();
-    return __int_as_float(*slot);
-  };
-
-  float s1 = 1.0f;
-#pragma unroll 1
-  for (int pass = 0; pass < 2; ++pass) {               // second pass: rare (diverging samples), rewrites the operands scaled
-    const float mx = load_rows(s1);
-    if (pass == 1) break;
-    s1 = pow2_scale_for(tile_max(mx));
-    if (s1 == 1.0f) break;
-  }
-  fence_proxy_async();
-  tc_fence_before();
-  workers_sync();
-  mark(0);   // rows loaded / converted
-
-  // ---- MMA issue helper (thread 0): consume `nh` half-blocks of the ring starting at ring index i0 ------------------
-  const uint32_t idesc = umma_idesc(128, n_pad);
-  auto issue = [&](int i0, int nh, const uint8_t* const* xhi_of, uint32_t acc_col, int acc_bar) {
-    // xhi_of[j]: node-operand hi base for half-block j of this GEMM (lo = hi + X_BYTES); kc offset = 8*(j&1)
-    tc_fence_after();
-    for (int j = 0; j < nh; ++j) {
-      const int i = i0 + j, s = i % n_ring;
-      mbar_wait(bar_full + 8 * s, (i / n_ring) & 1);
-      tc_fence_after();
-      const uint32_t xh = smem_u32(xhi_of[j]) + (8 * (j & 1)) * X_LBO, xl = xh + X_BYTES;
-      const uint32_t wh = sbase + off_ws + s * STAGE_BYTES, wl = wh + HALF_BYTES;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks) {
-        const uint64_t a_hi = umma_desc(wh + ks * 2 * W_LBO, W_LBO, SBO), a_lo = umma_desc(wl + ks * 2 * W_LBO, W_LBO, SBO);
-        const uint64_t b_hi = umma_desc(xh + ks * 2 * X_LBO, X_LBO, SBO), b_lo = umma_desc(xl + ks * 2 * X_LBO, X_LBO, SBO);
-        umma_f16(tmem + acc_col, a_lo, b_hi, idesc, (j | ks) != 0);
-        umma_f16(tmem + acc_col, a_hi, b_lo, idesc, 1);
-        umma_f16(tmem + acc_col, a_hi, b_hi, idesc, 1);
-      }
-      umma_commit(bar_empty + 8 * s);            // ring slot reusable once these MMAs have read it
-    }
-    umma_commit(bar_acc + 8 * acc_bar);
-  };
-
-  float s3 = s1;
-  if (!a.proj_only) {
-    // ---- G1: W3 [h, agg]^T -> accumulator 0 ---------------------------------------------------------------------------
-    if (tid == 0) {
-      const uint8_t* xs[4] = {xa_hi, xa_hi, xb_hi, xb_hi};
-      issue(0, 4, xs, 0, 0);
-    }
-    mbar_wait(bar_acc, 0);
-    tc_fence_after();
-    mark(1);   // G1 accumulator ready
-    float s2;
-    {
-      const float ds = a.w3_descale / s1;
-      const float bias = __ldg(a.b3 + c);
-      auto epi1 = [&](float scale) -> float {           // hid = silu(D*ds + b3) -> XB (agg operand is dead: G1 is complete)
-        float mx = 0.f;
-        uint32_t r[2][8];
-        if (ng > 0) TMEM_LD_X8(trow, r[0]);
-        #pragma unroll
-        for (int k = 0; k < CW / 8; ++k) {
-          if (k < ng) {                                  // warp-uniform
-            tmem_ld_wait();
-            if (k + 1 < ng) TMEM_LD_X8(trow + (k + 1) * 8, r[(k + 1) & 1]);
-        #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const float v = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
-              mx = fmaxf(mx, fabsf(v));                  // |silu(v)| <= |v|
-              store_elem(xb_hi, xb_lo, X_LBO, c, ncol0 + k * 8 + u, silu_f(v) * scale);
-            }
-          }
-        }
-        return mx;
-      };
-      s2 = 1.0f;
-#pragma unroll 1
-      for (int pass = 0; pass < 2; ++pass) {
-        const float mx = epi1(s2);
-        if (pass == 1) break;
-        s2 = pow2_scale_for(tile_max(mx));
-        if (s2 == 1.0f) break;
-      }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    workers_sync();
-    mark(2);   // epilogue 1 done
-
-    // ---- G2: W4 hid^T -> accumulator 1; residual, mask ------------------------------------------------------------------------
-    if (tid == 0) {
-      const uint8_t* xs[2] = {xb_hi, xb_hi};
-      issue(4, 2, xs, 128, 1);
-    }
-    mbar_wait(bar_acc + 8, 0);
-    tc_fence_after();
-    mark(3);   // G2 accumulator ready
-    {
-      const float ds = a.w4_descale / s2;
-      const float bias = __ldg(a.b4 + c);
-      float* hcol = a.h + (size_t)g0 * H + c;            // h[(g0+n)*128 + c]: a warp covers 128 contiguous bytes per node
-      float mx = 0.f;
-      uint32_t r[2][8];
-      float hv[2][8];
-      if (ng > 0) {
-      #pragma unroll
-        for (int u = 0; u < 8; ++u) hv[0][u] = (ncol0 + u < n_live) ? hcol[(size_t)(ncol0 + u) * H] : 0.f;
-        TMEM_LD_X8(trow + 128, r[0]);
-      }
-      #pragma unroll
-      for (int k = 0; k < CW / 8; ++k) {
-        if (k < ng) {                                    // warp-uniform
-          tmem_ld_wait();
-          if (k + 1 < ng) {
-            TMEM_LD_X8(trow + 128 + (k + 1) * 8, r[(k + 1) & 1]);
-      #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int nn = ncol0 + (k + 1) * 8 + u;
-              hv[(k + 1) & 1][u] = (nn < n_live) ? hcol[(size_t)nn * H] : 0.f;
-            }
-          }
-      #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int n = ncol0 + k * 8 + u;
-            const float o = (hv[k & 1][u] + fmaf(__uint_as_float(r[k & 1][u]), ds, bias)) * nms[n];     // egnn.py:71,78-79
-            if (n < n_live) hcol[(size_t)n * H] = o;
-            mx = fmaxf(mx, fabsf(o));
-            store_elem(xa_hi, xa_lo, X_LBO, c, n, o);
-          }
-        }
-      }
-      s3 = pow2_scale_for(tile_max(mx));
-      if (s3 != 1.0f) {                                  // rare: rewrite h' scaled (own global writes, program order)
-        for (int n = ncol0; n < ncol0 + 8 * ng; ++n) store_elem(xa_hi, xa_lo, X_LBO, c, n, (n < n_live ? hcol[(size_t)n * H] : 0.f) * s3);
-      }
-    }
-    fence_proxy_async();
-    tc_fence_before();
-    workers_sync();
-    mark(4);   // epilogue 2 done (h' stored, operand rewritten)
-  }
-
-  // ---- projections: A -> accumulator 2, B -> accumulator 3 (second consumer reuses 0 / 1) --------------------------------
-  if (tid == 0) {
-    const uint8_t* xs[2] = {xa_hi, xa_hi};
-    const int r0 = 2 * (3 - blk0);                   // ring position of the first projection half-block
-    issue(r0, 2, xs, 256, 2);
-    issue(r0 + 2, 2, xs, 384, 3);
-    if (a.n_proj > 1) {
-      issue(r0 + 4, 2, xs, 0, 0);
-      issue(r0 + 6, 2, xs, 128, 1);
-    }
-  }
-  for (int p = 0; p < a.n_proj; ++p) {
-    const float ds = a.p_descale[p] / s3;
-#pragma unroll 1
-    for (int part = 0; part < 2; ++part) {
-      const int accn = p == 0 ? 2 + part : part;
-      mbar_wait(bar_acc + 8 * accn, (p == 0 || a.proj_only) ? 0 : 1);   // accumulators 0/1 were used by G1/G2 before
-      tc_fence_after();
-      const float bias = part == 0 ? __ldg(a.pb1[p] + c) : 0.f;
-      float* abcol = a.AB[p] + (size_t)g0 * 2 * H + part * H + c;
-      float mx = 0.f;
-      uint32_t r[2][8];
-      if (ng > 0) TMEM_LD_X8(trow + accn * 128, r[0]);
-      #pragma unroll
-      for (int k = 0; k < CW / 8; ++k) {
-        if (k < ng) {                                  // warp-uniform
-          tmem_ld_wait();
-          if (k + 1 < ng) TMEM_LD_X8(trow + accn * 128 + (k + 1) * 8, r[(k + 1) & 1]);
-      #pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int n = ncol0 + k * 8 + u;
-            const float o = fmaf(__uint_as_float(r[k & 1][u]), ds, bias);
-            if (n < n_live) { abcol[(size_t)n * 2 * H] = o; mx = fmaxf(mx, fabsf(o)); }
-          }
-        }
-      }
-      // range bound for the consumer's fp16 operands: the TILE maximum of |A| (|B|) is written for every node of the
-      // tile -- a valid, slightly looser bound than the per-node maximum, at the cost of one block reduction.
-      const float tmx = tile_max(mx);
-      if (tid < n_live) a.ABmax[p][(size_t)(g0 + tid) * 2 + part] = tmx;
-    }
-  }
-  mark(6);   // projections written
-  tc_fence_before();
-  workers_sync();
-  if (warp == 0) tmem_dealloc(tmem, 512);
-}
-
 // ---------------------------------------------------------------------------------------------------------
-// k_node_tc2: same arithmetic, software-pipelined. In k_node_tc every GEMM phase has all workers waiting for the tensor core
-// and every epilogue has the tensor core waiting for the workers (measured: 13 K of the 31 K cycles are MMA phases, 18 K
-// epilogues). Here the tile's node columns are split into two CHUNKS (UMMA N ranges of the same operand tiles and
-// accumulators) and a dedicated warp issues the MMAs as soon as a chunk's operand is ready (mbarriers instead of the block
-// barrier), so the tensor core works on one chunk while the workers run the epilogue of the other.
-//   workers : rows(c0) rows(c1) | epi1(c0) epi1(c1) | epi2(c0) epi2(c1) | proj epilogues ...      (lockstep among themselves)
-//   MMA warp:          G1(c0)   G1(c1)   G2(c0)   G2(c1)   PA(c0) PA(c1) PB(c0) PB(c1) ...
-// Ring slots are released after BOTH chunks consumed a half-block; with fewer than four slots (wide tiles) G1 walks the
-// half-blocks chunk-interleaved so that two slots always suffice.
+// k_node_tc2: three roles. 24 worker warps (rows -> operand tiles, the epilogues), one weight-loader warp, and one
+// warp-convergent MMA issuer that is fed by mbarriers: the workers signal "operand ready" (rows / hid / h') and wait on the
+// accumulator barriers the issuer commits, so MMA issue never waits for a block barrier or for a worker thread's own work
+// (the first version issued from worker thread 0 after a block barrier: 22.9 / 29.1 us per launch vs 21.5 / 24.9 us).
+// The column range is written as "chunks" because a two-chunk pipelined variant (tensor core on one chunk, workers on the
+// other) was built on this structure; it measured slower (see the comment at `nchunk`).
 // ---------------------------------------------------------------------------------------------------------
 constexpr int W2_LOADER = NW, W2_MMA = NW + 1;
 constexpr int NODE_TC2_THREADS = 32 * (NW + 2);
@@ -766,18 +466,13 @@ inline void profile_node(int n, const NodeTcArgs& ta_in, cudaStream_t st, int nu
 }
 
 inline dl_status configure_node() {
-  if (cudaFuncSetAttribute(k_node_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, N_SMEM_BYTES) != cudaSuccess ||
-      cudaFuncSetAttribute(k_node_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, N2_SMEM_BYTES) != cudaSuccess)
-    return DL_ERR_CUDA;
+  if (cudaFuncSetAttribute(k_node_tc2, cudaFuncAttributeMaxDynamicSharedMemorySize, N2_SMEM_BYTES) != cudaSuccess) return DL_ERR_CUDA;
   return DL_OK;
 }
 
-// DL_NODE_V1=1 keeps the unpipelined kernel (A/B measurements)
 inline void launch_node(int n, const NodeTcArgs& ta, cudaStream_t st, long long* prof) {
-  static const bool v1 = getenv("DL_NODE_V1") != nullptr;
   const int grid = (n + ta.tile_nodes - 1) / ta.tile_nodes;
-  if (v1) k_node_tc<<<grid, NODE_TC_THREADS, N_SMEM_BYTES, st>>>(n, ta, prof);
-  else k_node_tc2<<<grid, NODE_TC2_THREADS, N2_SMEM_BYTES, st>>>(n, ta, prof);
+  k_node_tc2<<<grid, NODE_TC2_THREADS, N2_SMEM_BYTES, st>>>(n, ta, prof);
 }
 
 }  // namespace tcn
