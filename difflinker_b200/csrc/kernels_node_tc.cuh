@@ -14,8 +14,13 @@
 // Same 3xFP16 numerics as the edge kernel (kernels_tc.cuh). Range scaling is per TILE here (one exact power of
 // two chosen from the tile's maximum, only ever != 1 for diverging samples): operands are first written unscaled
 // while the maximum is reduced, and rewritten only in the rare case the bound exceeds 2^14.
-// Weights stream through a 2-stage ring of K=64 half-blocks (2 x 16 KB cp.async.bulk each) fed by a dedicated
-// loader warp; the MMA issuer thread only waits on the ring's full barriers.
+// Roles (k_node_tc2): 24 worker warps (row staging, epilogues; thread = output channel of one lane quarter), one loader
+// warp streaming K=64 weight half-blocks (2 x 16 KB cp.async.bulk each) through a ring of up to 4 stages, and one
+// warp-convergent MMA issuer (elect.sync) that walks a table of half-blocks and is fed by mbarriers only: `rdy` (the
+// workers have written the GEMM's operand tile) and the ring's `full`; it commits to `acc` per GEMM and to `empty` per
+// ring stage. The tile width is chosen at launch so that one wave of CTAs covers all nodes (72 nodes on cfg 2).
+// Measured: the GEMM phases take (4096 + 32 N)/64 cycles per MMA (shared-memory operand fetch at 64 B/clk), so splitting
+// the tile into pipelined column chunks doubles the tensor time (nchunk stays 1).
 #pragma once
 #include "kernels_tc.cuh"
 
