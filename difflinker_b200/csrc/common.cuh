@@ -9,6 +9,30 @@ constexpr int H = 128;         // hidden_nf (configs/*.yml `nf: 128`), compile-t
 constexpr int MAX_DIN = 32;    // F + C + 1 upper bound
 constexpr int MAX_XHD = 16;    // 3 + F upper bound (threads per node in k_finish)
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------------------------------------
+// The kernels of one forward form a strict chain on one stream. Launched with the programmatic-stream-serialization
+// attribute (launch_chain below), a kernel's CTAs may become resident while the previous kernel is still draining: they run
+// their prologue (barrier init, TMEM allocation, weight staging -- nothing the chain writes) and then block in chain_wait()
+// until the previous grid has COMPLETED and its memory operations are visible. Every kernel of the chain calls chain_wait()
+// before it touches anything another kernel of the chain produces or still reads, and only then chain_release()
+// (griddepcontrol.launch_dependents), so at most two consecutive kernels overlap and completion is transitive along the
+// chain. Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void chain_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void chain_release() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool& chain_overlap_enabled() { static bool on = true; return on; }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = chain_overlap_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(static_cast<Args&&>(args))...);
+}
+
 // silu(x) = x * sigmoid(x) (nn.SiLU, reference src/lightning.py:23-27) = x / (1 + 2^(-x log2 e)).
 // Raw ex2.approx / rcp.approx (2 MUFU + 3 FP32 ops; ~2 ulp each, far inside the 1e-4 end-to-end tolerance,
 // DESIGN.md "numerics"); the libdevice wrappers (__expf, __fdividef) add range-fixup instructions that this

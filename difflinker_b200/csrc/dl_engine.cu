@@ -374,7 +374,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   pa.coef = io.sampler ? e->coef_dev : nullptr;
   pa.step_prep = io.sampler ? e->step_ctr : nullptr;
   pa.step_fin = io.sampler ? e->step_ctr + 1 : nullptr;
-  TIMED("k_prep", st, (k_prep<<<node_blocks, 256, 0, st>>>(gm, pa)));
+  TIMED("k_prep", st, (launch_chain(k_prep, dim3(node_blocks), dim3(256), 0, st, gm, pa)));
   LAUNCH_CHECK();
   e->launches += 1;
   if (e->use_tc) {
@@ -415,7 +415,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
       // table: x == x0 there) + the x -> x_next copy that precedes the block's coordinate update
       tc3::TileDSet s0{ws.n_items, ws.tij[0], ws.td[0], ws.tdmax[0], ws.td0[0], ws.td0max[0], nullptr, nullptr};
       tc3::TileDSet s1{ws.n_xitems, ws.tij[1], ws.td[1], ws.tdmax[1], ws.td0[1], ws.td0max[1], ws.ts[1], ws.tcd};
-      TIMED("k_tiles_d", st, (tc3::k_tiles_d<<<dim3(e->num_sms * 8, 2), tc::TN, 0, st>>>(s0, s1, xin4, l == 0 ? 1 : 0, gm.norm_constant, n * 3, xin, xout, xin4, xout4)));
+      TIMED("k_tiles_d", st, (launch_chain(tc3::k_tiles_d, dim3(e->num_sms * 8, 2), dim3(tc::TN), 0, st, s0, s1, xin4, l == 0 ? 1 : 0, gm.norm_constant, n * 3, xin, xout, xin4, xout4)));
       LAUNCH_CHECK();
       e->launches += 1;
     }
@@ -508,7 +508,7 @@ dl_status enqueue_forward(dl_engine* e, int B, int N, const FwdIO& io, cudaStrea
   } else if (io.sampler) {
     fa.tag_step = e->step_ctr + 1;
   }
-  TIMED("k_finish", st, (k_finish<<<(n + 15) / 16, 256, 0, st>>>(gm, fa)));
+  TIMED("k_finish", st, (launch_chain(k_finish, dim3((n + 15) / 16), dim3(256), 0, st, gm, fa)));
   LAUNCH_CHECK();
   e->launches += 1;
   if (e->cfg.centering || io.inpaint) {
@@ -598,6 +598,7 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * CUT_SMEM_PER_NODE));
   if (getenv("DL_TIME_KERNELS")) g_times.on = true;
   if (const char* v = getenv("DL_EDGE_V3")) e->allow_v3 = atoi(v) != 0;
+  if (const char* v = getenv("DL_CHAIN_OVERLAP")) chain_overlap_enabled() = atoi(v) != 0;   // 0: plain stream order between kernels
   if (const char* v = getenv("DL_EDGE_V3_COORD")) e->allow_v3_coord = atoi(v) != 0;
   dl_status s = tc::configure();
   if (s == DL_OK) s = tcn::configure_node();

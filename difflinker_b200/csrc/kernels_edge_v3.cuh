@@ -210,6 +210,12 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       // =================================== table warps =================================================================
       // Tile-parallel: table warp k serves tiles t = k, k+3, ...; all three walk the same tile sequence.
       const int tw = warp - W3_TBL;
+      // Everything this CTA reads that another kernel of the forward produces (projections, tile tables, coordinates) enters
+      // through the table warps, and everything it writes leaves after tiles have travelled the pipeline: the table warps
+      // are the only ones that have to wait for the previous kernel. The prologue above and the W2 -> tensor memory copy of
+      // the epilogue warps overlap the previous kernel's tail.
+      chain_wait();
+      if (warp == W3_TBL && lane == 0) chain_release();
       TileIter3 iter(tt, N);
       Tile3 cur;
       int q = -1, prev_b = -1, ps = 0, pu = 0;              // ps = t % NPS3, pu = t / NPS3
@@ -578,6 +584,8 @@ __global__ void __launch_bounds__(TN) k_tiles_d(TileDSet s0, TileDSet s1, const 
   __shared__ float red[2][TN / 32];
   const int e = threadIdx.x;
   const TileDSet& s = blockIdx.y == 0 ? s0 : s1;
+  chain_wait();
+  chain_release();
   if (blockIdx.y == 0 && xdst != nullptr) {                // grid-stride copy (the grid is a few CTAs per SM, not one per tile)
     for (int i = blockIdx.x * TN + e; i < n3; i += gridDim.x * TN) {
       xdst[i] = xsrc[i];
@@ -680,8 +688,8 @@ inline dl_status configure3() {
 inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt,
                            int num_sms, cudaStream_t st) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
-  if (coord) k_edge_v3<false, true><<<num_sms, 32 * (W3_EPI + NEPI), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
-  else k_edge_v3<false, false><<<num_sms, 32 * (W3_EPI + NEPI), SMEM3_BYTES, st>>>(gm, ea, w, tm, tt, nullptr);
+  if (coord) launch_chain(k_edge_v3<false, true>, dim3(num_sms), dim3(32 * (W3_EPI + NEPI)), SMEM3_BYTES, st, gm, ea, w, tm, tt, nullptr);
+  else launch_chain(k_edge_v3<false, false>, dim3(num_sms), dim3(32 * (W3_EPI + NEPI)), SMEM3_BYTES, st, gm, ea, w, tm, tt, nullptr);
 }
 
 // Debug: one profiled GCL launch (clock64 accounting per role: wait vs total cycles), averaged over the CTAs, to stderr.

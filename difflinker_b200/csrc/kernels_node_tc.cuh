@@ -146,12 +146,19 @@ __global__ void __launch_bounds__(NODE_TC2_THREADS, 1) k_node_tc2(int n_total, N
     fence_barrier_init();
   }
   if (tid < 16) tilemax[tid] = 0;
-  if (tid < TM) nms[tid] = tid < n_live ? a.nm[g0 + tid] : 0.f;
   if (warp == 0) tmem_alloc(smem_u32(tmem_slot), 512);      // worker warp 0 allocates and, at the end, frees
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  // Up to here, and the loader warp's first weight stages below, nothing depends on the previous kernel of the forward: it
+  // overlaps that kernel's tail. The workers are the only role that touches chain-produced memory (h, agg, node mask in;
+  // h, projections out), so they wait; the node mask is first used after a workers_sync (tile_max) of the row pass.
+  if (warp < NW) {
+    chain_wait();
+    if (tid == 0) chain_release();
+    if (tid < TM) nms[tid] = tid < n_live ? a.nm[g0 + tid] : 0.f;
+  }
 
   const int blk0 = a.proj_only ? 3 : 0;
   const int n_blocks = 3 + 2 * a.n_proj - blk0;
@@ -477,7 +484,7 @@ inline dl_status configure_node() {
 
 inline void launch_node(int n, const NodeTcArgs& ta, cudaStream_t st, long long* prof) {
   const int grid = (n + ta.tile_nodes - 1) / ta.tile_nodes;
-  k_node_tc2<<<grid, NODE_TC2_THREADS, N2_SMEM_BYTES, st>>>(n, ta, prof);
+  launch_chain(k_node_tc2, dim3(grid), dim3(NODE_TC2_THREADS), N2_SMEM_BYTES, st, n, ta, prof);
 }
 
 }  // namespace tcn

@@ -235,6 +235,8 @@ __global__ void __launch_bounds__(256) k_prep(Geom gm, PrepArgs a) {
   const int g0 = blockIdx.x * NODE_TM;
   const int xd = 3 + gm.F;
   int step = 0;
+  chain_wait();
+  chain_release();
   if (a.step_prep != nullptr) {
     step = *a.step_prep;
     if (blockIdx.x == 0 && tid == 0) *a.step_fin = step;
@@ -841,6 +843,18 @@ __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
   const int n_total = gm.B * gm.N;
   const int g = blockIdx.x * 16 + r;
   const int xd = 3 + gm.F;
+  const bool act = g < n_total && d < xd;
+  // embedding_out operands staged in shared memory: the 16 nodes' h rows (coalesced loads) and Wo transposed to [k][j], so
+  // the 16 lanes of a node read 16 consecutive floats per k (the direct form -- every lane streaming its own 512-byte
+  // Wo row -- was bound by L1 wavefronts: 23 us for 14 MFLOP)
+  __shared__ __align__(16) float hs[16][H + 4];
+  __shared__ float ws[H][16];
+  for (int idx = tid; idx < 16 * H; idx += 256) {           // weights: not produced by the chain, staged before the wait
+    const int j = idx / H, k = idx - j * H;
+    ws[k][j] = j < gm.F ? __ldg(a.Wo + (size_t)j * H + k) : 0.f;
+  }
+  chain_wait();
+  chain_release();
   int step = 0;
   if (a.z != nullptr) {
     step = *a.step_fin;
@@ -848,21 +862,11 @@ __global__ void __launch_bounds__(256) k_finish(Geom gm, FinishArgs a) {
   } else if (a.tag_step != nullptr) {
     step = *a.tag_step;
   }
-  const bool act = g < n_total && d < xd;
-  // embedding_out operands staged in shared memory: the 16 nodes' h rows (coalesced loads) and Wo transposed to [k][j], so
-  // the 16 lanes of a node read 16 consecutive floats per k (the direct form -- every lane streaming its own 512-byte
-  // Wo row -- was bound by L1 wavefronts: 23 us for 14 MFLOP)
-  __shared__ __align__(16) float hs[16][H + 4];
-  __shared__ float ws[H][16];
   for (int idx = tid; idx < 16 * (H / 4); idx += 256) {
     const int rr = idx / (H / 4), k4 = idx - rr * (H / 4);
     const int gg = blockIdx.x * 16 + rr;
     const float4 v = gg < n_total ? *reinterpret_cast<const float4*>(a.h + (size_t)gg * H + k4 * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
     *reinterpret_cast<float4*>(&hs[rr][k4 * 4]) = v;
-  }
-  for (int idx = tid; idx < 16 * H; idx += 256) {
-    const int j = idx / H, k = idx - j * H;
-    ws[k][j] = j < gm.F ? __ldg(a.Wo + (size_t)j * H + k) : 0.f;
   }
   __syncthreads();
   float e = 0.f;
