@@ -320,6 +320,8 @@ tc3::TileTables make_tile_tables(const Workspace& ws, bool coord) {
   t.tcd = coord ? ws.tcd : nullptr;
   t.items = coord ? ws.xitems : ws.items; t.n_items = coord ? ws.n_xitems : ws.n_items; t.rowidx = coord ? ws.xrowidx : ws.rowidx;
   t.cta_begin = ws.cta_begin[k];
+  static const int stream_tasks = [] { const char* v = getenv("DL_V3_STREAM_TASKS"); return v ? atoi(v) : 1; }();
+  t.stream_tasks = stream_tasks;
   return t;
 }
 
@@ -598,6 +600,7 @@ dl_status dl_create(const dl_config* cfg, dl_engine** out) {
   CK(cudaFuncSetAttribute(k_nbr, cudaFuncAttributeMaxDynamicSharedMemorySize, 4000 * CUT_SMEM_PER_NODE));
   if (getenv("DL_TIME_KERNELS")) g_times.on = true;
   if (const char* v = getenv("DL_EDGE_V3")) e->allow_v3 = atoi(v) != 0;
+  if (const char* v = getenv("DL_WAIT_MODE")) { const int m = atoi(v); cudaMemcpyToSymbol(tc::c_wait_mode, &m, sizeof(int)); }
   if (const char* v = getenv("DL_CHAIN_OVERLAP")) chain_overlap_enabled() = atoi(v) != 0;   // 0: plain stream order between kernels
   if (const char* v = getenv("DL_EDGE_V3_COORD")) e->allow_v3_coord = atoi(v) != 0;
   dl_status s = tc::configure();

@@ -87,6 +87,7 @@ struct TileTables {
   const int* n_items;
   const int* rowidx;
   const int* cta_begin;   // [gridDim.x + 1] cost-balanced contiguous slices of the tile list (k_plan_items)
+  int stream_tasks;       // producers: deal the warp-tasks of consecutive tiles round-robin (0: warp w always takes task w)
 };
 
 // Warp layout: producers 0..15, MMA issuer 16, table warps 17..19, epilogue 20..31 (20 % 4 == 0: an epilogue warp's TMEM lane
@@ -337,8 +338,10 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       w0r[0] = make_float2(z0v.x, z0v.y); w0r[1] = make_float2(z0v.z, z0v.w); w0r[2] = make_float2(z1v.x, z1v.y); w0r[3] = make_float2(z1v.z, z1v.w);
     }
     const uint8_t* panel = sm + O3_PANEL + kc * 16;
-    const int grp = 2 * pw + esub;                           // this thread's group of four consecutive edges (same tile row)
-    const int e_base = 4 * grp;
+    // A tile's producer work is ceil(Et / 8) warp-tasks (two groups of four consecutive edges x 16 channel chunks). The tasks of
+    // consecutive tiles form one stream dealt round-robin to the 16 producer warps, so a tile with 15 tasks (3 rows of 40)
+    // leaves one warp free to start on the next tile and the short last tile of a molecule (5 tasks) occupies 5 warps, not 16.
+    int task_base = 0;                                       // tasks of all earlier tiles, mod 16
     int ps = 0;
     for (int t = 0;; ++t, ps = (ps + 1 == NPS3 ? 0 : ps + 1)) {
       const int s = t & (N_STAGE - 1), slot = t & (NES - 1);
@@ -355,6 +358,9 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       }
       if (t >= N_STAGE) wait_on(bars + B3_EMPTY + 8 * s, ((t - N_STAGE) / N_STAGE) & 1, 1);
       if (Et > 0) {
+        const int grp = 2 * ((pw - task_base) & (N_PROD_WARPS - 1)) + esub;   // this thread's group of four consecutive edges
+        const int e_base = 4 * grp;
+        if (tt.stream_tasks) task_base = (task_base + ((Et + 7) >> 3)) & (N_PROD_WARPS - 1);
         if (e_base < Et) {
           uint8_t* bhi = sm + O3_ST + s * STAGE_BYTES + kc * B_LBO + e_base * 16;
           uint8_t* blo = bhi + B_BYTES;

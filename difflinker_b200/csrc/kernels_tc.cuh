@@ -95,8 +95,30 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 // Bounded spin: a protocol bug must surface as a launch error, never as a hung GPU.
+// How a waiting thread waits (set once per process from DL_WAIT_MODE, experiment switch):
+//   0  bare try_wait loop: a failed try_wait returns after a few cycles on this part, so a waiting warp keeps issuing
+//      (try_wait, select, compare, branch) and competes with the warps it is waiting FOR: a third of all instructions the
+//      edge kernel issued were such polls
+//   1  try_wait with a suspend-time hint: the hardware parks the thread until the phase completes or the time limit passes
+//   2  try_wait, then nanosleep(32) between polls
+__device__ __constant__ int c_wait_mode = 1;
+constexpr uint32_t WAIT_HINT_NS = 20000;
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
+  const int mode = c_wait_mode;
+  if (mode == 1) {
+    for (uint32_t spin = 0; spin < (1u << 20); ++spin) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+          "selp.u32 %0, 1, 0, p;\n\t}"
+          : "=r"(done)
+          : "r"(bar), "r"(parity), "r"(WAIT_HINT_NS)
+          : "memory");
+      if (done) return;
+    }
+    __trap();
+  }
   for (uint32_t spin = 0; spin < (1u << 28); ++spin) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -106,6 +128,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         : "r"(bar), "r"(parity)
         : "memory");
     if (done) return;
+    if (mode == 2) __nanosleep(32);
   }
   __trap();
 }
