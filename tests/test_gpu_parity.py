@@ -138,16 +138,17 @@ def test_public_ddpm_sample_chain_matches_reference_golden(name):
         assert rel_err(chain[0][..., :3], want[0][..., :3]) <= REL_TOL
     else:
         # Per molecule: 1e-4 of the coordinate scale, or -- where the trajectory itself is ill-conditioned -- 30x the distance
-        # between the REFERENCE's own fp32 and fp64 runs on the same noise (`drift64`, oracle/make_golden_r2.py). With random
-        # weights at L=8 two of the eight molecules are chaotic: the reference's fp32 and fp64 results are Angstroms apart,
-        # and so is every re-ordering of the fp32 arithmetic (the fp32 SIMT path lands 4 A from the fixture, the reference's
-        # fp64 run a comparable distance); for the other molecules and for L=6 / cfg3 the 1e-4 bound is the binding one.
+        # between the REFERENCE's own fp32 and fp64 runs on the same noise (`drift64`, oracle/make_golden_r2.py drift). For the
+        # L=6 and cfg3 fixtures drift64 is 1e-4 .. 6e-4 A on coordinates of 170 .. 330 A and the 1e-4 bound is the binding one
+        # for every molecule. With random weights at L=8 (coord_mlp gain x100, 8 blocks) the reference's fp32 and fp64 results
+        # are 6.7 A and 2.2 A apart for two of the eight molecules and 1e-3 .. 1e-2 A for three more; every re-ordering of the
+        # fp32 arithmetic moves those by a comparable amount (the fp32 SIMT path lands 4.2 A from the fixture on molecule 1, the
+        # tcgen05 path 6.3 A). At least half of the molecules must meet the plain 1e-4 bound outright (measured: 5 of 8 at L=8).
         scale = want[0][..., :3].abs().max().item()
         err = ((chain[0][..., :3] - want[0][..., :3]) * lm).abs().flatten(1).max(1).values
         tol = torch.maximum(torch.full_like(err, REL_TOL * scale), 30.0 * a["drift64"].float())
         assert (err <= tol).all(), (err.tolist(), tol.tolist())
-        well_conditioned = a["drift64"].float() * 30.0 <= REL_TOL * scale
-        assert well_conditioned.sum() >= (B + 1) // 2, "fixture too chaotic to pin anything"
+        assert (err <= REL_TOL * scale).sum() >= (B + 1) // 2, (err.tolist(), REL_TOL * scale)
     for f in range(1, meta["keep_frames"]):
         assert rel_err(chain[f], want[f]) <= REL_TOL, f
 
