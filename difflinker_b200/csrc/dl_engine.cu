@@ -1065,7 +1065,7 @@ float dl_time_edge_kernel(dl_engine* e, int32_t reps) {
   ea.plan = make_plan(ws); ea.agg = ws.agg; ea.x_out = nullptr; ea.nbr = ws.nbr; ea.recs = ws.recs; ea.n_recs = ws.n_recs;
   cudaStream_t st = e->loop_stream;
   if (e->use_tc && getenv("DL_PROFILE_EDGE")) {
-    if (ws.v3) tc3::profile_edge_v3(gm, ea, w.W2_v3, ws.tm_abg, make_tile_tables(ws, false), e->num_sms, st);
+    if (ws.v3) tc3::profile_edge_v3(gm, ea, w.W2_v3, ws.tm_abg, make_tile_tables(ws, false), e->num_sms, st, false);
     else tc::profile_edge_tc(gm, ea, w.W2_tc, e->num_sms, st);
   }
   if (e->use_tc && getenv("DL_PROFILE_NODE")) {

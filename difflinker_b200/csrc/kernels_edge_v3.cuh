@@ -32,6 +32,7 @@ namespace tc3 {
 
 using namespace dl::tc;
 
+constexpr int PROF_SLOTS = 32;                 // u64 per CTA of the profiling variant: 16 role counters + 16 timeline marks
 constexpr int MAXR3 = 8;                       // rows per tile (A rows staged per producer-side slot)
 constexpr int NACC3 = 3;                       // TMEM accumulator stages: columns 128 + 128 a (columns 0..127 hold W2 hi | lo)
 constexpr int NPS3 = 3;                        // ring of producer-side table slots (freed by the producers)
@@ -181,9 +182,14 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
   };
   auto prof_flush = [&](int base) {
     if (PROF && lane == 0) {
-      unsigned long long* o = prof + (size_t)blockIdx.x * 16 + base;
+      unsigned long long* o = prof + (size_t)blockIdx.x * PROF_SLOTS + base;
       o[0] = pc[0]; o[1] = pc[1]; o[2] = pc[2]; o[3] = (unsigned long long)(clock64() - t_begin);
     }
+  };
+  // timeline marks (cycles since kernel entry; each costs the marking warp a global round trip -- read them as an ordering with
+  // ~1 K cycles of overhead per mark on the same warp, not as exact times)
+  auto mark = [&](int i) {
+    if (PROF && lane == 0) { unsigned long long* o = prof + (size_t)blockIdx.x * PROF_SLOTS + 16 + i; if (*o == 0) *o = (unsigned long long)(clock64() - t_begin); }
   };
 
   if (tid == 0) {
@@ -215,8 +221,12 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       // through the table warps, and everything it writes leaves after tiles have travelled the pipeline: the table warps
       // are the only ones that have to wait for the previous kernel. The prologue above and the W2 -> tensor memory copy of
       // the epilogue warps overlap the previous kernel's tail.
+      if (warp == W3_TBL) mark(0);                          // prologue done
       chain_wait();
+      if (warp == W3_TBL) mark(1);                          // previous kernel complete
       if (warp == W3_TBL && lane == 0) chain_release();
+      // (Walking the per-plan tile list for the first tile BEFORE the wait -- it does not depend on the chain -- was measured
+      // slower, 77.9 vs 75.3 us per GCL launch on the same box.)
       TileIter3 iter(tt, N);
       Tile3 cur;
       int q = -1, prev_b = -1, ps = 0, pu = 0;              // ps = t % NPS3, pu = t / NPS3
@@ -287,6 +297,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(bar);
+        if (t == 0) mark(2);                                 // first tile's copies issued
         if (!more) break;
       }
       if (warp == W3_TBL) prof_flush(0);
@@ -319,6 +330,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
           }
           umma_commit_elect(bars + B3_EMPTY + 8 * s);
           umma_commit_elect(bars + B3_TFULL + 8 * acc);
+          if (t == 0) mark(5);                               // first tile's MMAs issued
           pc[2] += 1;
           if (++acc == NACC3) { acc = 0; ++use; }
         }
@@ -346,6 +358,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
     for (int t = 0;; ++t, ps = (ps + 1 == NPS3 ? 0 : ps + 1)) {
       const int s = t & (N_STAGE - 1), slot = t & (NES - 1);
       wait_on(bars + B3_TBL + 8 * slot, (t / NES) & 1, 0);
+      if (t == 0 && warp == W3_PROD) mark(3);               // first tile's tables have landed
       const uint8_t* tb = sm + O3_PT + ps * P3_BYTES;        // producer-side slot
       const int* hdr = reinterpret_cast<const int*>(sm + O3_ET + slot * EB + E3_HDR);
       const int* dyn = reinterpret_cast<const int*>(sm + O3_ET + slot * EB + E3_DYN);
@@ -408,7 +421,8 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       }
       __syncwarp();
       if (lane == 0) { mbar_arrive(bars + B3_FULL + 8 * s); mbar_arrive(bars + B3_PFREE + 8 * ps); }
-      if (Et <= 0) break;
+      if (t == 0 && warp == W3_PROD) mark(4);               // first operand tile written
+      if (Et <= 0) { if (warp == W3_PROD) mark(8); break; }
     }
     if (warp == W3_PROD) prof_flush(4);
   } else {
@@ -435,6 +449,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bars + B3_W);
+      if (warp == W3_EPI) mark(9);                           // W2 in tensor memory
     }
     const float bias = b2s[c];
     const float2 bias2 = make_float2(bias, bias);
@@ -443,6 +458,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       const int slot = t & (NES - 1);
       wait_on(bars + B3_TBL + 8 * slot, (t / NES) & 1, 0);
       wait_on(bars + B3_TFULL + 8 * acc, use & 1, 1);
+      if (t == 0 && warp == W3_EPI) mark(6);                // first accumulator complete
       tc_fence_after();
       const uint8_t* tb = sm + O3_ET + slot * EB;
       const int* hdr = reinterpret_cast<const int*>(tb + E3_HDR);
@@ -532,6 +548,7 @@ __global__ void __launch_bounds__(32 * (W3_EPI + NEPI), 1) k_edge_v3(Geom gm, Ed
       tc_fence_before();
       __syncwarp();
       if (lane == 0) { mbar_arrive(bars + B3_TEMPTY + 8 * acc); mbar_arrive(bars + B3_TFREE + 8 * slot); }
+      if (t == 0 && warp == W3_EPI) mark(7);                // first tile's epilogue done
       if (++acc == NACC3) { acc = 0; ++use; }
       if (++rot == NG) rot = 0;
     }
@@ -687,35 +704,55 @@ inline dl_status make_panel_map(CUtensorMap* out, const float* AB, int B, int N)
 inline dl_status configure3() {
   const bool ok = cudaFuncSetAttribute(k_edge_v3<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
                   cudaFuncSetAttribute(k_edge_v3<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
+                  cudaFuncSetAttribute(k_edge_v3<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess &&
                   cudaFuncSetAttribute(k_edge_v3<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM3_BYTES) == cudaSuccess;
   return ok ? DL_OK : DL_ERR_CUDA;
 }
 
+inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt, int num_sms,
+                                 cudaStream_t st, bool coord);
+
 inline void launch_edge_v3(const Geom& gm, const EdgeArgs& ea, bool coord, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt,
                            int num_sms, cudaStream_t st) {
   const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
+  // DL_PROFILE_EDGE_LIVE=k: the launches k .. k+17 of the process (one forward's worth at L=6) run the profiling variant,
+  // each synchronised and printed -- eager Dynamics.forward only (not inside a stream capture)
+  static const int live0 = [] { const char* v = getenv("DL_PROFILE_EDGE_LIVE"); return v ? atoi(v) : -1; }();
+  static int n_launch = 0;
+  if (live0 >= 0) {
+    const int i = n_launch++;
+    if (i >= live0 && i < live0 + 18) { profile_edge_v3(gm, ea, w2_v3, tm, tt, num_sms, st, coord); return; }
+  }
   if (coord) launch_chain(k_edge_v3<false, true>, dim3(num_sms), dim3(32 * (W3_EPI + NEPI)), SMEM3_BYTES, st, gm, ea, w, tm, tt, nullptr);
   else launch_chain(k_edge_v3<false, false>, dim3(num_sms), dim3(32 * (W3_EPI + NEPI)), SMEM3_BYTES, st, gm, ea, w, tm, tt, nullptr);
 }
 
-// Debug: one profiled GCL launch (clock64 accounting per role: wait vs total cycles), averaged over the CTAs, to stderr.
+// Debug: one profiled launch (clock64 accounting per role: wait vs total cycles, and a timeline of the first tile), averaged
+// over the CTAs, to stderr. Synchronises the stream: eager calls only.
 inline dl_status profile_edge_v3(const Geom& gm, const EdgeArgs& ea, const void* w2_v3, const CUtensorMap& tm, const TileTables& tt, int num_sms,
-                                 cudaStream_t st) {
+                                 cudaStream_t st, bool coord) {
   unsigned long long* d = nullptr;
-  if (cudaMalloc(&d, (size_t)num_sms * 16 * 8) != cudaSuccess) return DL_ERR_CUDA;
-  cudaMemsetAsync(d, 0, (size_t)num_sms * 16 * 8, st);
-  k_edge_v3<true, false><<<num_sms, 32 * (W3_EPI + NEPI), SMEM3_BYTES, st>>>(gm, ea, reinterpret_cast<const uint32_t*>(w2_v3), tm, tt, d);
+  if (cudaMalloc(&d, (size_t)num_sms * PROF_SLOTS * 8) != cudaSuccess) return DL_ERR_CUDA;
+  cudaMemsetAsync(d, 0, (size_t)num_sms * PROF_SLOTS * 8, st);
+  const uint32_t* w = reinterpret_cast<const uint32_t*>(w2_v3);
+  if (coord) launch_chain(k_edge_v3<true, true>, dim3(num_sms), dim3(32 * (W3_EPI + NEPI)), SMEM3_BYTES, st, gm, ea, w, tm, tt, d);
+  else launch_chain(k_edge_v3<true, false>, dim3(num_sms), dim3(32 * (W3_EPI + NEPI)), SMEM3_BYTES, st, gm, ea, w, tm, tt, d);
   if (cudaStreamSynchronize(st) != cudaSuccess) { cudaFree(d); return DL_ERR_CUDA; }
-  std::vector<unsigned long long> h((size_t)num_sms * 16);
+  std::vector<unsigned long long> h((size_t)num_sms * PROF_SLOTS);
   cudaMemcpy(h.data(), d, h.size() * 8, cudaMemcpyDeviceToHost);
   cudaFree(d);
-  double avg[16] = {0};
-  for (int b = 0; b < num_sms; ++b) for (int i = 0; i < 16; ++i) avg[i] += (double)h[(size_t)b * 16 + i] / num_sms;
-  fprintf(stderr, "[dl prof v3] cycles per CTA (avg over %d), tiles %.1f\n", num_sms, avg[10]);
-  fprintf(stderr, "[dl prof v3]  table   : wait tfree %.0f, wait pempty %.0f, wait pfree %.0f | total %.0f\n", avg[0], avg[1], avg[2], avg[3]);
-  fprintf(stderr, "[dl prof v3]  producer: wait tbl %.0f, wait empty %.0f, wait panel %.0f | total %.0f\n", avg[4], avg[5], avg[6], avg[7]);
-  fprintf(stderr, "[dl prof v3]  mma     : wait full %.0f, wait tempty %.0f | total %.0f\n", avg[8], avg[9], avg[11]);
-  fprintf(stderr, "[dl prof v3]  epilogue: wait tbl %.0f, wait tfull %.0f | total %.0f\n", avg[12], avg[13], avg[15]);
+  double avg[PROF_SLOTS] = {0}, mx[PROF_SLOTS] = {0};
+  for (int b = 0; b < num_sms; ++b)
+    for (int i = 0; i < PROF_SLOTS; ++i) { const double v = (double)h[(size_t)b * PROF_SLOTS + i]; avg[i] += v / num_sms; mx[i] = std::max(mx[i], v); }
+  const char* k = coord ? "COORD" : "GCL";
+  fprintf(stderr, "[dl prof v3 %s] cycles per CTA (avg over %d), tiles %.1f (max %.0f)\n", k, num_sms, avg[10], mx[10]);
+  fprintf(stderr, "[dl prof v3 %s]  table   : wait tfree %.0f, wait pempty %.0f, wait pfree %.0f | total %.0f\n", k, avg[0], avg[1], avg[2], avg[3]);
+  fprintf(stderr, "[dl prof v3 %s]  producer: wait tbl %.0f, wait empty %.0f, wait panel %.0f | total %.0f\n", k, avg[4], avg[5], avg[6], avg[7]);
+  fprintf(stderr, "[dl prof v3 %s]  mma     : wait full %.0f, wait tempty %.0f | total %.0f\n", k, avg[8], avg[9], avg[11]);
+  fprintf(stderr, "[dl prof v3 %s]  epilogue: wait tbl %.0f, wait tfull %.0f | total %.0f (max %.0f)\n", k, avg[12], avg[13], avg[15], mx[15]);
+  fprintf(stderr, "[dl prof v3 %s]  timeline: prologue %.0f | chain wait over %.0f | copies of tile 0 issued %.0f | tables landed %.0f | operand tile 0 %.0f | "
+                  "MMAs of tile 0 issued %.0f | W2 in TMEM %.0f | accumulator 0 complete %.0f | epilogue of tile 0 done %.0f | producers done %.0f\n",
+          k, avg[16], avg[17], avg[18], avg[19], avg[20], avg[21], avg[25], avg[22], avg[23], avg[24]);
   return DL_OK;
 }
 

@@ -87,6 +87,14 @@ if os.path.isfile(lp):
         rc = os.path.join(src, "role_cycles.txt")
         if os.path.isfile(rc):
             f.write("\n## per-role cycle accounting (clock64 inside the kernels: DL_PROFILE_EDGE / DL_PROFILE_NODE)\n\n```\n" + open(rc).read() + "```\n")
+        pl = os.path.join(src, "prof_live.txt")
+        if os.path.isfile(pl):
+            lines = open(pl).read().splitlines()
+            coord = [l for l in lines if "COORD]" in l][:6]
+            gcl = [l for l in lines if "GCL]" in l][6:12]
+            f.write("\n## one eager forward, every edge launch profiled (DL_PROFILE_EDGE_LIVE: per-role cycles and the timeline of the first tile;\n"
+                    "synchronised launches, so no overlap with the previous kernel; every timeline mark costs the marking warp a global round trip --\n"
+                    "read it as an ordering with ~1 K cycles of overhead per mark on the same warp)\n\n```\n" + "\n".join(gcl + coord) + "\n```\n")
     print(open(os.path.join(here, f"{tag}_launches.md")).read())
 
 # ---- full captures ---------------------------------------------------------------------------------------------
