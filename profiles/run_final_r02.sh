@@ -19,6 +19,7 @@ done
 DL_TIME_KERNELS=1 python profiles/time_kernels.py cfg2_zinc 20 2>&1 | grep "dl times" > $O/live_kernel_times.txt
 DL_PROFILE_EDGE=1 DL_PROFILE_NODE=1 python bench.py --steps 1 --warmup 1 --T 20 --no-e2e --no-cpu-baseline 2>&1 >/dev/null | grep "dl prof" > $O/role_cycles.txt
 DL_PROFILE_EDGE_LIVE=72 DL_TIME_KERNELS=0 python profiles/time_kernels.py cfg2_zinc 6 2>&1 | grep "dl prof v3" > $O/prof_live.txt
+timeout 900 compute-sanitizer --tool memcheck python profiles/sanitize.py 2>&1 | grep -v "^=========\s*$" | tail -12 > $O/sanitizer_memcheck.txt
 # launch list: kernels of the bench command (T shortened so that the capture window covers whole forwards)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:k_ -s 150 -c 240 --csv \
   --log-file $O/launches.csv python bench.py --steps 1 --warmup 1 --T 10 --no-e2e --no-cpu-baseline > $O/launches.log 2>&1

@@ -166,3 +166,14 @@ if os.path.isfile(rep):
         json.dump({"note": f"dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/{tag}_ncu_summary.md (ncu --set full, cold caches)",
                    "cfg2_zinc": {"edge_gcl": traffic.get("GCL"), "edge_coord": traffic.get("COORD"), "node": traffic.get("node")}},
                   open(os.path.join(here, "ncu_traffic.json"), "w"))
+
+# ---- compute-sanitizer -------------------------------------------------------------------------------------------
+sm = os.path.join(src, "sanitizer_memcheck.txt")
+if os.path.isfile(sm):
+    with open(os.path.join(here, f"{tag}_sanitizer.md"), "w") as f:
+        f.write(f"# compute-sanitizer memcheck ({tag} build)\n\n`compute-sanitizer --tool memcheck python profiles/sanitize.py` on a B200 -- one small call of every native\n"
+                "entry point: FC chain through the public `DDPM.sample_chain` (third-generation edge kernels, tile tables, device-side Philox noise,\n"
+                "programmatic dependent launches inside the captured graph), InpaintingEDM chain, N=150 forward (second-generation kernels), cut-off graph forward,\n"
+                "size classifier, bond orders, frame restore.\n\n```\n" + open(sm).read() + "```\n")
+    print(open(os.path.join(here, f"{tag}_sanitizer.md")).read())
+
