@@ -55,8 +55,11 @@ def measured_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line, every 200 ms).
+    The process is started BEFORE the warm-up steps -- NVML initialisation inside the timed region stalls command submission --
+    and every sample carries nvidia-smi's own timestamp; `stop()` keeps the samples taken between `mark_begin()` and
+    `mark_end()` (wall clock; both are called next to the CUDA events that bracket the timed steps)."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
@@ -64,15 +67,23 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.path = None
+        self.t_begin = self.t_end = None
 
     def start(self):
-        if shutil.which("nvidia-smi") is None:
+        if shutil.which("nvidia-smi") is None or os.environ.get("BENCH_NO_CLOCKS"):      # the switch is for diagnosing the sampler itself
             return
         fd, self.path = tempfile.mkstemp(suffix=".csv")
         os.close(fd)
         self.out = open(self.path, "w")
         self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu), "-lms", "100"], stdout=self.out, stderr=subprocess.DEVNULL)
+                                      "-i", str(self.gpu), "-lms", os.environ.get("BENCH_CLOCKS_MS", "200")],
+                                     stdout=self.out, stderr=subprocess.DEVNULL)
+
+    def mark_begin(self):
+        self.t_begin = time.time()
+
+    def mark_end(self):
+        self.t_end = time.time()
 
     def stop(self):
         if self.proc is None:
@@ -83,24 +94,31 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         self.out.close()
-        sm, mx, reasons = [], [], set()
+        import datetime
+        sm, mx, reasons, n_all = [], [], set(), 0
         with open(self.path) as f:
             for line in f:
                 parts = [p.strip() for p in line.split(",")]
-                if len(parts) < 8:
+                if len(parts) < 9:
                     continue
                 try:
-                    sm.append(float(parts[1])); mx.append(float(parts[2]))
+                    ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                    clk, cmax = float(parts[2]), float(parts[3])
                 except ValueError:
                     continue
-                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[4:8]):
+                n_all += 1
+                if self.t_begin is not None and not (self.t_begin - 0.05 <= ts <= (self.t_end or time.time()) + 0.05):
+                    continue
+                sm.append(clk); mx.append(cmax)
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], parts[5:9]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
         os.unlink(self.path)
         if not sm:
             return None
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "samples_outside_timed_region": n_all - len(sm)}
 
 
 def cpu_reference_step(fwd, sample):
@@ -294,23 +312,26 @@ def main():
     else:
         resident = [resident_inputs(b) for b in host_batches]
     torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()                                                      # before the warm-up: see ClockSampler
+    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for i in range(args.warmup):
+        l2_flush.zero_()
         edm.sample_chain(**resident[i], keep_frames=1)
     eng = edm.dynamics.engine(local_rank)
-    sampler = ClockSampler(local_rank)
     barrier()
     launches0 = lib.dl_launch_count(eng)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sampler.mark_begin()
     ev0.record()
     loop_ms = []
-    l2_flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     for i in range(args.steps):
         l2_flush.zero_()                                                 # larger than the 126 MB L2
         chain = edm.sample_chain(**resident[args.warmup + i], keep_frames=1)
         loop_ms.append(edm.last_loop_ms)
     ev1.record()
     barrier()
+    sampler.mark_end()
     clocks = sampler.stop()
     launches = lib.dl_launch_count(eng) - launches0
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))

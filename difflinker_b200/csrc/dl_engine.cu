@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <map>
 #include <string>
 #include <vector>
@@ -900,6 +901,11 @@ static dl_status sample_chain_impl(dl_engine* e, int32_t sampler, int32_t B, int
   CK(cudaSetDevice(e->cfg.device));
   cudaStream_t user = reinterpret_cast<cudaStream_t>(stream);
   cudaStream_t st = e->loop_stream;
+  // DL_TIME_CHAIN=1: host-clock breakdown of one call to stderr (adds stream synchronisations: diagnostic only)
+  static const bool time_chain = getenv("DL_TIME_CHAIN") != nullptr;
+  auto now_ms = [] { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6; };
+  const double tc0 = time_chain ? now_ms() : 0.0;
+  double tc_plan = 0, tc_capture = 0, tc_inst = 0, tc_launch = 0;
   if ((s = ensure_workspace(e, B, N)) != DL_OK) return s;
   if (e->coef_cap < T + 1) {
     if (e->coef_dev) cudaFree(e->coef_dev);
@@ -929,6 +935,7 @@ static dl_status sample_chain_impl(dl_engine* e, int32_t sampler, int32_t B, int
   // inpainting: the dynamics see linker_mask=None (edm.py:632), so every live row gets a coordinate update
   if ((s = build_plan(e, B, N, node_mask, inpaint ? nullptr : linker_mask, edge_mask, st)) != DL_OK) return s;
 
+  if (time_chain) { cudaStreamSynchronize(st); tc_plan = now_ms(); }
   FwdIO io;
   io.sampler = true; io.inpaint = inpaint; io.xh0 = xh; io.upd_linker_mask = linker_mask;
   io.node_mask = node_mask; io.linker_mask = inpaint ? nullptr : linker_mask; io.edge_mask = edge_mask;
@@ -948,7 +955,9 @@ static dl_status sample_chain_impl(dl_engine* e, int32_t sampler, int32_t B, int
   const int64_t per_step = e->launches - before;
   // every exit below releases the captured graph and its executable (destruction is deferred by the runtime until the
   // launched work has finished)
+  if (time_chain) tc_capture = now_ms();
   cudaError_t ge = cudaGraphInstantiate(&exec, graph, 0);
+  if (time_chain) tc_inst = now_ms();
   if (ge == cudaSuccess) ge = cudaEventRecord(e->ev_t0, st);
   int failed_step = -1;
   for (int r = 0; ge == cudaSuccess && r <= T; ++r) {
@@ -956,6 +965,14 @@ static dl_status sample_chain_impl(dl_engine* e, int32_t sampler, int32_t B, int
     if (ge != cudaSuccess) failed_step = r;
   }
   if (ge == cudaSuccess) ge = cudaEventRecord(e->ev_t1, st);
+  if (time_chain) {
+    tc_launch = now_ms();
+    cudaStreamSynchronize(st);
+    const double tc_done = now_ms();
+    float loop = 0.f; cudaEventElapsedTime(&loop, e->ev_t0, e->ev_t1);
+    fprintf(stderr, "[dl chain] setup+plan %.2f ms | capture %.2f | instantiate %.2f | %d graph launches enqueued in %.2f | wait for the GPU %.2f | device loop %.2f\n",
+            tc_plan - tc0, tc_capture - tc_plan, tc_inst - tc_capture, T + 1, tc_launch - tc_inst, tc_done - tc_launch, loop);
+  }
   if (ge == cudaSuccess && user != st) {
     ge = cudaEventRecord(e->ev_out, st);
     if (ge == cudaSuccess) ge = cudaStreamWaitEvent(user, e->ev_out, 0);
