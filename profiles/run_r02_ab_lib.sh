@@ -23,6 +23,6 @@ for which in prev cur; do
   echo "== live kernel times, $which"
   DL_TIME_KERNELS=1 python profiles/time_kernels.py cfg2_zinc 20 2>&1 | grep "dl times" | grep "edge\|tiles"
 done
-DL_PROFILE_EDGE_LIVE=72 DL_TIME_KERNELS=0 python profiles/time_kernels.py cfg2_zinc 6 2>&1 | grep "dl prof v3" > gpurun_out/prof_live.txt
-grep "COORD" gpurun_out/prof_live.txt | head -6
-grep "GCL" gpurun_out/prof_live.txt | sed -n 7,12p
+
+
+
