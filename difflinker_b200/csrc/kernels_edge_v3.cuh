@@ -17,7 +17,13 @@
 //     roles are dependency-latency bound per warp, so the split is chosen to balance them (measured: 8 epilogue warps
 //     with deeper software pipelining per warp were 35 % slower);
 //   * the producer-side and epilogue-side table slots are separate rings (3 and 8 deep) so the table warps run as far
-//     ahead of the epilogue as the epilogue-side ring allows instead of being throttled by the slowest consumer.
+//     ahead of the epilogue as the epilogue-side ring allows instead of being throttled by the slowest consumer;
+//   * the producer work of a tile is ceil(Et / 8) warp-tasks, dealt round-robin to the 16 producer warps ACROSS tiles (a
+//     15-task tile of 3 x 40 edges leaves one warp free to start on the next tile, the short last tile of a molecule
+//     occupies 5 warps instead of 16);
+//   * launched with programmatic stream serialization (common.cuh launch_chain): barrier init, TMEM allocation and the
+//     W2 -> tensor memory copy run while the previous kernel of the forward drains; only the table warps -- the one role
+//     that reads what other kernels produce -- execute griddepcontrol.wait.
 //
 // K permutation: producer thread kc owns channels {4kc..4kc+3} u {64+4kc..64+4kc+3} (two conflict-free 16-byte reads of
 // a 512-byte panel row per half-warp) and writes them as operand positions 8kc..8kc+7; W2 is packed with the same
