@@ -3,6 +3,12 @@
 Usage: python profiles/summarize_r02.py [gpurun_out/final_r02] [tag]"""
 import csv, glob, io, json, os, re, subprocess, sys
 
+def edge_kind(kn):
+    """'GCL' / 'COORD' from the last template argument of k_edge_v3<PROF, COORD> (ncu prints `<0, 1>` or `<(bool)0, (bool)1>`)."""
+    m = re.search(r"k_edge_v3<([^>]*)>", kn)
+    last = m.group(1).split(",")[-1].replace("(bool)", "").strip() if m else "0"
+    return "COORD" if last in ("1", "true") else "GCL"
+
 src = sys.argv[1] if len(sys.argv) > 1 else "gpurun_out/final_r02"
 tag = sys.argv[2] if len(sys.argv) > 2 else "r02"
 here = os.path.dirname(os.path.abspath(__file__))
@@ -68,7 +74,7 @@ if os.path.isfile(lp):
         us = v / 1e3 if r[ui] in ("ns", "nsecond") else (v if r[ui] in ("us", "usecond") else v * 1e3)
         name = re.sub(r"\(.*", "", r[ki]).replace("dl::", "")
         if "k_edge_v3" in r[ki]:
-            name += " COORD" if ", 1>" in r[ki] or ",1>" in r[ki] else " GCL"
+            name += " " + edge_kind(r[ki])
         a = agg.setdefault(name, [0, 0.0])
         a[0] += 1; a[1] += us
     tot = sum(a[1] for a in agg.values())
@@ -114,7 +120,7 @@ if os.path.isfile(rep):
     for r in rws[2:]:
         d = dict(zip(hdr, r))
         kn = d['Kernel Name']
-        key = ("COORD" if "12, 1>" in kn else "GCL") if "k_edge_v3" in kn else "node"
+        key = edge_kind(kn) if "k_edge_v3" in kn else "node"
         if key in seen:
             continue
         seen.add(key)
@@ -136,7 +142,7 @@ if os.path.isfile(rep):
     done = set()
     for si, st in enumerate(starts):
         kn = rs[st][1]
-        key = ("COORD" if "1>(" in kn.replace("(bool)1>", "1>").replace("(bool)", "") and "k_edge_v3" in kn and "(bool)1>" in kn else "GCL") if "k_edge_v3" in kn else "node"
+        key = edge_kind(kn) if "k_edge_v3" in kn else "node"
         if key in done:
             continue
         done.add(key)
