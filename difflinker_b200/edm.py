@@ -249,7 +249,8 @@ class InpaintingEDM(EDM):
             sigma_s, sigma_t, alpha_s = self.sigma(g_s), self.sigma(g_t), self.alpha(g_s)
             rows[r].qa = float((alpha_ts * (sigma_s ** 2) / (sigma_t ** 2))[0])      # edm.py:661-664
             rows[r].qb = float((alpha_s * sigma2_ts / (sigma_t ** 2))[0])
-            # the chain frame is written after the COM projection by the per-molecule kernel: frame 0 is live too
+            # the chain frame is written after the COM projection by the per-molecule kernel; frame 0 is left to the final
+            # step, which overwrites chain[0] with the sampled x, h (edm.py:716-725) -- hence `frame > 0`
             frame = (s * keep_frames) // T
             last_writer = (s == 0 or ((s - 1) * keep_frames) // T != frame) and frame > 0
             rows[r].frame = frame if last_writer else -1
