@@ -370,6 +370,33 @@ def test_bench_reference_arm_contract_on_cpu():
     assert d["e2e"]["value"] == d["value"] and d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
 
 
+def test_bench_clock_sampler_keeps_the_samples_of_the_timed_region(tmp_path):
+    """bench.py's nvidia-smi sampler runs from before the warm-up; `stop()` must report only the samples whose timestamps fall
+    between mark_begin() and mark_end() (the timed steps), and the throttle reasons seen there."""
+    import datetime, importlib.util, time
+    spec_ = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec_)
+    spec_.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    t0 = time.time()
+    fmt = lambda t: datetime.datetime.fromtimestamp(t).strftime("%Y/%m/%d %H:%M:%S.%f")[:-3]
+    rows = [(t0 - 3.0, 1200, "Not Active", "Not Active"), (t0 - 2.8, 1300, "Not Active", "Active"),      # warm-up: ignored
+            (t0 + 0.1, 1965, "Not Active", "Not Active"), (t0 + 0.3, 1950, "Not Active", "Active"),
+            (t0 + 0.5, 1965, "Not Active", "Not Active"), (t0 + 5.0, 900, "Active", "Not Active")]       # after the end: ignored
+    path = tmp_path / "clocks.csv"
+    path.write_text("".join(f"{fmt(t)}, 0, {clk}, 1965, 700.00, {hw}, Not Active, Not Active, {cap}\n" for t, clk, hw, cap in rows)
+                    + "garbage line\n")
+
+    class Done:
+        def terminate(self): pass
+        def wait(self, timeout=None): return 0
+    s.proc, s.path, s.out = Done(), str(path), open(os.devnull, "w")
+    s.t_begin, s.t_end = t0, t0 + 1.0
+    got = s.stop()
+    assert got == {"sm_mhz": 1965.0, "sm_max_mhz": 1965.0, "reasons": ["sw_power_cap"], "samples": 3, "samples_outside_timed_region": 3}
+    assert not path.exists()
+
+
 def test_load_from_checkpoint_reads_lightning_checkpoints(tmp_path):
     """generate.py:101 / :88 -- `DDPM.load_from_checkpoint(path, map_location)` and `SizeClassifier.load_from_checkpoint`
     on the Lightning checkpoint layout ({'hyper_parameters', 'state_dict', ...}), strict key match, overrides as kwargs."""
