@@ -1,8 +1,8 @@
 #!/bin/bash
-# A/B within one box of two builds: the in-tree library against profiles/ab/lib_new.so (built from an earlier commit)
+# A/B within one box: the in-tree library (cur) against every experimental build profiles/ab/lib_*.so (git-ignored, built by hand
+# from a patched copy of csrc/): forward parity tests on each, then graph-replayed forward + isolated GCL time, twice, alternating.
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "not T500" 2>&1 | tail -3
 cp difflinker_b200/libdifflinker_b200.so /tmp/lib_cur.so
 one() {
   timeout 300 python bench.py --steps 3 --warmup 3 --T 100 --no-e2e --no-cpu-baseline "${@:2}" > gpurun_out/abl.json 2> gpurun_out/abl.err
@@ -12,17 +12,14 @@ d=json.loads(open("gpurun_out/abl.json").read().strip().splitlines()[-1])
 print("$1 ${@:2} fwd_ms", round(d["forward"]["ms"],4), "gcl_ms", round(d["roofline"]["kernel_ms"],5), "parity", d["parity"]["rel_err"])
 PY
 }
+for lib in profiles/ab/lib_*.so; do
+  cp $lib difflinker_b200/libdifflinker_b200.so
+  echo "== $lib: $(timeout 600 python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k 'golden and not T500 or config_shapes or odd or sweep or nan' 2>&1 | tail -1)"
+done
 for rep in 1 2; do
-  cp profiles/ab/lib_new.so difflinker_b200/libdifflinker_b200.so; one new
   cp /tmp/lib_cur.so difflinker_b200/libdifflinker_b200.so; one cur
+  for lib in profiles/ab/lib_*.so; do cp $lib difflinker_b200/libdifflinker_b200.so; one $(basename $lib .so); done
 done
-cp profiles/ab/lib_new.so difflinker_b200/libdifflinker_b200.so; one new --workload cfg3_geom
 cp /tmp/lib_cur.so difflinker_b200/libdifflinker_b200.so; one cur --workload cfg3_geom
-for which in new cur; do
-  if [ $which = new ]; then cp profiles/ab/lib_new.so difflinker_b200/libdifflinker_b200.so; else cp /tmp/lib_cur.so difflinker_b200/libdifflinker_b200.so; fi
-  echo "== live kernel times, $which"
-  DL_TIME_KERNELS=1 python profiles/time_kernels.py cfg2_zinc 20 2>&1 | grep "dl times" | grep "edge\|tiles"
-done
-
-
-
+for lib in profiles/ab/lib_*.so; do cp $lib difflinker_b200/libdifflinker_b200.so; one $(basename $lib .so) --workload cfg3_geom; done
+cp /tmp/lib_cur.so difflinker_b200/libdifflinker_b200.so
