@@ -129,3 +129,20 @@ def random_latent(batch, seed, pad_garbage=True):
         z = z + 3.0 * torch.randn(z.shape, generator=g) * (1 - batch['atom_mask'].float())
     t = torch.rand((z.shape[0], 1), generator=g)
     return z, t
+
+
+def build_c_example(out_dir):
+    """gcc build of examples/c_sampler.c against the in-tree library and the CUDA runtime; returns the binary's path."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib_dir = os.path.join(root, "difflinker_b200")
+    cuda = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    exe = os.path.join(str(out_dir), "c_sampler")
+    cmd = ["gcc", "-std=c99", "-O2", "-Wall", "-Wextra", os.path.join(root, "examples", "c_sampler.c"), "-I" + os.path.join(root, "include"),
+           "-I" + os.path.join(cuda, "include"), "-L" + lib_dir, "-ldifflinker_b200", "-L" + os.path.join(cuda, "lib64"), "-lcudart",
+           "-Wl,-rpath," + lib_dir, "-Wl,-rpath," + os.path.join(cuda, "lib64"), "-o", exe]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr[-3000:]
+    assert "warning" not in res.stderr.replace("ISO C99 doesn", ""), res.stderr[-3000:]
+    return exe
+

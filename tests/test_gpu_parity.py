@@ -21,6 +21,7 @@ IMPLS = ["simt", "auto"]
 
 def dev():
     assert torch.cuda.is_available()
+    torch.cuda.init()               # torch.cuda.default_generators is empty until torch's own lazy CUDA initialisation has run
     return torch.device("cuda", 0)
 
 
@@ -683,6 +684,37 @@ def test_sampler_with_device_side_noise_equals_sampler_fed_the_torch_tensor():
     chain_ten, _ = ddpm.sample_chain(data, keep_frames=3)
     assert torch.cuda.default_generators[d.index or 0].get_offset() == end_dev
     assert torch.equal(chain_dev, chain_ten)
+
+
+def test_plain_c_caller_samples_the_chain_the_python_entry_produces(tmp_path):
+    """the boundary is a C-ABI. examples/c_sampler.c -- C99, no Python, no torch, no noise tensor -- creates the engine,
+    loads the weights under the reference's state_dict names, and samples with `dl_sample_chain_rng` from a Philox (seed, offset)
+    pair; its chain equals, bit for bit, what `EDM.sample_chain` returns in Python for a torch generator in that state (which in turn
+    is the reference's torch.randn call sequence, see the tests above), and it reports the same generator advance."""
+    import subprocess
+    from difflinker_b200 import export_job
+    from difflinker_b200.ddpm import sampler_inputs
+    spec = synthetic.SPECS["cfg2_zinc_ragged"]
+    ddpm, hp = helpers.build_ddpm(spec, 0)
+    ddpm.edm.T = 25
+    d = dev()
+    ddpm = ddpm.to(d)
+    data = {k: (v.to(d) if torch.is_tensor(v) else v) for k, v in collate(synthetic.make_items(spec, batch=6)).items()}
+    kw = sampler_inputs(ddpm, data)
+    seed = 20240607
+    torch.manual_seed(seed)
+    gen = torch.cuda.default_generators[d.index or 0]
+    off0 = gen.get_offset()
+    want = ddpm.edm.sample_chain(**kw, keep_frames=3).cpu()
+    job, out = str(tmp_path / "job.bin"), str(tmp_path / "out.bin")
+    meta = export_job.write_job(job, ddpm.edm, **kw, keep_frames=3, seed=seed, offset=off0, device_index=d.index or 0)
+    exe = helpers.build_c_example(tmp_path)
+    res = subprocess.run([exe, job, out], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, (res.stdout, res.stderr)
+    status, consumed, chain, flags = export_job.read_result(out, meta["B"], meta["N"], meta["keep_frames"], meta["xd"])
+    assert status == 0 and not flags.any()
+    assert consumed == gen.get_offset() - off0
+    assert torch.equal(chain, want)
 
 
 @pytest.mark.parametrize("world", [2, 3])

@@ -397,6 +397,30 @@ def test_bench_clock_sampler_keeps_the_samples_of_the_timed_region(tmp_path):
     assert not path.exists()
 
 
+def test_plain_c_caller_builds_and_refuses_to_run_without_a_gpu(tmp_path):
+    """examples/c_sampler.c -- a C99 program that samples through the C-ABI with device-side noise (`dl_sample_chain_rng`) from a job
+    file written by difflinker_b200/export_job.py -- compiles warning-free against include/difflinker_b200.h, links against the
+    in-tree library, and without a B200 fails loudly at dl_create (no CPU fallback). The GPU suite runs it for real."""
+    from difflinker_b200 import export_job
+    from difflinker_b200.batching import collate
+    from difflinker_b200.ddpm import sampler_inputs
+    _native.load_library()
+    spec = synthetic.SPECS["cfg1_plumbing"]
+    ddpm, hp = helpers.build_ddpm(spec, 0)
+    ddpm.edm.T = 6
+    kw = sampler_inputs(ddpm, collate(synthetic.make_items(spec)))
+    job = str(tmp_path / "job.bin")
+    meta = export_job.write_job(job, ddpm.edm, **kw, keep_frames=2, seed=1234)
+    n_w = sum(p.numel() for p in ddpm.edm.dynamics.dynamics.state_dict().values())
+    assert meta == {"B": 4, "N": 30, "T": 6, "keep_frames": 2, "xd": 3 + spec.F} and os.path.getsize(job) > 4 * n_w
+    exe = helpers.build_c_example(tmp_path)
+    res = subprocess.run([exe, job, str(tmp_path / "out.bin")], capture_output=True, text=True, timeout=300)
+    if not torch.cuda.is_available():
+        assert res.returncode == 2 and "dl_create" in res.stderr and not os.path.exists(tmp_path / "out.bin"), (res.stdout, res.stderr)
+    else:
+        assert res.returncode == 0, res.stderr
+
+
 def test_load_from_checkpoint_reads_lightning_checkpoints(tmp_path):
     """generate.py:101 / :88 -- `DDPM.load_from_checkpoint(path, map_location)` and `SizeClassifier.load_from_checkpoint`
     on the Lightning checkpoint layout ({'hyper_parameters', 'state_dict', ...}), strict key match, overrides as kwargs."""
